@@ -1,0 +1,163 @@
+/*
+ * swat_b200.h -- C-ABI of the B200-native retrieval hot path (score -> per-class top-k -> T2I walk).
+ *
+ * The reference (tian1327/SWAT) has no FFI: the path is inline Python in
+ * retrieval/sample_retrieval.py.  Every entry point below therefore cites the reference call site
+ * (file:line into /root/reference/retrieval/sample_retrieval.py) whose work it replaces; the Python
+ * mirror of the reference's functions (swat_b200/retrieval.py) binds these with ctypes and
+ * INTEGRATION.md shows the stub a SWAT maintainer would add.
+ *
+ * Conventions
+ *  - plain C linkage, pointers and sizes only; no C++/torch types cross the boundary;
+ *  - every function returns 0 on success or a negative swat_status; swat_last_error() gives a
+ *    thread-local message for the last failure on the calling thread;
+ *  - "d_" pointers are device memory on the context's device, "h_" pointers are host memory;
+ *    the caller owns every buffer it passes in; the library owns what *_create returns;
+ *  - device work is enqueued on the caller's stream (cudaStream_t passed as void*, NULL = legacy
+ *    default stream) and is asynchronous unless the comment says it synchronises;
+ *  - one swat_ctx per device; a ctx and its children are not thread-safe, distinct ctxs are;
+ *  - rows are D = 512 wide (OpenCLIP ViT-B/32 embedding size, utils/extras.py:97-114);
+ *  - result order inside a class is the reference's walk order: score descending, ties by
+ *    ascending row id (Python's stable sorted(..., reverse=True), :754, :807);
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SWAT_B200_H
+#define SWAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWAT_DIM 512
+#define SWAT_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  SWAT_OK = 0,
+  SWAT_ERR_INVALID = -1,     /* bad argument */
+  SWAT_ERR_CUDA = -2,        /* CUDA runtime / driver error (message has the CUDA error string) */
+  SWAT_ERR_NO_DEVICE = -3,   /* no CUDA device / wrong architecture (needs sm_100) */
+  SWAT_ERR_OVERFLOW = -4,    /* candidate buffers overflowed and the retry budget was exhausted */
+  SWAT_ERR_INCOMPLETE = -5,  /* T2I walk could not be proven exact within the escalation budget */
+  SWAT_ERR_UNSUPPORTED = -6  /* valid request this build cannot serve (e.g. k too large) */
+} swat_status;
+
+typedef enum { SWAT_BF16 = 0, SWAT_F32 = 1 } swat_dtype;
+
+/* per-class reduce over the query columns of one class:
+ * NONE: one query per class, the re-normalised mean prompt (:749-750, :801-802);
+ * MEAN: torch.mean over R prompt columns (:403-404, :341-342);
+ * MAX / MIN: i2i_similarity_p2p modes (:377-385); MAX is the north star's "max over synonyms". */
+typedef enum { SWAT_REDUCE_NONE = 0, SWAT_REDUCE_MEAN = 1, SWAT_REDUCE_MAX = 2, SWAT_REDUCE_MIN = 3 } swat_reduce;
+
+/* which scan kernel: AUTO = tcgen05 kernel for bf16 banks, SIMT fp32-FMA kernel for fp32 banks. */
+typedef enum { SWAT_ENGINE_AUTO = 0, SWAT_ENGINE_TC = 1, SWAT_ENGINE_SIMT = 2 } swat_engine;
+
+typedef struct swat_ctx swat_ctx;
+typedef struct swat_queries swat_queries;
+typedef struct swat_job swat_job;
+
+int32_t swat_version(void);
+const char* swat_last_error(void);
+
+/* One context per device.  Fails with SWAT_ERR_NO_DEVICE when the device is not sm_100. */
+int32_t swat_ctx_create(int32_t device, swat_ctx** out);
+int32_t swat_ctx_destroy(swat_ctx* ctx);
+/* tuning knobs (all optional): "cta_group" (1|2), "max_ctas", "cand_cap", "overfetch", "host_chunk_rows" */
+int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value);
+/* counters since ctx creation: kernels launched by this library (bench.py's gpu_launches claim) */
+int64_t swat_ctx_launch_count(const swat_ctx* ctx);
+
+/* The prompt tensors of the reference: prompt_tensors[cls]['mean'] ([512], one query per class) or
+ * ['all'] ([P_c,512], a group per class) (utils/features.py:39-64; consumed at :749-750, :801-802).
+ * h_queries: [n_queries, 512] fp32 host, rows of one class adjacent; h_class_of_query: [n_queries]
+ * dense class index 0..n_classes-1, non-decreasing (NULL = identity, needs n_queries == n_classes).
+ * Uploads an fp32 copy and a bf16 (round-to-nearest-even) copy. Synchronises. */
+int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_queries,
+                            const int32_t* h_class_of_query, int32_t n_classes, int32_t reduce,
+                            swat_queries** out);
+int32_t swat_queries_destroy(swat_queries* q);
+
+/* ---- streaming job: running per-class top-k_fetch over any number of bank views ------------- */
+/* Replaces, for all classes at once, the per-class  t2t_similarity -> sorted() -> walk  of
+ * t2t_ranked_sampler (:752-758): state = per-class threshold, histogram and candidate buffer. */
+int32_t swat_job_create(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float t2t_threshold,
+                        swat_job** out);
+int32_t swat_job_reset(swat_job* job, void* stream);
+/* Score one bank view (rows [row_base, row_base+n_rows) of the shard) against every query and fold
+ * it into the job.  d_bank: [n_rows,512] row-major, 16-byte aligned, dtype bf16|f32.
+ * d_t2i_bank (nullable): same rows of the image bank; when given, the predicate
+ * t2i >= t2i_threshold is evaluated in-pass for every row (exact for any data, 2x the bytes).
+ * d_row_class (nullable): [n_rows] dense class index of each row, -1 = none: the reference's
+ * partitioned case, a row is eligible only for its own class (transform_extracted_fea :1387-1415).
+ * d_exclude (nullable): bitmap over the view's rows, bit set = never accept
+ * (duplicates_dict / filtered_images_dict of add_to_split :454-456). */
+int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base,
+                      const void* d_t2i_bank, float t2i_threshold, const int32_t* d_row_class,
+                      const uint32_t* d_exclude, int32_t engine, void* stream);
+/* Sorted top-k_fetch of every class: d_scores [C,k_fetch] f32, d_rows [C,k_fetch] i64 (shard-local
+ * row ids as passed via row_base, -1 padded), d_counts [C] i32, d_truncated [C] i32 (nullable;
+ * 1 = more than k_fetch rows were eligible, i.e. the list is a strict prefix of the walk). */
+int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t* d_counts,
+                        int32_t* d_truncated, void* stream);
+/* Synchronises the stream the job last ran on; *overflowed = 1 if a candidate buffer overflowed
+ * (results invalid; re-run with a larger "cand_cap"). */
+int32_t swat_job_status(swat_job* job, int32_t* overflowed);
+int32_t swat_job_destroy(swat_job* job);
+
+/* ---- T2I stage: cal_t2i_similarity (:335-353) + add_t2t_ranked_t2i_tshd_to_split (:492-540) ---- */
+/* For the candidates of each class (walk order), score the image row against the class queries,
+ * keep rows with t2i >= t2i_threshold and stop at k.  d_img_bank row r is shard row
+ * img_row_base + r; with d_img_index != NULL the bank is a compact gather and candidate j of class c
+ * reads bank row d_img_index[c*k_fetch + j].  d_incomplete [C]: 1 = fewer than k accepted although
+ * the candidate list was truncated (caller must escalate k_fetch). */
+int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_bank, int32_t dtype,
+                      int64_t img_rows, int64_t img_row_base, const int64_t* d_img_index,
+                      const float* d_cand_scores, const int64_t* d_cand_rows, const int32_t* d_cand_counts,
+                      const int32_t* d_truncated, int32_t k_fetch, int32_t k, float t2i_threshold,
+                      float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts,
+                      int32_t* d_incomplete, void* stream);
+
+/* ---- multi-GPU: merge after the single NCCL gather ------------------------------ */
+/* d_scores/d_rows: [G,C,k] gathered shard results (rows already global), d_counts [G,C]. */
+int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux,
+                        const int32_t* d_counts, int32_t n_shards, int32_t n_classes, int32_t k,
+                        float* d_out_scores, int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts,
+                        void* stream);
+
+/* ---- S1 compatibility: t2t_similarity / cal_t2i_similarity (:397-416, :335-353) ---------------- */
+/* d_out [n_rows, n_classes] f32 class scores (after the reduce).  Tests and back-compat only: the
+ * fast path never materialises this matrix. */
+int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype,
+                          int64_t n_rows, float* d_out, int32_t engine, void* stream);
+
+/* ---- whole pipeline on HBM-resident banks ------------------------------------------------------ */
+/* t2t_ranked_sampler (:724-771) when d_t2i_bank == NULL, t2t_ranked_t2i_tshd_sampler (:774-825)
+ * otherwise, for all classes at once.  Outputs [C,k] (d_out_t2i nullable), rows are
+ * row_offset + local row.  Handles candidate-buffer overflow and T2I over-fetch escalation
+ * internally (falls back to the exact in-pass predicate).  Synchronises. */
+int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, const void* d_t2i_bank,
+                  int32_t dtype, int64_t n_rows, int64_t row_offset, int32_t k, float t2t_threshold,
+                  float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude,
+                  float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts,
+                  void* stream);
+
+/* ---- whole pipeline on HOST banks (the reference's torch.load'ed CPU tensors, :1473-1476) ------ */
+/* Streams the caption bank host->device in chunks overlapped with the scan, gathers only the
+ * candidates' image rows for the T2I stage, returns results in host memory.  Pinned host memory
+ * gives full PCIe rate.  Synchronises. */
+int32_t swat_topk_host(swat_ctx* ctx, const swat_queries* q, const void* h_t2t_bank, const void* h_t2i_bank,
+                       int32_t dtype, int64_t n_rows, int64_t row_offset, int32_t k, float t2t_threshold,
+                       float t2i_threshold, const int32_t* h_row_class, const uint32_t* h_exclude,
+                       float* h_out_scores, int64_t* h_out_rows, float* h_out_t2i, int32_t* h_out_counts);
+
+/* timing of the last swat_topk / swat_topk_host on this ctx, CUDA-event milliseconds:
+ * [0] scan kernels, [1] select, [2] T2I stage, [3] whole call; plus [4] scan launches,
+ * [5] H2D bytes, [6] D2H bytes, [7] escalation rounds. */
+int32_t swat_ctx_last_timing(const swat_ctx* ctx, double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWAT_B200_H */

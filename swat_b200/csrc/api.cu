@@ -1,0 +1,806 @@
+// C-ABI of swat_b200 (include/swat_b200.h): contexts, query sets, streaming jobs, and the two
+// whole-pipeline entry points (HBM-resident banks, host banks).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/swat_b200.h"
+#include "common.cuh"
+#include "scan_tc.h"
+
+using namespace swat;
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_OK(expr)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(SWAT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define SW_OK(expr)              \
+  do {                           \
+    int32_t r__ = (expr);        \
+    if (r__ != SWAT_OK) return r__; \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);
+  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+struct DevBuf {   // grow-only device workspace
+  void* p = nullptr;
+  size_t cap = 0;
+  int32_t ensure(size_t bytes) {
+    if (bytes <= cap) return SWAT_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    CU_OK(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return SWAT_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct swat_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  EncodeTiledFn encode = nullptr;
+  // options
+  int cta_group = 2;
+  int max_ctas = 0;
+  int64_t cand_cap = 0;       // 0 = auto
+  int overfetch = 0;          // 0 = auto
+  int64_t host_chunk_rows = 1 << 18;
+  // stats
+  int64_t launches = 0;
+  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // workspaces for the whole-pipeline calls
+  DevBuf w_scores, w_rows, w_counts, w_trunc, w_t2i, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
+  DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts;
+  cudaStream_t copy_stream = nullptr, work_stream = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_used[3] = {nullptr, nullptr, nullptr};
+  void* h_pinned = nullptr;
+  size_t h_pinned_cap = 0;
+};
+
+struct swat_queries {
+  swat_ctx* ctx = nullptr;
+  int Q = 0, C = 0, reduce = 0;
+  std::vector<int32_t> class_begin;   // [C+1]
+  // unpadded (T2I re-score) and padded-by-Q-block (scan kernels) device copies
+  float* d_q_f32 = nullptr; uint16_t* d_q_bf16 = nullptr; int32_t* d_class_begin = nullptr;
+  float* d_qp_f32 = nullptr; uint16_t* d_qp_bf16 = nullptr; int32_t* d_col_class = nullptr; float* d_col_count = nullptr;
+  int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
+  CUtensorMap tm_q;
+};
+
+struct swat_job {
+  swat_ctx* ctx = nullptr;
+  const swat_queries* q = nullptr;
+  JobState st;
+  cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int32_t encode_2d_bf16(swat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint32_t box_rows) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SWAT_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d, rows %llu, box %u)", (int)r,
+                                     (unsigned long long)rows, box_rows);
+  return SWAT_OK;
+}
+
+// Split the Q query columns into n_qb blocks at class boundaries, every block padded to the same
+// n_blk (multiple of 16).  max_cols = what one CTA (pair) can keep resident.
+bool plan_blocks(const std::vector<int32_t>& class_begin, int max_cols, int& n_qb, int& n_blk, std::vector<int>& blk_first_class) {
+  const int C = static_cast<int>(class_begin.size()) - 1;
+  const int Q = class_begin[C];
+  for (n_qb = std::max(1, (Q + max_cols - 1) / max_cols); n_qb <= std::max(1, C); ++n_qb) {
+    blk_first_class.assign(1, 0);
+    int widest = 0, start_col = 0;
+    bool ok = true;
+    for (int b = 0, c = 0; b < n_qb; ++b) {
+      const int64_t target = (static_cast<int64_t>(b + 1) * Q + n_qb - 1) / n_qb;   // cumulative column target
+      int c_end = c;
+      while (c_end < C && (class_begin[c_end + 1] <= target || c_end == c)) ++c_end;
+      if (b == n_qb - 1) c_end = C;
+      const int cols = class_begin[c_end] - start_col;
+      if (cols > max_cols) { ok = false; break; }
+      widest = std::max(widest, cols);
+      start_col = class_begin[c_end];
+      c = c_end;
+      blk_first_class.push_back(c);
+    }
+    if (ok) {
+      n_blk = std::max(16, (widest + 15) / 16 * 16);
+      return true;
+    }
+  }
+  return false;
+}
+
+int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
+                  float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, float* dense_out,
+                  cudaStream_t stream) {
+  swat_ctx* ctx = job->ctx;
+  const swat_queries* q = job->q;
+  if (n_rows == 0) return SWAT_OK;
+  if (n_rows < 0 || row_base < 0 || row_base + n_rows > 0xFFFFFFFEll || n_rows > 0x7FFFFF00ll)
+    return fail(SWAT_ERR_INVALID, "bank view out of range: n_rows=%lld row_base=%lld (shard-local row ids are 32-bit)",
+                (long long)n_rows, (long long)row_base);
+  if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
+  if ((reinterpret_cast<uintptr_t>(d_bank) & 15) != 0) return fail(SWAT_ERR_INVALID, "bank pointer must be 16-byte aligned");
+  if (engine == SWAT_ENGINE_AUTO) engine = (dtype == SWAT_BF16 && d_t2i_bank == nullptr) ? SWAT_ENGINE_TC : SWAT_ENGINE_SIMT;
+  if (engine == SWAT_ENGINE_TC && (dtype != SWAT_BF16 || d_t2i_bank != nullptr))
+    return fail(SWAT_ERR_UNSUPPORTED, "the tcgen05 engine serves bf16 banks without the in-pass T2I predicate");
+  ScanArgs a;
+  a.st = job->st;
+  a.col_class = q->d_col_class;
+  a.col_count = q->d_col_count;
+  a.n_cols = q->n_cols;
+  a.n_rows = n_rows;
+  a.row_base = static_cast<uint32_t>(row_base);
+  a.row_class = d_row_class;
+  a.exclude = d_exclude;
+  a.t2i_thr = t2i_threshold;
+  a.dense_out = dense_out;
+  a.n_classes = q->C;
+  job->last_stream = stream;
+  if (engine == SWAT_ENGINE_TC) {
+    if (q->n_stages <= 0) return fail(SWAT_ERR_UNSUPPORTED, "query block does not fit in shared memory for the tcgen05 engine");
+    CUtensorMap tm_bank;
+    SW_OK(encode_2d_bf16(ctx, &tm_bank, d_bank, static_cast<uint64_t>(n_rows), 128));
+    TcArgs p;
+    p.s = a;
+    p.n_qb = q->n_qb;
+    p.n_blk = q->n_blk;
+    p.n_stages = q->n_stages;
+    p.smem_b_bytes = static_cast<uint32_t>(8) * (q->n_blk / q->ctas) * 128;
+    p.bank_hint = (q->n_qb == 1) ? 0x12F0000000000000ull /* evict_first: streamed once */ : 0x1000000000000000ull;
+    int grid = ctx->sm_count;
+    if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
+    grid = std::max(q->ctas, grid / q->ctas * q->ctas);
+    CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
+  } else {
+    const void* qp = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_qp_bf16) : static_cast<const void*>(q->d_qp_f32);
+    CU_OK(launch_scan_simt(a, d_bank, d_t2i_bank, qp, dtype, q->reduce, d_row_class != nullptr, dense_out != nullptr, stream));
+  }
+  ctx->launches += 1;
+  return SWAT_OK;
+}
+
+int64_t auto_cap(const swat_ctx* ctx, int k_fetch) {
+  if (ctx->cand_cap > 0) return ctx->cand_cap;
+  int64_t cap = 32768;
+  while (cap < 32ll * k_fetch) cap <<= 1;
+  return cap;
+}
+
+int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, swat_job** out) {
+  if (!ctx || !q || !out) return fail(SWAT_ERR_INVALID, "null argument");
+  if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
+  if (thr != thr) return fail(SWAT_ERR_INVALID, "threshold is NaN");
+  CU_OK(cudaSetDevice(ctx->device));
+  swat_job* j = new swat_job();
+  j->ctx = ctx;
+  j->q = q;
+  const size_t C = static_cast<size_t>(q->C);
+  JobState& st = j->st;
+  memset(&st, 0, sizeof(st));
+  st.cap = static_cast<uint32_t>(cap);
+  st.k_fetch = static_cast<uint32_t>(k_fetch);
+  st.refresh_every = static_cast<uint32_t>(std::max(32, k_fetch / 4));
+  st.thr = thr;
+  float lo = std::max(thr, -1.0f);
+  float hi = std::max(1.0f, lo + 1.0f / 64.0f);
+  if (lo >= 1.0f) hi = lo + 1.0f;
+  st.hist_lo = lo;
+  st.hist_scale = static_cast<float>(kHistBins) / (hi - lo);
+  st.hist_inv_scale = (hi - lo) / static_cast<float>(kHistBins);
+  cudaError_t e = cudaMalloc(&st.tau_enc, C * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&st.count, C * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&st.hist, C * kHistBins * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&st.cand, C * static_cast<size_t>(cap) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&st.flags, 16);
+  if (e != cudaSuccess) {
+    swat_job_destroy(j);
+    return fail(SWAT_ERR_CUDA, "job allocation failed (C=%zu, cap=%lld): %s", C, (long long)cap, cudaGetErrorString(e));
+  }
+  *out = j;
+  return SWAT_OK;
+}
+
+// describes where the banks live for the whole-pipeline calls
+struct BankSrc {
+  bool host = false;
+  const void* t2t = nullptr; const void* t2i = nullptr;
+  int dtype = 0; int64_t n_rows = 0;
+  const int32_t* row_class = nullptr; const uint32_t* exclude = nullptr;
+};
+
+size_t elem_size(int dtype) { return dtype == SWAT_BF16 ? 2 : 4; }
+
+// one pass over the whole bank, folding every view into `job`
+int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, bool dual, float t2i_thr, cudaStream_t stream) {
+  if (!b.host) {
+    const int64_t max_view = 0x40000000ll;   // TMA coordinates are int32
+    for (int64_t r0 = 0; r0 < b.n_rows; r0 += max_view) {
+      const int64_t n = std::min(max_view, b.n_rows - r0);
+      const size_t off = static_cast<size_t>(r0) * kDim * elem_size(b.dtype);
+      SW_OK(scan_view(job, static_cast<const char*>(b.t2t) + off, b.dtype, n, r0,
+                      dual ? static_cast<const char*>(b.t2i) + off : nullptr, t2i_thr,
+                      b.row_class ? b.row_class + r0 : nullptr, b.exclude ? b.exclude + r0 / 32 : nullptr, SWAT_ENGINE_AUTO,
+                      nullptr, stream));
+    }
+    return SWAT_OK;
+  }
+  // host bank: stream chunks through three device staging buffers, copies overlapped with the scan
+  const int64_t chunk = std::max<int64_t>(4096, ctx->host_chunk_rows / 32 * 32);
+  const size_t row_bytes = static_cast<size_t>(kDim) * elem_size(b.dtype);
+  const int nbuf = 3;
+  for (int i = 0; i < nbuf; ++i) {
+    SW_OK(ctx->w_stage[i].ensure(static_cast<size_t>(chunk) * row_bytes * (dual ? 2 : 1)));
+    if (b.row_class) SW_OK(ctx->w_rc[i].ensure(static_cast<size_t>(chunk) * 4));
+    if (b.exclude) SW_OK(ctx->w_ex[i].ensure(static_cast<size_t>(chunk) / 8 + 8));
+  }
+  CU_OK(cudaEventRecord(ctx->ev_used[0], stream));   // order the copy stream after prior work on `stream`
+  CU_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[0], 0));
+  int64_t i = 0;
+  for (int64_t r0 = 0; r0 < b.n_rows; r0 += chunk, ++i) {
+    const int s = static_cast<int>(i % nbuf);
+    const int64_t n = std::min(chunk, b.n_rows - r0);
+    if (i >= nbuf) CU_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_used[s], 0));
+    char* dst = ctx->w_stage[s].as<char>();
+    CU_OK(cudaMemcpyAsync(dst, static_cast<const char*>(b.t2t) + static_cast<size_t>(r0) * row_bytes, static_cast<size_t>(n) * row_bytes,
+                          cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->timing[5] += static_cast<double>(n) * row_bytes;
+    char* dst2 = nullptr;
+    if (dual) {
+      dst2 = dst + static_cast<size_t>(chunk) * row_bytes;
+      CU_OK(cudaMemcpyAsync(dst2, static_cast<const char*>(b.t2i) + static_cast<size_t>(r0) * row_bytes, static_cast<size_t>(n) * row_bytes,
+                            cudaMemcpyHostToDevice, ctx->copy_stream));
+      ctx->timing[5] += static_cast<double>(n) * row_bytes;
+    }
+    if (b.row_class) {
+      CU_OK(cudaMemcpyAsync(ctx->w_rc[s].p, b.row_class + r0, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      ctx->timing[5] += static_cast<double>(n) * 4;
+    }
+    if (b.exclude) {
+      CU_OK(cudaMemcpyAsync(ctx->w_ex[s].p, b.exclude + r0 / 32, static_cast<size_t>((n + 31) / 32) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      ctx->timing[5] += static_cast<double>((n + 31) / 32) * 4;
+    }
+    CU_OK(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
+    CU_OK(cudaStreamWaitEvent(stream, ctx->ev_copied[s], 0));
+    SW_OK(scan_view(job, dst, b.dtype, n, r0, dst2, t2i_thr, b.row_class ? ctx->w_rc[s].as<int32_t>() : nullptr,
+                    b.exclude ? ctx->w_ex[s].as<uint32_t>() : nullptr, SWAT_ENGINE_AUTO, nullptr, stream));
+    CU_OK(cudaEventRecord(ctx->ev_used[s], stream));
+  }
+  return SWAT_OK;
+}
+
+int32_t ensure_pinned(swat_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_pinned_cap) return SWAT_OK;
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0;
+  CU_OK(cudaMallocHost(&ctx->h_pinned, bytes));
+  ctx->h_pinned_cap = bytes;
+  return SWAT_OK;
+}
+
+// The whole pipeline.  Results land in d_out_* (device).  See swat_topk / swat_topk_host.
+int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
+                     float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream) {
+  if (k < 1 || k > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k must be in [1, %d], got %d", kMaxKFetch, k);
+  const int C = q->C;
+  const bool want_t2i = b.t2i != nullptr;
+  for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
+  int32_t k_fetch = k;
+  if (want_t2i) {
+    k_fetch = ctx->overfetch > 0 ? ctx->overfetch : std::max(2 * k, 1024);
+    k_fetch = std::min(std::max(k_fetch, k), kMaxKFetch);
+  }
+  int64_t cap = auto_cap(ctx, k_fetch);
+  bool dual = false;          // exact in-pass predicate fallback
+  int rounds = 0;
+  CU_OK(cudaEventRecord(ctx->ev[6], stream));
+  for (;; ++rounds) {
+    if (rounds > 12) return fail(SWAT_ERR_OVERFLOW, "retry budget exhausted (cap=%lld k_fetch=%d)", (long long)cap, k_fetch);
+    swat_job* job = nullptr;
+    SW_OK(job_create_cap(ctx, q, dual ? k : k_fetch, thr, cap, &job));
+    const int32_t kf = dual ? k : k_fetch;
+    int32_t rc = swat_job_reset(job, stream);
+    if (rc == SWAT_OK) rc = (cudaEventRecord(ctx->ev[0], stream) == cudaSuccess) ? SWAT_OK : SWAT_ERR_CUDA;
+    if (rc == SWAT_OK) rc = scan_all(ctx, job, b, dual, t2i_thr, stream);
+    if (rc == SWAT_OK) rc = (cudaEventRecord(ctx->ev[1], stream) == cudaSuccess) ? SWAT_OK : SWAT_ERR_CUDA;
+    const bool direct = !want_t2i || dual;     // select writes the final result
+    if (rc == SWAT_OK && !direct) {
+      rc = ctx->w_scores.ensure(static_cast<size_t>(C) * kf * 4);
+      if (rc == SWAT_OK) rc = ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8);
+      if (rc == SWAT_OK) rc = ctx->w_counts.ensure(static_cast<size_t>(C) * 4);
+      if (rc == SWAT_OK) rc = ctx->w_trunc.ensure(static_cast<size_t>(C) * 4);
+      if (rc == SWAT_OK) rc = ctx->w_t2i.ensure(static_cast<size_t>(C) * kf * 4);
+      if (rc == SWAT_OK) rc = ctx->w_incomplete.ensure(static_cast<size_t>(C) * 4);
+    }
+    if (rc == SWAT_OK) {
+      // resident banks: rows leave the select as global ids (row_offset + shard-local row)
+      cudaError_t se;
+      if (direct) se = launch_select(job->st, C, row_offset, d_out_scores, d_out_rows, d_out_counts, nullptr, stream);
+      else se = launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(),
+                              ctx->w_counts.as<int32_t>(), ctx->w_trunc.as<int32_t>(), stream);
+      if (se != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "select launch failed: %s", cudaGetErrorString(se));
+      job->last_stream = stream;
+      ctx->launches += 1;
+    }
+    if (rc == SWAT_OK) rc = (cudaEventRecord(ctx->ev[2], stream) == cudaSuccess) ? SWAT_OK : SWAT_ERR_CUDA;
+    int32_t overflowed = 0;
+    if (rc == SWAT_OK) rc = swat_job_status(job, &overflowed);
+    if (rc == SWAT_OK) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing[0] += ms;
+      cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing[1] += ms;
+    }
+    swat_job_destroy(job);
+    if (rc != SWAT_OK) return rc;
+    if (overflowed) {
+      if (cap >= std::max<int64_t>(b.n_rows, 1 << 16)) return fail(SWAT_ERR_OVERFLOW, "candidate buffer overflow with cap >= n_rows");
+      cap = std::min<int64_t>(cap * 4, std::max<int64_t>(b.n_rows, 1 << 16));
+      ctx->timing[7] += 1;
+      continue;
+    }
+    if (direct) {
+      if (dual && d_out_t2i) {
+        // in-pass mode proves t2i >= threshold but does not keep the value: re-score the k winners
+        SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(C) * k * 4));
+        SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
+      }
+      if (!(dual && d_out_t2i)) break;
+    }
+    // ---- T2I stage on the candidates
+    CU_OK(cudaEventRecord(ctx->ev[3], stream));
+    T2iArgs t;
+    memset(&t, 0, sizeof(t));
+    t.dtype = b.dtype;
+    t.queries = (b.dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
+    t.class_begin = q->d_class_begin;
+    t.reduce = q->reduce;
+    t.n_classes = C;
+    t.t2i_thr = direct ? -INFINITY : t2i_thr;
+    t.k = k;
+    t.k_fetch = direct ? k : kf;
+    t.cand_scores = direct ? d_out_scores : ctx->w_scores.as<float>();
+    t.cand_rows = direct ? d_out_rows : ctx->w_rows.as<int64_t>();
+    t.cand_counts = direct ? d_out_counts : ctx->w_counts.as<int32_t>();
+    t.truncated = direct ? nullptr : ctx->w_trunc.as<int32_t>();
+    t.t2i_scratch = ctx->w_t2i.as<float>();
+    SW_OK(ctx->w_out_scores.ensure(static_cast<size_t>(C) * k * 4));
+    SW_OK(ctx->w_out_rows.ensure(static_cast<size_t>(C) * k * 8));
+    SW_OK(ctx->w_out_counts.ensure(static_cast<size_t>(C) * 4));
+    SW_OK(ctx->w_incomplete.ensure(static_cast<size_t>(C) * 4));
+    // when re-scoring in place (direct) write to scratch outputs, then copy back
+    t.out_scores = direct ? ctx->w_out_scores.as<float>() : d_out_scores;
+    t.out_rows = direct ? ctx->w_out_rows.as<int64_t>() : d_out_rows;
+    t.out_t2i = d_out_t2i;
+    t.out_counts = direct ? ctx->w_out_counts.as<int32_t>() : d_out_counts;
+    t.incomplete = ctx->w_incomplete.as<int32_t>();
+    if (!b.host) {
+      t.img_bank = b.t2i;
+      t.img_rows = b.n_rows;
+      t.img_row_base = row_offset;
+      t.img_index = nullptr;
+    } else {
+      // gather only the candidates' image rows on the host, ship the compact block
+      const size_t n_slots = static_cast<size_t>(C) * t.k_fetch;
+      const size_t row_bytes = static_cast<size_t>(kDim) * elem_size(b.dtype);
+      std::vector<int64_t> h_rows(n_slots);
+      std::vector<int32_t> h_counts(C);
+      CU_OK(cudaMemcpyAsync(h_rows.data(), t.cand_rows, n_slots * 8, cudaMemcpyDeviceToHost, stream));
+      CU_OK(cudaMemcpyAsync(h_counts.data(), t.cand_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+      CU_OK(cudaStreamSynchronize(stream));
+      ctx->timing[6] += static_cast<double>(n_slots * 8 + C * 4);
+      std::vector<int64_t> h_index(n_slots, -1);
+      std::vector<int64_t> src;
+      src.reserve(n_slots);
+      for (int c = 0; c < C; ++c)
+        for (int j = 0; j < h_counts[c]; ++j) {
+          h_index[static_cast<size_t>(c) * t.k_fetch + j] = static_cast<int64_t>(src.size());
+          src.push_back(h_rows[static_cast<size_t>(c) * t.k_fetch + j] - row_offset);
+        }
+      const size_t n_src = src.size();
+      SW_OK(ensure_pinned(ctx, std::max<size_t>(n_src, 1) * row_bytes));
+      char* stage = static_cast<char*>(ctx->h_pinned);
+      const char* img = static_cast<const char*>(b.t2i);
+      const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> th;
+      for (unsigned w = 0; w < nt; ++w)
+        th.emplace_back([&, w]() {
+          for (size_t i = w; i < n_src; i += nt) memcpy(stage + i * row_bytes, img + static_cast<size_t>(src[i]) * row_bytes, row_bytes);
+        });
+      for (auto& x : th) x.join();
+      SW_OK(ctx->w_img.ensure(std::max<size_t>(n_src, 1) * row_bytes));
+      SW_OK(ctx->w_idx.ensure(n_slots * 8));
+      CU_OK(cudaMemcpyAsync(ctx->w_img.p, stage, n_src * row_bytes, cudaMemcpyHostToDevice, stream));
+      CU_OK(cudaMemcpyAsync(ctx->w_idx.p, h_index.data(), n_slots * 8, cudaMemcpyHostToDevice, stream));
+      CU_OK(cudaStreamSynchronize(stream));   // h_index is pageable and dies at scope end
+      ctx->timing[5] += static_cast<double>(n_src * row_bytes + n_slots * 8);
+      t.img_bank = ctx->w_img.p;
+      t.img_rows = static_cast<int64_t>(n_src);
+      t.img_row_base = 0;
+      t.img_index = ctx->w_idx.as<int64_t>();
+    }
+    CU_OK(launch_t2i_walk(t, stream));
+    ctx->launches += 2;
+    if (direct) {
+      CU_OK(cudaMemcpyAsync(d_out_scores, t.out_scores, static_cast<size_t>(C) * k * 4, cudaMemcpyDeviceToDevice, stream));
+      CU_OK(cudaMemcpyAsync(d_out_rows, t.out_rows, static_cast<size_t>(C) * k * 8, cudaMemcpyDeviceToDevice, stream));
+      CU_OK(cudaMemcpyAsync(d_out_counts, t.out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    CU_OK(cudaEventRecord(ctx->ev[4], stream));
+    std::vector<int32_t> inc(C, 0);
+    CU_OK(cudaMemcpyAsync(inc.data(), t.incomplete, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaStreamSynchronize(stream));
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+      ctx->timing[2] += ms;
+    }
+    if (direct) break;
+    bool any = false;
+    for (int c = 0; c < C; ++c) any = any || inc[c] != 0;
+    if (!any) break;
+    // some class ran out of candidates before k passed T2I although more rows were eligible:
+    // widen the over-fetch, then fall back to the exact in-pass predicate
+    ctx->timing[7] += 1;
+    if (k_fetch < kMaxKFetch) {
+      k_fetch = std::min(kMaxKFetch, k_fetch * 4);
+      cap = std::max(cap, auto_cap(ctx, k_fetch));
+    } else {
+      dual = true;
+    }
+  }
+  CU_OK(cudaEventRecord(ctx->ev[7], stream));
+  CU_OK(cudaStreamSynchronize(stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+  ctx->timing[3] = ms;
+  return SWAT_OK;
+}
+
+}  // namespace
+
+// ================================================================================== C-ABI
+extern "C" {
+
+int32_t swat_version(void) { return SWAT_VERSION; }
+const char* swat_last_error(void) { return g_err.c_str(); }
+
+int32_t swat_ctx_create(int32_t device, swat_ctx** out) {
+  if (!out) return fail(SWAT_ERR_INVALID, "out is null");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(SWAT_ERR_NO_DEVICE, "no CUDA device: swat_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(SWAT_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SWAT_ERR_NO_DEVICE, "device %d is sm_%d%d; swat_b200 is built for sm_100a only", device, prop.major, prop.minor);
+  CU_OK(cudaSetDevice(device));
+  swat_ctx* ctx = new swat_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return fail(SWAT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  CU_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU_OK(cudaStreamCreateWithFlags(&ctx->work_stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev) CU_OK(cudaEventCreate(&ev));
+  for (int i = 0; i < 3; ++i) {
+    CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    CU_OK(cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+  }
+  *out = ctx;
+  return SWAT_OK;
+}
+
+int32_t swat_ctx_destroy(swat_ctx* ctx) {
+  if (!ctx) return SWAT_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_t2i, &ctx->w_incomplete, &ctx->w_keys,
+                    &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
+                    &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
+                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->work_stream) cudaStreamDestroy(ctx->work_stream);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 3; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]); }
+  delete ctx;
+  return SWAT_OK;
+}
+
+int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return fail(SWAT_ERR_INVALID, "null argument");
+  const std::string n(name);
+  if (n == "cta_group") { if (value != 1 && value != 2) return fail(SWAT_ERR_INVALID, "cta_group must be 1 or 2"); ctx->cta_group = (int)value; }
+  else if (n == "max_ctas") ctx->max_ctas = static_cast<int>(value);
+  else if (n == "cand_cap") ctx->cand_cap = value;
+  else if (n == "overfetch") ctx->overfetch = static_cast<int>(value);
+  else if (n == "host_chunk_rows") ctx->host_chunk_rows = value;
+  else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
+  return SWAT_OK;
+}
+
+int64_t swat_ctx_launch_count(const swat_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t swat_ctx_last_timing(const swat_ctx* ctx, double out[8]) {
+  if (!ctx || !out) return fail(SWAT_ERR_INVALID, "null argument");
+  for (int i = 0; i < 8; ++i) out[i] = ctx->timing[i];
+  return SWAT_OK;
+}
+
+int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_queries, const int32_t* h_class_of_query,
+                            int32_t n_classes, int32_t reduce, swat_queries** out) {
+  if (!ctx || !h_queries || !out) return fail(SWAT_ERR_INVALID, "null argument");
+  if (n_queries < 1 || n_classes < 1) return fail(SWAT_ERR_INVALID, "need at least one query and one class");
+  if (reduce < SWAT_REDUCE_NONE || reduce > SWAT_REDUCE_MIN) return fail(SWAT_ERR_INVALID, "bad reduce mode %d", reduce);
+  if (!h_class_of_query && n_queries != n_classes) return fail(SWAT_ERR_INVALID, "class_of_query is required when n_queries != n_classes");
+  CU_OK(cudaSetDevice(ctx->device));
+  std::vector<int32_t> cb(n_classes + 1, 0);
+  for (int i = 0; i < n_queries; ++i) {
+    const int c = h_class_of_query ? h_class_of_query[i] : i;
+    if (c < 0 || c >= n_classes) return fail(SWAT_ERR_INVALID, "class_of_query[%d]=%d out of range", i, c);
+    if (i > 0 && c < (h_class_of_query ? h_class_of_query[i - 1] : i - 1)) return fail(SWAT_ERR_INVALID, "class_of_query must be non-decreasing (queries of one class adjacent)");
+    cb[c + 1] += 1;
+  }
+  for (int c = 0; c < n_classes; ++c) {
+    if (cb[c + 1] == 0) return fail(SWAT_ERR_INVALID, "class %d has no query", c);
+    if (reduce == SWAT_REDUCE_NONE && cb[c + 1] != 1) return fail(SWAT_ERR_INVALID, "SWAT_REDUCE_NONE needs exactly one query per class (class %d has %d)", c, cb[c + 1]);
+    cb[c + 1] += cb[c];
+  }
+  swat_queries* q = new swat_queries();
+  q->ctx = ctx; q->Q = n_queries; q->C = n_classes; q->reduce = reduce; q->class_begin = cb; q->ctas = ctx->cta_group;
+  const int max_cols = (q->ctas == 2) ? 256 : 144;
+  std::vector<int> first;
+  if (!plan_blocks(cb, max_cols, q->n_qb, q->n_blk, first)) {
+    delete q;
+    return fail(SWAT_ERR_UNSUPPORTED, "a class has more than %d queries; cannot keep it resident", max_cols);
+  }
+  q->n_cols = q->n_qb * q->n_blk;
+  q->n_stages = tc_pick_stages(q->n_blk, q->ctas, ctx->smem_optin);
+  // host staging: padded layouts
+  const size_t Q = n_queries, NC = q->n_cols;
+  std::vector<uint16_t> h_bf(Q * kDim), h_pbf(NC * kDim, 0);
+  std::vector<float> h_pf(NC * kDim, 0.0f), h_cnt(NC, 0.0f);
+  std::vector<int32_t> h_cls(NC, -1);
+  for (size_t i = 0; i < Q * kDim; ++i) h_bf[i] = f32_to_bf16_rne(h_queries[i]);
+  for (int b = 0; b < q->n_qb; ++b) {
+    int col = b * q->n_blk;
+    for (int c = first[b]; c < first[b + 1]; ++c)
+      for (int qi = cb[c]; qi < cb[c + 1]; ++qi, ++col) {
+        memcpy(&h_pf[static_cast<size_t>(col) * kDim], &h_queries[static_cast<size_t>(qi) * kDim], kDim * 4);
+        memcpy(&h_pbf[static_cast<size_t>(col) * kDim], &h_bf[static_cast<size_t>(qi) * kDim], kDim * 2);
+        h_cls[col] = c;
+        if (qi == cb[c + 1] - 1) h_cnt[col] = static_cast<float>(cb[c + 1] - cb[c]);
+      }
+  }
+  cudaError_t e = cudaMalloc(&q->d_q_f32, Q * kDim * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_q_bf16, Q * kDim * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_class_begin, (n_classes + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_qp_f32, NC * kDim * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_qp_bf16, NC * kDim * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_col_class, NC * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_col_count, NC * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_q_f32, h_queries, Q * kDim * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_q_bf16, h_bf.data(), Q * kDim * 2, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_class_begin, cb.data(), (n_classes + 1) * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_qp_f32, h_pf.data(), NC * kDim * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_qp_bf16, h_pbf.data(), NC * kDim * 2, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_col_class, h_cls.data(), NC * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_col_count, h_cnt.data(), NC * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    swat_queries_destroy(q);
+    return fail(SWAT_ERR_CUDA, "query upload failed: %s", cudaGetErrorString(e));
+  }
+  int32_t rc = encode_2d_bf16(ctx, &q->tm_q, q->d_qp_bf16, NC, static_cast<uint32_t>(q->n_blk / q->ctas));
+  if (rc != SWAT_OK) { swat_queries_destroy(q); return rc; }
+  *out = q;
+  return SWAT_OK;
+}
+
+int32_t swat_queries_destroy(swat_queries* q) {
+  if (!q) return SWAT_OK;
+  cudaSetDevice(q->ctx->device);
+  cudaFree(q->d_q_f32); cudaFree(q->d_q_bf16); cudaFree(q->d_class_begin);
+  cudaFree(q->d_qp_f32); cudaFree(q->d_qp_bf16); cudaFree(q->d_col_class); cudaFree(q->d_col_count);
+  delete q;
+  return SWAT_OK;
+}
+
+int32_t swat_job_create(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float t2t_threshold, swat_job** out) {
+  if (!ctx) return fail(SWAT_ERR_INVALID, "null ctx");
+  SW_OK(job_create_cap(ctx, q, k_fetch, t2t_threshold, auto_cap(ctx, k_fetch), out));
+  return swat_job_reset(*out, nullptr);
+}
+
+int32_t swat_job_reset(swat_job* job, void* stream) {
+  if (!job) return fail(SWAT_ERR_INVALID, "null job");
+  CU_OK(cudaSetDevice(job->ctx->device));
+  CU_OK(launch_job_reset(job->st, job->q->C, static_cast<cudaStream_t>(stream)));
+  job->last_stream = static_cast<cudaStream_t>(stream);
+  job->ctx->launches += 1;
+  return SWAT_OK;
+}
+
+int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
+                      float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, void* stream) {
+  if (!job || (!d_bank && n_rows > 0)) return fail(SWAT_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(job->ctx->device));
+  return scan_view(job, d_bank, dtype, n_rows, row_base, d_t2i_bank, t2i_threshold, d_row_class, d_exclude, engine, nullptr,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t* d_counts, int32_t* d_truncated, void* stream) {
+  if (!job || !d_scores || !d_rows || !d_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(job->ctx->device));
+  CU_OK(launch_select(job->st, job->q->C, 0, d_scores, d_rows, d_counts, d_truncated, static_cast<cudaStream_t>(stream)));
+  job->last_stream = static_cast<cudaStream_t>(stream);
+  job->ctx->launches += 1;
+  return SWAT_OK;
+}
+
+int32_t swat_job_status(swat_job* job, int32_t* overflowed) {
+  if (!job || !overflowed) return fail(SWAT_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(job->ctx->device));
+  uint32_t flags = 0;
+  CU_OK(cudaMemcpyAsync(&flags, job->st.flags, 4, cudaMemcpyDeviceToHost, job->last_stream));
+  CU_OK(cudaStreamSynchronize(job->last_stream));
+  *overflowed = (flags & 1u) ? 1 : 0;
+  return SWAT_OK;
+}
+
+int32_t swat_job_destroy(swat_job* job) {
+  if (!job) return SWAT_OK;
+  cudaSetDevice(job->ctx->device);
+  cudaFree(job->st.tau_enc); cudaFree(job->st.count); cudaFree(job->st.hist); cudaFree(job->st.cand); cudaFree(job->st.flags);
+  delete job;
+  return SWAT_OK;
+}
+
+int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_bank, int32_t dtype, int64_t img_rows,
+                      int64_t img_row_base, const int64_t* d_img_index, const float* d_cand_scores, const int64_t* d_cand_rows,
+                      const int32_t* d_cand_counts, const int32_t* d_truncated, int32_t k_fetch, int32_t k, float t2i_threshold,
+                      float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, int32_t* d_incomplete,
+                      void* stream) {
+  if (!ctx || !q || !d_img_bank || !d_cand_scores || !d_cand_rows || !d_cand_counts || !d_out_scores || !d_out_rows || !d_out_counts)
+    return fail(SWAT_ERR_INVALID, "null argument");
+  if (k_fetch < 1 || k_fetch > kMaxKFetch || k < 1 || k > k_fetch) return fail(SWAT_ERR_INVALID, "need 1 <= k <= k_fetch <= %d", kMaxKFetch);
+  CU_OK(cudaSetDevice(ctx->device));
+  SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(q->C) * k_fetch * 4));
+  T2iArgs t;
+  memset(&t, 0, sizeof(t));
+  t.img_bank = d_img_bank; t.dtype = dtype; t.img_rows = img_rows; t.img_row_base = img_row_base; t.img_index = d_img_index;
+  t.queries = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
+  t.class_begin = q->d_class_begin; t.reduce = q->reduce;
+  t.cand_scores = d_cand_scores; t.cand_rows = d_cand_rows; t.cand_counts = d_cand_counts; t.truncated = d_truncated;
+  t.k_fetch = k_fetch; t.k = k; t.t2i_thr = t2i_threshold; t.n_classes = q->C;
+  t.t2i_scratch = ctx->w_t2i.as<float>();
+  t.out_scores = d_out_scores; t.out_rows = d_out_rows; t.out_t2i = d_out_t2i; t.out_counts = d_out_counts; t.incomplete = d_incomplete;
+  CU_OK(launch_t2i_walk(t, static_cast<cudaStream_t>(stream)));
+  ctx->launches += 2;
+  return SWAT_OK;
+}
+
+int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
+                        int32_t n_shards, int32_t n_classes, int32_t k, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
+                        int32_t* d_out_counts, void* stream) {
+  if (!ctx || !d_scores || !d_rows || !d_counts || !d_out_scores || !d_out_rows || !d_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  if (n_shards < 1 || n_classes < 1 || k < 1 || k > kMaxKFetch) return fail(SWAT_ERR_INVALID, "bad merge shape G=%d C=%d k=%d", n_shards, n_classes, k);
+  CU_OK(cudaSetDevice(ctx->device));
+  SW_OK(ctx->w_keys.ensure(static_cast<size_t>(n_shards) * n_classes * k * 8));
+  CU_OK(launch_merge(d_scores, d_rows, d_aux, d_counts, n_shards, n_classes, k, ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows,
+                     d_out_aux, d_out_counts, static_cast<cudaStream_t>(stream)));
+  ctx->launches += 2;
+  return SWAT_OK;
+}
+
+int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows, float* d_out,
+                          int32_t engine, void* stream) {
+  if (!ctx || !q || !d_bank || !d_out) return fail(SWAT_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(ctx->device));
+  swat_job tmp;   // dense mode never touches job state
+  tmp.ctx = ctx; tmp.q = q;
+  memset(&tmp.st, 0, sizeof(tmp.st));
+  return scan_view(&tmp, d_bank, dtype, n_rows, 0, nullptr, 0.0f, nullptr, nullptr, engine, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, const void* d_t2i_bank, int32_t dtype, int64_t n_rows,
+                  int64_t row_offset, int32_t k, float t2t_threshold, float t2i_threshold, const int32_t* d_row_class,
+                  const uint32_t* d_exclude, float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts,
+                  void* stream) {
+  if (!ctx || !q || (!d_t2t_bank && n_rows > 0) || !d_out_scores || !d_out_rows || !d_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(ctx->device));
+  BankSrc b;
+  b.host = false; b.t2t = d_t2t_bank; b.t2i = d_t2i_bank; b.dtype = dtype; b.n_rows = n_rows; b.row_class = d_row_class; b.exclude = d_exclude;
+  return run_pipeline(ctx, q, b, row_offset, k, t2t_threshold, t2i_threshold, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int32_t swat_topk_host(swat_ctx* ctx, const swat_queries* q, const void* h_t2t_bank, const void* h_t2i_bank, int32_t dtype, int64_t n_rows,
+                       int64_t row_offset, int32_t k, float t2t_threshold, float t2i_threshold, const int32_t* h_row_class,
+                       const uint32_t* h_exclude, float* h_out_scores, int64_t* h_out_rows, float* h_out_t2i, int32_t* h_out_counts) {
+  if (!ctx || !q || (!h_t2t_bank && n_rows > 0) || !h_out_scores || !h_out_rows || !h_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(ctx->device));
+  const size_t C = q->C;
+  SW_OK(ctx->w_out_t2i.ensure(C * k * 4));
+  DevBuf o_scores, o_rows, o_counts;
+  int32_t rc = o_scores.ensure(C * k * 4);
+  if (rc == SWAT_OK) rc = o_rows.ensure(C * k * 8);
+  if (rc == SWAT_OK) rc = o_counts.ensure(C * 4);
+  BankSrc b;
+  b.host = true; b.t2t = h_t2t_bank; b.t2i = h_t2i_bank; b.dtype = dtype; b.n_rows = n_rows; b.row_class = h_row_class; b.exclude = h_exclude;
+  cudaStream_t s = ctx->work_stream;
+  if (rc == SWAT_OK)
+    rc = run_pipeline(ctx, q, b, 0, k, t2t_threshold, t2i_threshold, o_scores.as<float>(), o_rows.as<int64_t>(),
+                      (h_out_t2i && h_t2i_bank) ? ctx->w_out_t2i.as<float>() : nullptr, o_counts.as<int32_t>(), s);
+  if (rc == SWAT_OK) {
+    cudaError_t e = cudaMemcpyAsync(h_out_scores, o_scores.p, C * k * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out_rows, o_rows.p, C * k * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out_counts, o_counts.p, C * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && h_out_t2i && h_t2i_bank) e = cudaMemcpyAsync(h_out_t2i, ctx->w_out_t2i.p, C * k * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(e));
+    ctx->timing[6] += static_cast<double>(C * k * 12 + C * 4 + ((h_out_t2i && h_t2i_bank) ? C * k * 4 : 0));
+    if (rc == SWAT_OK && row_offset != 0)
+      for (size_t i = 0; i < C * static_cast<size_t>(k); ++i) if (h_out_rows[i] >= 0) h_out_rows[i] += row_offset;
+  }
+  o_scores.release(); o_rows.release(); o_counts.release();
+  return rc;
+}
+
+}  // extern "C"

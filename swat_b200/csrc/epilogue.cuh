@@ -1,0 +1,144 @@
+// Fused selection epilogue shared by the tcgen05 and the SIMT scan kernels.
+//
+// A thread owns ONE bank row and receives that row's scores against NC consecutive query columns in
+// registers.  Columns of one class are adjacent; the last column of a class carries the group size
+// and the class threshold.  The common case -- no lane of the warp beats the class threshold -- costs
+// a compare, a vote and an untaken branch per class.  Survivors (rare after warm-up: about
+// k*ln(N/k) per class over the whole scan) take the slow path: warp-aggregated append to the class
+// candidate buffer, histogram update, and every `refresh_every` appends a threshold refresh from the
+// histogram.  The N x Q score matrix never reaches HBM.
+//
+// Replaces, for all classes at once: t2t_similarity -> sorted() -> add_to_split of
+// /root/reference/retrieval/sample_retrieval.py:752-758 (and :804-812 with the in-pass T2I predicate).
+#pragma once
+#include "common.cuh"
+
+namespace swat {
+
+struct EpiCtx {
+  float* tau_col;          // smem, thresholds by block-local column (valid at group-end columns)
+  const int32_t* cls_col;  // smem, global class index by block-local column (-1 = padding)
+  const float* cnt_col;    // smem, group size by block-local column (at group-end columns)
+  uint32_t row;            // view-local row owned by this thread
+  bool row_valid;
+  int my_cls;              // partitioned mode: class of this row (-1 = none)
+  float acc, acc2;         // running group reduce (T2T, in-pass T2I)
+};
+
+// Recompute the class threshold from its histogram: the largest bin edge with at least k_fetch
+// appended scores at or above it.  Valid at any time: every counted score belongs to a distinct bank
+// row, so at least k_fetch rows score >= the edge and no row below it can enter the top k_fetch.
+static __device__ __noinline__ void refresh_tau(const JobState& st, int cls, float* tau_slot) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t* h = st.hist + static_cast<size_t>(cls) * kHistBins + lane * 32;
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 t = ld_cg_u32x4(h + 4 * i);
+    v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mine += v[i];
+  uint32_t suf = mine;  // inclusive suffix sum over lanes (higher lane = higher scores)
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_down_sync(0xffffffffu, suf, d);
+    if (lane + d < 32) suf += t;
+  }
+  const uint32_t K = st.k_fetch;
+  const uint32_t ball = __ballot_sync(0xffffffffu, suf >= K);
+  if (ball == 0) return;
+  const int L = 31 - __clz(ball);
+  int bin = -1;
+  if (lane == L) {
+    uint32_t run = suf - mine;
+#pragma unroll
+    for (int j = 31; j >= 0; --j) {
+      if (bin < 0) {
+        run += v[j];
+        if (run >= K) bin = lane * 32 + j;
+      }
+    }
+  }
+  bin = __shfl_sync(0xffffffffu, bin, L);
+  if (bin >= 1 && lane == 0) {
+    const uint32_t e = f32_enc(hist_edge(st, bin));
+    const uint32_t old = atomicMax(&st.tau_enc[cls], e);
+    *tau_slot = f32_dec(old > e ? old : e);
+  }
+}
+
+// Slow path: at least one lane of the warp passed the fast predicate for class `cls`.
+static __device__ __noinline__ void slow_append(const ScanArgs& a, float* tau_slot, int cls, float val, bool pass,
+                                         uint32_t row) {
+  const JobState& st = a.st;
+  if (pass && a.exclude != nullptr) pass = ((a.exclude[row >> 5] >> (row & 31)) & 1u) == 0u;
+  const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = __popc(ballot);
+  uint32_t slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(&st.count[cls], n);
+  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  if (pass) {
+    const float s = val + 0.0f;  // -0.0 -> +0.0: Python compares them equal, the key must too
+    const uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < st.cap) {
+      st.cand[static_cast<size_t>(cls) * st.cap + slot] = make_key(s, a.row_base + row);
+    } else {
+      atomicOr(st.flags, 1u);
+    }
+    atomicAdd(&st.hist[static_cast<size_t>(cls) * kHistBins + hist_bin(st, s)], 1u);
+  }
+  const uint32_t after = slot0 + n;
+  if (after >= st.k_fetch && (slot0 < st.k_fetch || after / st.refresh_every != slot0 / st.refresh_every)) {
+    refresh_tau(st, cls, tau_slot);
+  }
+}
+
+// NC columns starting at block-local column col0.  endmask bit j: column col0+j closes a class.
+template <int NC, int RED, bool PART, bool DUAL, bool DENSE>
+__device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, const float (&v)[NC],
+                                              const float (&v2)[NC], int col0, uint32_t endmask) {
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    if (RED == RED_NONE) {
+      cx.acc = v[j];
+      if (DUAL) cx.acc2 = v2[j];
+    } else {
+      cx.acc = red_op<RED>(cx.acc, v[j]);
+      if (DUAL) cx.acc2 = red_op<RED>(cx.acc2, v2[j]);
+    }
+    if ((endmask >> j) & 1u) {  // warp-uniform
+      const int col = col0 + j;
+      const float val = red_fin<RED>(cx.acc, cx.cnt_col[col]);
+      if (DENSE) {
+        if (cx.row_valid) a.dense_out[static_cast<size_t>(cx.row) * a.n_classes + cx.cls_col[col]] = val;
+      } else {
+        bool pass = cx.row_valid && (val >= cx.tau_col[col]);
+        if (DUAL) pass = pass && (red_fin<RED>(cx.acc2, cx.cnt_col[col]) >= a.t2i_thr);
+        if (PART) pass = pass && (cx.my_cls == cx.cls_col[col]);
+        if (__any_sync(0xffffffffu, pass)) slow_append(a, &cx.tau_col[col], cx.cls_col[col], val, pass, cx.row);
+      }
+      if (RED != RED_NONE) {
+        cx.acc = red_init<RED>();
+        if (DUAL) cx.acc2 = red_init<RED>();
+      }
+    }
+  }
+}
+
+// Fill the per-column threshold table of one Q block from the global class thresholds.
+// Called by `nthreads` cooperating threads (tid = 0..nthreads-1) before a tile's epilogue.
+__device__ __forceinline__ void load_tau_table(const JobState& st, float* tau_col, const int32_t* cls_col,
+                                               const float* cnt_col, int ncols, int tid, int nthreads) {
+  for (int c = tid; c < ncols; c += nthreads) {
+    const int cls = cls_col[c];
+    float t = INFINITY;
+    if (cls >= 0 && cnt_col[c] > 0.0f) t = f32_dec(ld_cg_u32(&st.tau_enc[cls]));
+    tau_col[c] = t;
+  }
+}
+
+}  // namespace swat

@@ -1,0 +1,367 @@
+// tcgen05 / TMEM / TMA scan kernel: bank[N,512] bf16  x  queries^T  ->  fused per-class selection.
+//
+// One persistent CTA (cta_group::1) or CTA pair (cta_group::2, 256 bank rows per MMA) per SM.
+//   warp 0   TMA producer : query block once (resident for the whole kernel), then the bank, each
+//                           byte exactly once per Q block, 128 rows x 64 k (16 KB, SWIZZLE_128B) per stage
+//   warp 1   MMA issuer   : one thread, tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM),
+//                           M = 128*ctas, N = padded query columns (<=256), K = 16 per instruction
+//   warp 2   TMEM allocator (512 columns = two accumulator buffers of <=256 columns)
+//   warps 4-7 epilogue    : tcgen05.ld 32 columns at a time -> process_chunk (epilogue.cuh); the
+//                           accumulator buffer is released as soon as its last column is in registers
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue).
+//
+// Replaces caption_embeddings.cuda() @ class_prompt.t() + sorted() + walk,
+// /root/reference/retrieval/sample_retrieval.py:400, :754, :439-482 for every class at once.
+#include <cuda.h>
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "scan_tc.h"
+
+namespace swat {
+namespace {
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier addressed in the shared::cluster window (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();   // a hang becomes a launch failure, not a dead GPU
+  } while (!done);
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+template <int kCtas>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint64_t hint) {
+  if (kCtas == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int kCtas> __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  if (kCtas == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int kCtas> __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  if (kCtas == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+template <int kCtas>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (kCtas == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+// arrive on `bar` (same smem offset in every CTA of the group) once all MMAs issued so far retire
+template <int kCtas> __device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (kCtas == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return static_cast<uint64_t>((saddr >> 4) & 0x3FFFu)   // start address
+       | (1ull << 16)                                    // leading byte offset (unused for SW128 K-major)
+       | (64ull << 32)                                   // stride byte offset 1024 >> 4
+       | (1ull << 46)                                    // descriptor version (sm_100)
+       | (2ull << 61);                                   // SWIZZLE_128B
+}
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4)                               // D = f32
+       | (1u << 7) | (1u << 10)                  // A = B = bf16
+       | (static_cast<uint32_t>(N >> 3) << 17)   // both K-major (bits 15,16 = 0)
+       | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+constexpr int kStageBytes = 128 * 128;   // 128 bank rows x 64 bf16
+constexpr int kTailBytes = 5120;         // barriers + tables
+
+// ---------------------------------------------------------------------------------------- kernel
+template <int kCtas, int RED, bool PART, bool DENSE>
+__global__ void __launch_bounds__(256, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constant__ CUtensorMap tm_q, const TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const int pair_id = blockIdx.x / kCtas, n_pairs = gridDim.x / kCtas;
+  const int qb = pair_id % p.n_qb;
+  const int pair_in_qb = pair_id / p.n_qb;
+  const int pairs_qb = (n_pairs - qb + p.n_qb - 1) / p.n_qb;
+  const int NB = p.n_blk, NBC = NB / kCtas;
+  const uint32_t b_chunk_bytes = static_cast<uint32_t>(NBC) * 128u;
+  constexpr int kTileRows = 128 * kCtas;
+  const int64_t n_tiles = (p.s.n_rows + kTileRows - 1) / kTileRows;
+
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + p.smem_b_bytes;
+  uint8_t* tail = sA + p.n_stages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [8]
+  uint64_t* empty_bar = full_bar + 8;                         // [8]
+  uint64_t* tfull_bar = empty_bar + 8;                        // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                       // [2]
+  uint64_t* q_bar = tempty_bar + 2;                           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+  float* s_tau = reinterpret_cast<float*>(tail + 256);        // [2][256]
+  int32_t* s_cls = reinterpret_cast<int32_t*>(s_tau + 512);   // [256]
+  float* s_cnt = reinterpret_cast<float*>(s_cls + 256);       // [256]
+  uint32_t* s_end = reinterpret_cast<uint32_t*>(s_cnt + 256); // [8]
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_bank);
+    prefetch_tmap(&tm_q);
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4 * kCtas); }
+    mbar_init(smem_u32(q_bar), 1);
+    fence_barrier_init();
+  }
+  for (int c = threadIdx.x; c < 256; c += 256) {
+    const bool in = c < NB;
+    s_cls[c] = in ? p.s.col_class[qb * NB + c] : -1;
+    s_cnt[c] = in ? p.s.col_count[qb * NB + c] : 0.0f;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    uint32_t m = 0;
+    for (int j = 0; j < 32; ++j) if (s_cnt[threadIdx.x * 32 + j] > 0.0f) m |= 1u << j;
+    s_end[threadIdx.x] = m;
+  }
+  if (warp == 2) tmem_alloc<kCtas>(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t q_bar_a = smem_u32(q_bar);
+      const uint32_t q_bar_lead = (kCtas == 2) ? mapa_rank0(q_bar_a) : q_bar_a;
+      if (rank == 0) mbar_arrive_expect_tx(q_bar_a, 8u * b_chunk_bytes * kCtas);
+      for (int kc = 0; kc < 8; ++kc)
+        tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
+                           0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
+      uint32_t stage = 0, phase = 0;
+      for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb) {
+        const int row0 = static_cast<int>(t * kTileRows + rank * 128);
+        for (int kc = 0; kc < 8; ++kc) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          if (rank == 0) mbar_arrive_expect_tx(fb, static_cast<uint32_t>(kStageBytes) * kCtas);
+          tma_load_2d<kCtas>(smem_u32(sA + stage * kStageBytes), &tm_bank, (kCtas == 2) ? mapa_rank0(fb) : fb, kc * 64, row0, p.bank_hint);
+          if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer (leader CTA)
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128 * kCtas, NB);
+      mbar_wait(smem_u32(q_bar), 0);
+      tc_fence_after();
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
+        const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+        mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256u;
+        for (int kc = 0; kc < 8; ++kc) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint64_t a0 = make_smem_desc(smem_u32(sA + stage * kStageBytes));
+          const uint64_t b0 = make_smem_desc(smem_u32(sB + kc * b_chunk_bytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 64-wide K chunk = 4 x UMMA_K(16); +32 B inside the swizzle atom
+            umma_bf16<kCtas>(d_tmem, a0 + 2u * k, b0 + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_commit<kCtas>(smem_u32(&empty_bar[stage]));
+          if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit<kCtas>(smem_u32(&tfull_bar[buf]));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== epilogue
+    const int ew = warp - 4;
+    const int etid = threadIdx.x - 128;
+    EpiCtx cx;
+    cx.cls_col = s_cls;
+    cx.cnt_col = s_cnt;
+    uint32_t it = 0;
+    for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
+      const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+      cx.tau_col = s_tau + buf * 256;
+      if (!DENSE) {
+        load_tau_table(p.s.st, cx.tau_col, s_cls, s_cnt, NB, etid, 128);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const int64_t row = t * kTileRows + rank * 128 + ew * 32 + lane;
+      cx.row = static_cast<uint32_t>(row);
+      cx.row_valid = row < p.s.n_rows;
+      cx.my_cls = -1;
+      if (PART && cx.row_valid) cx.my_cls = p.s.row_class[row];
+      cx.acc = red_init<RED>();
+      cx.acc2 = 0.0f;
+      mbar_wait(smem_u32(&tfull_bar[buf]), bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256u;
+      const uint32_t tempty_a = smem_u32(&tempty_bar[buf]);
+      const uint32_t tempty_lead = (kCtas == 2) ? mapa_rank0(tempty_a) : tempty_a;
+      for (int c0 = 0; c0 < NB; c0 += 32) {
+        if (NB - c0 >= 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          if (c0 + 32 >= NB) {   // accumulator fully in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_lead);
+          }
+          process_chunk<32, RED, PART, false, DENSE>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
+        } else {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_lead);
+          process_chunk<16, RED, PART, false, DENSE>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCtas>(tmem_base, 512);
+}
+
+template <int kCtas, int RED, bool PART, bool DENSE>
+cudaError_t launch_one(const CUtensorMap& tm_bank, const CUtensorMap& tm_q, const TcArgs& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = scan_tc_kernel<kCtas, RED, PART, DENSE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tm_bank, tm_q, p);
+}
+
+template <int kCtas, int RED>
+cudaError_t launch_red(const CUtensorMap& a, const CUtensorMap& b, const TcArgs& p, bool part, bool dense, int grid, size_t smem, cudaStream_t s) {
+  if (dense) return launch_one<kCtas, RED, false, true>(a, b, p, grid, smem, s);
+  if (part) return launch_one<kCtas, RED, true, false>(a, b, p, grid, smem, s);
+  return launch_one<kCtas, RED, false, false>(a, b, p, grid, smem, s);
+}
+template <int kCtas>
+cudaError_t launch_ctas(const CUtensorMap& a, const CUtensorMap& b, const TcArgs& p, int red, bool part, bool dense, int grid, size_t smem, cudaStream_t s) {
+  switch (red) {
+    case RED_NONE: return launch_red<kCtas, RED_NONE>(a, b, p, part, dense, grid, smem, s);
+    case RED_MEAN: return launch_red<kCtas, RED_MEAN>(a, b, p, part, dense, grid, smem, s);
+    case RED_MAX: return launch_red<kCtas, RED_MAX>(a, b, p, part, dense, grid, smem, s);
+    default: return launch_red<kCtas, RED_MIN>(a, b, p, part, dense, grid, smem, s);
+  }
+}
+
+}  // namespace
+
+size_t tc_smem_bytes(int n_blk, int ctas, int n_stages) {
+  const size_t b = static_cast<size_t>(8) * (n_blk / ctas) * 128;
+  return 1024 /* alignment slack */ + b + static_cast<size_t>(n_stages) * kStageBytes + kTailBytes;
+}
+
+int tc_pick_stages(int n_blk, int ctas, size_t smem_limit) {
+  for (int s = 8; s >= 2; --s)
+    if (tc_smem_bytes(n_blk, ctas, s) <= smem_limit) return s;
+  return 0;
+}
+
+cudaError_t launch_scan_tc(const void* tm_bank, const void* tm_q, const TcArgs& p, int ctas, int reduce, bool partitioned,
+                           bool dense, int grid, cudaStream_t stream) {
+  const size_t smem = tc_smem_bytes(p.n_blk, ctas, p.n_stages);
+  const CUtensorMap& a = *static_cast<const CUtensorMap*>(tm_bank);
+  const CUtensorMap& b = *static_cast<const CUtensorMap*>(tm_q);
+  if (ctas == 2) return launch_ctas<2>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
+  return launch_ctas<1>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
+}
+
+}  // namespace swat

@@ -1,0 +1,48 @@
+// Host-callable launchers of the swat_b200 kernels (internal; the public boundary is include/swat_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace swat {
+
+struct TcArgs {
+  ScanArgs s;
+  int32_t n_qb;           // Q blocks (each keeps <=256 padded query columns resident in shared memory)
+  int32_t n_blk;          // padded columns per Q block, multiple of 16
+  int32_t n_stages;       // bank-tile ring depth
+  uint32_t smem_b_bytes;  // per-CTA bytes of the resident query block
+  uint64_t bank_hint;     // L2 cache policy for bank tiles
+};
+
+size_t tc_smem_bytes(int n_blk, int ctas, int n_stages);
+int tc_pick_stages(int n_blk, int ctas, size_t smem_limit);
+// tm_bank / tm_q: CUtensorMap*
+cudaError_t launch_scan_tc(const void* tm_bank, const void* tm_q, const TcArgs& p, int ctas, int reduce,
+                           bool partitioned, bool dense, int grid, cudaStream_t stream);
+
+// SIMT fp32-FMA scan: any dtype, optional in-pass T2I predicate (bank2), exact reference arithmetic order
+cudaError_t launch_scan_simt(const ScanArgs& a, const void* bank, const void* bank2, const void* queries_padded,
+                             int dtype, int reduce, bool partitioned, bool dense, cudaStream_t stream);
+
+// final per-class select of the k_fetch best candidates
+cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
+                          int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream);
+
+struct T2iArgs {
+  const void* img_bank; int dtype; int64_t img_rows; int64_t img_row_base; const int64_t* img_index;
+  const void* queries;          // [Q,512] unpadded, same dtype as the bank
+  const int32_t* class_begin;   // [C+1] first query of each class
+  int reduce;
+  const float* cand_scores; const int64_t* cand_rows; const int32_t* cand_counts; const int32_t* truncated;
+  int k_fetch; int k; float t2i_thr; int n_classes;
+  float* t2i_scratch;           // [C, k_fetch]
+  float* out_scores; int64_t* out_rows; float* out_t2i; int32_t* out_counts; int32_t* incomplete;
+};
+cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream);
+
+cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
+                         int n_shards, int n_classes, int k, uint64_t* d_key_scratch, float* d_out_scores,
+                         int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts, cudaStream_t stream);
+
+cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t stream);
+
+}  // namespace swat

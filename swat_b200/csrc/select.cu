@@ -1,0 +1,339 @@
+// Per-class selection kernels: final top-k_fetch of a job, T2I re-score + accept walk, shard merge.
+#include "common.cuh"
+#include "scan_tc.h"
+
+namespace swat {
+namespace {
+
+constexpr int kSelThreads = 1024;
+
+// Exact top-`K` of n unique u64 keys in global memory, sorted descending into s_keys.
+// MSB-first 8-bit radix select narrows the candidate set until it fits the block sort
+// (usually 0-2 passes), then a bitonic sort orders it.  Returns min(n, >=K) sorted entries count
+// `total` (all keys >= the radix prefix); the caller takes the first min(K, total).
+__device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n, uint32_t K, uint64_t* s_keys,
+                                  uint32_t* s_hist, uint32_t* s_misc) {
+  const int tid = threadIdx.x;
+  uint64_t prefix = 0, mask = 0;
+  uint32_t need = K, m = n, sure = 0;
+  int shift = 56;
+  while (sure + m > static_cast<uint32_t>(kSortCap)) {   // uniform: all values come from shared memory
+    for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kSelThreads) {
+      const uint64_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t cum = 0;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (cum + s_hist[d] >= need) break;
+        cum += s_hist[d];
+      }
+      s_misc[0] = cum;            // keys strictly above the chosen digit: certainly selected
+      s_misc[1] = s_hist[d];      // keys matching the chosen digit: still undecided
+      s_misc[2] = static_cast<uint32_t>(d);
+    }
+    __syncthreads();
+    sure += s_misc[0];
+    need -= s_misc[0];
+    m = s_misc[1];
+    prefix |= static_cast<uint64_t>(s_misc[2]) << shift;
+    mask |= 0xFFull << shift;
+    shift -= 8;
+    __syncthreads();
+  }
+  // gather every key >= prefix (on the decided digits)
+  if (tid == 0) s_misc[3] = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += kSelThreads) {
+    const uint64_t key = keys[i];
+    if ((key & mask) >= prefix) {
+      const uint32_t pos = atomicAdd(&s_misc[3], 1u);
+      if (pos < static_cast<uint32_t>(kSortCap)) s_keys[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t total = min(s_misc[3], static_cast<uint32_t>(kSortCap));
+  uint32_t P = 2;
+  while (P < total) P <<= 1;
+  for (uint32_t i = total + tid; i < P; i += kSelThreads) s_keys[i] = 0ull;   // real keys are never 0
+  __syncthreads();
+  for (uint32_t k = 2; k <= P; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < P; i += kSelThreads) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = s_keys[i], y = s_keys[ixj];
+          const bool desc = (i & k) == 0;
+          if ((x < y) == desc) { s_keys[i] = y; s_keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+              int32_t* __restrict__ out_counts, int32_t* __restrict__ out_trunc) {
+  __shared__ uint64_t s_keys[kSortCap];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_misc[4];
+  const int c = blockIdx.x;
+  const uint32_t appended = st.count[c];
+  const uint32_t n = min(appended, st.cap);
+  const uint32_t K = st.k_fetch;
+  const uint32_t total = select_sorted(st.cand + static_cast<size_t>(c) * st.cap, n, K, s_keys, s_hist, s_misc);
+  const uint32_t cnt = min(K, total);
+  for (uint32_t i = threadIdx.x; i < K; i += kSelThreads) {
+    const bool ok = i < cnt;
+    const uint64_t key = ok ? s_keys[i] : 0ull;
+    out_scores[static_cast<size_t>(c) * K + i] = ok ? key_score(key) : 0.0f;
+    out_rows[static_cast<size_t>(c) * K + i] = ok ? static_cast<int64_t>(key_row(key)) + row_offset : -1;
+  }
+  if (threadIdx.x == 0) {
+    out_counts[c] = static_cast<int32_t>(cnt);
+    // more eligible rows than k_fetch exist iff more were appended, or the threshold ever rose
+    // (rows below a risen threshold are never appended)
+    if (out_trunc) out_trunc[c] = (appended > K || st.tau_enc[c] > f32_enc(st.thr)) ? 1 : 0;
+  }
+}
+
+__global__ void reset_kernel(const JobState st, int n_classes) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nh = static_cast<size_t>(n_classes) * kHistBins;
+  if (i < nh) st.hist[i] = 0;
+  if (i < static_cast<size_t>(n_classes)) { st.count[i] = 0; st.tau_enc[i] = f32_enc(st.thr); }
+  if (i == 0) st.flags[0] = 0;
+}
+
+// ---------------------------------------------------------------------------------- T2I stage
+template <typename T> __device__ __forceinline__ void load16(const T* p, float (&x)[16]);
+template <> __device__ __forceinline__ void load16<float>(const float* p, float (&x)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+}
+template <> __device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+      x[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+
+// one warp per candidate: t2i = reduce over the class's queries of <image row, query>
+// (cal_t2i_similarity, sample_retrieval.py:335-353)
+template <typename T>
+__global__ void __launch_bounds__(256) t2i_rescore_kernel(const T2iArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (g >= static_cast<int64_t>(a.n_classes) * a.k_fetch) return;
+  const int c = static_cast<int>(g / a.k_fetch), j = static_cast<int>(g % a.k_fetch);
+  if (j >= a.cand_counts[c]) return;
+  const int64_t r = a.img_index ? a.img_index[g] : a.cand_rows[g] - a.img_row_base;
+  float t2i = 0.0f;
+  if (r >= 0 && r < a.img_rows) {
+    float x[16], q[16];
+    load16<T>(static_cast<const T*>(a.img_bank) + r * kDim + lane * 16, x);
+    const int q0 = a.class_begin[c], q1 = a.class_begin[c + 1];
+    float red = (a.reduce == RED_MAX) ? -INFINITY : (a.reduce == RED_MIN) ? INFINITY : 0.0f;
+    for (int qi = q0; qi < q1; ++qi) {
+      load16<T>(static_cast<const T*>(a.queries) + static_cast<size_t>(qi) * kDim + lane * 16, q);
+      float d = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d = fmaf(x[i], q[i], d);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (a.reduce == RED_MAX) red = fmaxf(red, d);
+      else if (a.reduce == RED_MIN) red = fminf(red, d);
+      else if (a.reduce == RED_MEAN) red += d;
+      else red = d;
+    }
+    if (a.reduce == RED_MEAN) red = __fdiv_rn(red, static_cast<float>(q1 - q0));
+    t2i = red;
+  } else {
+    t2i = -INFINITY;
+  }
+  if (lane == 0) a.t2i_scratch[g] = t2i;
+}
+
+// accept walk of add_t2t_ranked_t2i_tshd_to_split (sample_retrieval.py:507-527): candidates are
+// already in T2T-descending order and pass the T2T threshold; keep those with t2i >= thr, stop at k.
+__global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) {
+  __shared__ uint32_t s_warp[32];
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.cand_counts[c];
+  constexpr int kPer = kMaxKFetch / kSelThreads;   // 4 consecutive candidates per thread
+  bool pass[kPer];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int j = tid * kPer + i;
+    pass[i] = (j < n) && (j < a.k_fetch) && (a.t2i_scratch[static_cast<size_t>(c) * a.k_fetch + j] >= a.t2i_thr);
+    mine += pass[i] ? 1u : 0u;
+  }
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    s_warp[lane] = wi - w;   // exclusive
+  }
+  __syncthreads();
+  uint32_t pos = s_warp[warp] + inc - mine;
+  __shared__ uint32_t s_total;
+  if (tid == kSelThreads - 1) s_total = pos + mine;
+  __syncthreads();
+  const uint32_t total = s_total;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    if (pass[i]) {
+      if (pos < static_cast<uint32_t>(a.k)) {
+        const size_t src = static_cast<size_t>(c) * a.k_fetch + tid * kPer + i;
+        const size_t dst = static_cast<size_t>(c) * a.k + pos;
+        a.out_scores[dst] = a.cand_scores[src];
+        a.out_rows[dst] = a.cand_rows[src];
+        if (a.out_t2i) a.out_t2i[dst] = a.t2i_scratch[src];
+      }
+      ++pos;
+    }
+  }
+  const uint32_t cnt = min(total, static_cast<uint32_t>(a.k));
+  for (uint32_t i = cnt + tid; i < static_cast<uint32_t>(a.k); i += kSelThreads) {
+    const size_t dst = static_cast<size_t>(c) * a.k + i;
+    a.out_scores[dst] = 0.0f;
+    a.out_rows[dst] = -1;
+    if (a.out_t2i) a.out_t2i[dst] = 0.0f;
+  }
+  if (tid == 0) {
+    a.out_counts[c] = static_cast<int32_t>(cnt);
+    if (a.incomplete) a.incomplete[c] = (total < static_cast<uint32_t>(a.k) && a.truncated && a.truncated[c]) ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------- shard merge
+__global__ void merge_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows,
+                                  const int32_t* __restrict__ counts, int G, int C, int k, uint64_t* __restrict__ keys) {
+  // keys laid out [C][G*k]; absent entries get key 0 (below every real key)
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(G) * C * k;
+  if (i >= total) return;
+  const int j = static_cast<int>(i % k);
+  const int c = static_cast<int>((i / k) % C);
+  const int g = static_cast<int>(i / (static_cast<size_t>(k) * C));
+  uint64_t key = 0;
+  if (j < counts[g * C + c]) key = make_key(scores[i] + 0.0f, static_cast<uint32_t>(rows[i]));
+  keys[(static_cast<size_t>(c) * G + g) * k + j] = key;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ aux, int G, int C, int k,
+             float* __restrict__ out_scores, int64_t* __restrict__ out_rows, float* __restrict__ out_aux,
+             int32_t* __restrict__ out_counts) {
+  __shared__ uint64_t s_keys[kSortCap];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_misc[4];
+  __shared__ uint32_t s_valid;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t n = static_cast<uint32_t>(G) * k;
+  const uint64_t* kc = keys + static_cast<size_t>(c) * n;
+  if (tid == 0) s_valid = 0;
+  __syncthreads();
+  uint32_t v = 0;
+  for (uint32_t i = tid; i < n; i += kSelThreads) v += kc[i] != 0ull ? 1u : 0u;
+  if (v) atomicAdd(&s_valid, v);
+  __syncthreads();
+  const uint32_t valid = s_valid;
+  const uint32_t total = select_sorted(kc, n, static_cast<uint32_t>(k), s_keys, s_hist, s_misc);
+  const uint32_t cnt = min(min(static_cast<uint32_t>(k), total), valid);
+  for (uint32_t i = tid; i < static_cast<uint32_t>(k); i += kSelThreads) {
+    const bool ok = i < cnt;
+    const uint64_t key = ok ? s_keys[i] : 0ull;
+    out_scores[static_cast<size_t>(c) * k + i] = ok ? key_score(key) : 0.0f;
+    out_rows[static_cast<size_t>(c) * k + i] = ok ? static_cast<int64_t>(key_row(key)) : -1;
+    if (out_aux && !ok) out_aux[static_cast<size_t>(c) * k + i] = 0.0f;
+  }
+  if (tid == 0) out_counts[c] = static_cast<int32_t>(cnt);
+  if (out_aux && aux) {
+    // route each surviving entry's aux value (e.g. its T2I score) to its merged position:
+    // keys are unique, binary-search the descending sorted list
+    for (uint32_t i = tid; i < n; i += kSelThreads) {
+      const uint64_t key = kc[i];
+      if (key == 0ull) continue;
+      uint32_t lo = 0, hi = cnt;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_keys[mid] > key) lo = mid + 1; else hi = mid;
+      }
+      if (lo < cnt && s_keys[lo] == key) {
+        const int g = static_cast<int>(i / k), j = static_cast<int>(i % k);
+        out_aux[static_cast<size_t>(c) * k + lo] = aux[(static_cast<size_t>(g) * C + c) * k + j];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
+                          int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream) {
+  if (n_classes <= 0) return cudaSuccess;
+  select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(n_classes) * kHistBins;
+  reset_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(st, n_classes);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream) {
+  const int64_t n = static_cast<int64_t>(a.n_classes) * a.k_fetch;
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((n + 7) / 8);
+  if (a.dtype == 0) t2i_rescore_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
+  else t2i_rescore_kernel<float><<<grid, 256, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  t2i_walk_kernel<<<a.n_classes, kSelThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
+                         int n_shards, int n_classes, int k, uint64_t* d_key_scratch, float* d_out_scores,
+                         int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(n_shards) * n_classes * k;
+  if (total == 0) return cudaSuccess;
+  merge_keys_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(d_scores, d_rows, d_counts, n_shards,
+                                                                                  n_classes, k, d_key_scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_aux, n_shards, n_classes, k, d_out_scores,
+                                                      d_out_rows, d_out_aux, d_out_counts);
+  return cudaGetLastError();
+}
+
+}  // namespace swat

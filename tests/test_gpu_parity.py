@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the golden vectors
+generated from the reference.  Everything here needs a B200 (``-m gpu``)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import swat_oracle as so
+from tests.golden_util import assert_walk_equal, load_bank_case
+
+pytestmark = pytest.mark.gpu
+
+# Parity contract (BASELINE.json north_star): indices identical after tie-breaking by row index,
+# score deltas allowed only between near-ties / at the k-th boundary; scores within 1e-3 absolute.
+# The tensor-core path accumulates exact bf16 products in fp32 in a different order than the CPU,
+# so near-ties are compared with TIE_TOL, far below the 1e-3 the contract allows.
+TIE_TOL = 2e-5
+SCORE_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from swat_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="module", params=[2, 1], ids=["cta_group2", "cta_group1"])
+def ctx(request, lib):
+    c = lib.Context(0, cta_group=request.param)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx2(lib):
+    c = lib.Context(0)
+    yield c
+    c.close()
+
+
+def _rand_unit(n, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.nn.functional.normalize(torch.randn(n, 512, generator=g), dim=-1)
+    return x.to(dtype)
+
+
+def check_result(scores, rows, counts, o_rows, o_scores, o_counts, S, tol, t2i=None, o_t2i=None, what=""):
+    scores, rows, counts = scores.cpu().numpy(), rows.cpu().numpy(), counts.cpu().numpy()
+    swaps = 0
+    for c in range(rows.shape[0]):
+        n = int(counts[c])
+        assert n == int(o_counts[c]), f"{what} class {c}: count {n} != oracle {int(o_counts[c])}"
+        swaps += assert_walk_equal(rows[c, :n], o_rows[c, :n], lambda r, c=c: S[r, c], tol, boundary_tol=SCORE_TOL, what=f"{what} class {c}")
+        assert np.all(rows[c, n:] == -1)
+        np.testing.assert_allclose(scores[c, :n], S[rows[c, :n], c], atol=SCORE_TOL)
+        np.testing.assert_allclose(scores[c, :n], o_scores[c, :n], atol=SCORE_TOL)
+        assert np.all(np.diff(scores[c, :n]) <= 0), f"{what} class {c}: scores not descending"
+    return swaps
+
+
+@pytest.mark.parametrize("n_rows,n_cls", [(1000, 37), (256, 16), (77, 5), (4099, 200)])
+def test_dense_scores_match_oracle(lib, ctx, n_rows, n_cls):
+    bank = _rand_unit(n_rows, 1, torch.bfloat16)
+    q = _rand_unit(n_cls, 2, torch.bfloat16).float()
+    ref = so.score_matrix(bank.float().numpy(), q.numpy())
+    qs = lib.Queries(ctx, q)
+    d_bank = bank.cuda()
+    tc = lib.scores_dense(ctx, qs, d_bank, engine="tc").cpu().numpy()
+    simt = lib.scores_dense(ctx, qs, d_bank, engine="simt").cpu().numpy()
+    np.testing.assert_allclose(simt, ref, atol=2e-6)
+    np.testing.assert_allclose(tc, ref, atol=1e-5)
+    f32 = lib.scores_dense(ctx, lib.Queries(ctx, _rand_unit(n_cls, 2)), _rand_unit(n_rows, 1).cuda()).cpu().numpy()
+    np.testing.assert_allclose(f32, so.score_matrix(_rand_unit(n_rows, 1).numpy(), _rand_unit(n_cls, 2).numpy()), atol=2e-6)
+
+
+@pytest.mark.parametrize("reduce", ["mean", "max", "min"])
+def test_dense_scores_grouped(lib, ctx, reduce):
+    sizes = [1, 3, 2, 5, 1, 4, 18, 2, 2, 7]
+    coq = np.repeat(np.arange(len(sizes)), sizes).astype(np.int32)
+    bank = _rand_unit(777, 3, torch.bfloat16)
+    q = _rand_unit(len(coq), 4, torch.bfloat16).float()
+    ref = so.score_matrix(bank.float().numpy(), q.numpy(), coq, len(sizes), reduce)
+    qs = lib.Queries(ctx, q, coq, len(sizes), reduce)
+    for eng in ("tc", "simt"):
+        got = lib.scores_dense(ctx, qs, bank.cuda(), engine=eng).cpu().numpy()
+        np.testing.assert_allclose(got, ref, atol=1e-5, err_msg=f"{reduce}/{eng}")
+
+
+@pytest.mark.parametrize("name", ["bank_bf16", "bank_f32"])
+def test_golden_reference_parity(lib, ctx, name):
+    """The reference's own outputs (tests/golden, made by oracle/gen_golden.py): T2T-rank and
+    T2T-rank-T2I-tshd, partitioned (the reference's real use) and unpartitioned."""
+    z, meta, cap, img, q = load_bank_case(name)
+    k = int(z["k"]); labels = z["labels"]; C = q.shape[0]
+    dt = torch.bfloat16 if name == "bank_bf16" else torch.float32
+    d_cap = torch.from_numpy(cap).to(dt).cuda(); d_img = torch.from_numpy(img).to(dt).cuda()
+    qs = lib.Queries(ctx, torch.from_numpy(q))
+    S = so.score_matrix(cap, q)
+    row_class = torch.from_numpy(labels.astype(np.int32)).cuda()
+    for tag, rc in (("unpart", None), ("part", row_class)):
+        for m, t2i in (("t2t", None), ("t2t_t2i", d_img)):
+            scores, rows, ti, counts = lib.topk(ctx, qs, d_cap, k, 0.0, t2i_bank=t2i, t2i_threshold=0.25, row_class=rc)
+            ref_rows = z[f"{tag}_{m}_rows"]; ref_labels = z[f"{tag}_{m}_labels"]
+            rows = rows.cpu().numpy(); counts = counts.cpu().numpy()
+            for c in range(C):
+                cid = int(z["class_ids"][c])
+                exp = ref_rows[ref_labels == cid]
+                assert int(counts[c]) == len(exp) == meta["counts"][tag][m][str(cid)], f"{name} {tag} {m} class {cid}"
+                assert_walk_equal(rows[c, :counts[c]], exp, lambda r, c=c: S[r, c], TIE_TOL, boundary_tol=SCORE_TOL,
+                                  what=f"{name} {tag} {m} class {cid}")
+            if ti is not None:
+                I = so.score_matrix(img, q)
+                ti = ti.cpu().numpy()
+                for c in range(C):
+                    n = int(counts[c])
+                    np.testing.assert_allclose(ti[c, :n], I[rows[c, :n], c], atol=SCORE_TOL)
+                    assert np.all(ti[c, :n] >= 0.25 - 1e-6)
+
+
+def test_tie_probe(lib, ctx2):
+    z = np.load("tests/golden/primitives.npz")
+    caps, imgs, q = z["probe_caps"], z["probe_imgs"], z["probe_q"]
+    qs = lib.Queries(ctx2, torch.from_numpy(q[None]))
+    s, r, t, c = lib.topk(ctx2, qs, torch.from_numpy(caps).cuda(), 4, 0.0)
+    assert r[0, :int(c[0])].tolist() == [3, 1, 4, 5]
+    s, r, t, c = lib.topk(ctx2, qs, torch.from_numpy(caps).cuda(), 4, 0.0, t2i_bank=torch.from_numpy(imgs).cuda())
+    assert r[0, :int(c[0])].tolist() == [1, 4, 5, 2]
+
+
+@pytest.mark.parametrize("n_rows,n_cls,k", [(200_000, 64, 500), (50_001, 200, 100), (3000, 8, 4000)])
+def test_topk_random_bank_vs_oracle(lib, ctx, n_rows, n_cls, k):
+    """Thresholds, histogram refresh and candidate buffers under load; k > rows-per-class included."""
+    from swat_b200 import synth
+    qc, queries, coq = synth.make_queries(n_cls, 1, seed=5, dtype=torch.bfloat16)
+    cap, img, labels = synth.make_bank(n_rows, qc, seed=5, dtype=torch.bfloat16, rho=0.2, tie_block=300, chunk=1 << 16)
+    capf, imgf, qf = cap.float().numpy(), img.float().numpy(), queries.float().numpy()
+    S = so.score_matrix(capf, qf)
+    qs = lib.Queries(ctx, queries.float())
+    o = so.topk_walk(capf, qf, k, 0.0)
+    g = lib.topk(ctx, qs, cap.cuda(), k, 0.0)
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what="t2t")
+    o = so.topk_walk(capf, qf, k, 0.0, t2i_bank=imgf, t2i_threshold=0.25)
+    g = lib.topk(ctx, qs, cap.cuda(), k, 0.0, t2i_bank=img.cuda(), t2i_threshold=0.25)
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what="t2t+t2i")
+
+
+@pytest.mark.parametrize("reduce", ["max", "mean", "min"])
+def test_topk_synonym_groups(lib, ctx, reduce):
+    from swat_b200 import synth
+    sizes = [1 + (i * 7) % 6 for i in range(90)]            # 90 classes, 1..6 synonyms each -> 2 Q blocks at cta_group 1
+    qc, queries, coq = synth.make_queries(len(sizes), sizes, seed=9, dtype=torch.bfloat16)
+    cap, img, _ = synth.make_bank(30_000, qc, seed=9, dtype=torch.bfloat16, rho=0.3, tie_block=100, chunk=1 << 15)
+    capf, imgf, qf = cap.float().numpy(), img.float().numpy(), queries.float().numpy()
+    coq_np = coq.numpy()
+    S = so.score_matrix(capf, qf, coq_np, len(sizes), reduce)
+    qs = lib.Queries(ctx, queries.float(), coq, len(sizes), reduce)
+    o = so.topk_walk(capf, qf, 200, 0.0, t2i_bank=imgf, class_of_query=coq_np, n_classes=len(sizes), reduce=reduce)
+    g = lib.topk(ctx, qs, cap.cuda(), 200, 0.0, t2i_bank=img.cuda())
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=reduce)
+
+
+def test_exclusion_bitmap_and_threshold(lib, ctx2):
+    bank = _rand_unit(5000, 11, torch.bfloat16)
+    q = _rand_unit(12, 12, torch.bfloat16)
+    S = so.score_matrix(bank.float().numpy(), q.float().numpy())
+    ex = np.zeros(5000, dtype=bool); ex[::3] = True
+    bits = np.packbits(ex, bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)]).view(np.int32)
+    qs = lib.Queries(ctx2, q.float())
+    for thr in (0.0, 0.05, -1.0):
+        o = so.topk_walk(bank.float().numpy(), q.float().numpy(), 64, thr, exclude=ex)
+        g = lib.topk(ctx2, qs, bank.cuda(), 64, thr, exclude=torch.from_numpy(bits).cuda())
+        check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=f"thr {thr}")
+        assert not np.any(ex[g[1].cpu().numpy()[g[1].cpu().numpy() >= 0]])
+
+
+def test_overflow_retry_and_t2i_escalation(lib):
+    """Tiny candidate buffers force the overflow retry; a T2I predicate almost nothing passes forces
+    over-fetch escalation and finally the exact in-pass predicate."""
+    ctx = lib.Context(0, cand_cap=4096, overfetch=64)
+    bank = _rand_unit(60_000, 21, torch.bfloat16)
+    img = _rand_unit(60_000, 22, torch.bfloat16)
+    q = _rand_unit(24, 23, torch.bfloat16)
+    img[1000:60_000:997] = q[3]                                  # ~60 rows pass T2I for class 3 only
+    bf, imf, qf = bank.float().numpy(), img.float().numpy(), q.float().numpy()
+    S = so.score_matrix(bf, qf)
+    qs = lib.Queries(ctx, q.float())
+    o = so.topk_walk(bf, qf, 40, 0.0)
+    g = lib.topk(ctx, qs, bank.cuda(), 40, 0.0)
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what="overflow")
+    assert ctx.last_timing()["escalations"] >= 1
+    o = so.topk_walk(bf, qf, 40, 0.0, t2i_bank=imf, t2i_threshold=0.25)
+    g = lib.topk(ctx, qs, bank.cuda(), 40, 0.0, t2i_bank=img.cuda(), t2i_threshold=0.25)
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what="escalation")
+    assert int(o[3][3]) > 0 and int(o[3].sum()) == int(o[3][3])
+    ctx.close()
+
+
+def test_host_pipeline_equals_resident(lib, ctx2):
+    from swat_b200 import synth
+    qc, queries, _ = synth.make_queries(40, 1, seed=31, dtype=torch.bfloat16)
+    cap, img, labels = synth.make_bank(70_000, qc, seed=31, dtype=torch.bfloat16, rho=0.2, tie_block=200, chunk=1 << 16)
+    qs = lib.Queries(ctx2, queries.float())
+    ctx2.set_option("host_chunk_rows", 8192)
+    for t2i_dev, t2i_host in ((None, None), (img.cuda(), img.pin_memory())):
+        r = lib.topk(ctx2, qs, cap.cuda(), 300, 0.0, t2i_bank=t2i_dev, row_offset=1000)
+        h = lib.topk_host(ctx2, qs, cap.pin_memory(), 300, 0.0, t2i_bank=t2i_host, row_offset=1000)
+        assert torch.equal(r[1].cpu(), h[1]) and torch.equal(r[3].cpu(), h[3])
+        assert torch.equal(r[0].cpu(), h[0])
+        if t2i_dev is not None:
+            assert torch.equal(r[2].cpu(), h[2])
+    ctx2.set_option("host_chunk_rows", 1 << 18)
+
+
+def test_merge_and_shard_invariance(lib, ctx2):
+    """Row-sharded scan + merge equals the single-shard result for any shard count."""
+    from swat_b200 import synth
+    qc, queries, _ = synth.make_queries(30, 1, seed=41, dtype=torch.bfloat16)
+    cap, img, _ = synth.make_bank(90_000, qc, seed=41, dtype=torch.bfloat16, rho=0.2, tie_block=500, chunk=1 << 16)
+    qs = lib.Queries(ctx2, queries.float())
+    d_cap, d_img = cap.cuda(), img.cuda()
+    full = lib.topk(ctx2, qs, d_cap, 250, 0.0, t2i_bank=d_img)
+    for G in (2, 3, 8):
+        bounds = np.linspace(0, 90_000, G + 1).astype(int)
+        parts = [lib.topk(ctx2, qs, d_cap[a:b], 250, 0.0, t2i_bank=d_img[a:b], row_offset=int(a)) for a, b in zip(bounds[:-1], bounds[1:])]
+        s = torch.stack([p[0] for p in parts]); r = torch.stack([p[1] for p in parts])
+        t = torch.stack([p[2] for p in parts]); c = torch.stack([p[3] for p in parts])
+        ms, mr, mt, mc = lib.merge_topk(ctx2, s, r, c, aux=t)
+        assert torch.equal(mr, full[1]) and torch.equal(mc, full[3]), f"G={G}"
+        assert torch.equal(ms, full[0]) and torch.equal(mt, full[2])
+
+
+def test_streaming_job_matches_single_view(lib, ctx2):
+    bank = _rand_unit(40_000, 51, torch.bfloat16).cuda()
+    q = _rand_unit(20, 52, torch.bfloat16)
+    qs = lib.Queries(ctx2, q.float())
+    job = lib.Job(ctx2, qs, 128, 0.0)
+    job.scan(bank)
+    a = job.select(); assert not job.overflowed()
+    job.reset()
+    for s0 in range(0, 40_000, 7777):
+        job.scan(bank[s0:s0 + 7777], row_base=s0)
+    b = job.select(); assert not job.overflowed()
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+    job.close()
+
+
+def test_bad_arguments_raise(lib, ctx2):
+    q = _rand_unit(4, 1)
+    with pytest.raises(lib.SwatError):
+        lib.Queries(ctx2, q, np.array([0, 0, 1, 1], np.int32), 2, "none")      # NONE needs one query per class
+    with pytest.raises(lib.SwatError):
+        lib.Queries(ctx2, q, np.array([1, 0, 1, 0], np.int32), 2, "max")       # not grouped
+    qs = lib.Queries(ctx2, q)
+    with pytest.raises(lib.SwatError):
+        lib.topk(ctx2, qs, _rand_unit(64, 2).cuda(), 100000)                   # k beyond the supported maximum
+    with pytest.raises((ValueError, TypeError)):
+        lib.topk(ctx2, qs, torch.zeros(64, 256).cuda(), 10)
