@@ -120,11 +120,16 @@ int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_ba
                       int32_t* d_incomplete, void* stream);
 
 /* ---- multi-GPU: merge after the single NCCL gather ------------------------------ */
-/* d_scores/d_rows: [G,C,k] gathered shard results (rows already global), d_counts [G,C]. */
+/* d_scores/d_rows/d_aux: [G,C,k_in] gathered shard candidate lists (rows already global, < 2^32),
+ * d_counts [G,C], d_truncated [G,C] (nullable).  Keeps, per class, the k_out best entries under
+ * (score desc, row asc) among those with aux >= aux_threshold (d_aux == NULL: no predicate) -- the
+ * reference's accept walk (:507-527) run over the union of the shards' candidates.
+ * d_incomplete [C] (nullable): 1 = the result reaches below the last candidate of a truncated shard
+ * (rows that shard never reported could belong in it): re-run the shards with a larger k_in. */
 int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux,
-                        const int32_t* d_counts, int32_t n_shards, int32_t n_classes, int32_t k,
-                        float* d_out_scores, int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts,
-                        void* stream);
+                        const int32_t* d_counts, const int32_t* d_truncated, int32_t n_shards, int32_t n_classes,
+                        int32_t k_in, int32_t k_out, float aux_threshold, float* d_out_scores, int64_t* d_out_rows,
+                        float* d_out_aux, int32_t* d_out_counts, int32_t* d_incomplete, void* stream);
 
 /* ---- S1 compatibility: t2t_similarity / cal_t2i_similarity (:397-416, :335-353) ---------------- */
 /* d_out [n_rows, n_classes] f32 class scores (after the reduce).  Tests and back-compat only: the

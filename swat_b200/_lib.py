@@ -65,7 +65,7 @@ def load() -> C.CDLL:
         "swat_job_status": [vp, C.POINTER(i32)],
         "swat_job_destroy": [vp],
         "swat_t2i_walk": [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
-        "swat_merge_topk": [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
+        "swat_merge_topk": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_scores_dense": [vp, vp, vp, i32, i64, vp, i32, vp],
         "swat_topk": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
         "swat_topk_host": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp],
@@ -306,15 +306,24 @@ def t2i_walk(ctx: Context, queries: Queries, img_bank: torch.Tensor, cand_scores
     return o_s, o_r, o_t, o_c, o_i
 
 
-def merge_topk(ctx: Context, scores: torch.Tensor, rows: torch.Tensor, counts: torch.Tensor, aux: Optional[torch.Tensor] = None):
-    """Merge gathered shard results ``[G,C,k]`` (rows global) into ``[C,k]``."""
-    G, Cn, k = scores.shape
+def merge_topk(ctx: Context, scores: torch.Tensor, rows: torch.Tensor, counts: torch.Tensor, aux: Optional[torch.Tensor] = None,
+               truncated: Optional[torch.Tensor] = None, k_out: Optional[int] = None, aux_threshold: float = float("-inf")):
+    """Merge gathered shard candidate lists ``[G,C,k_in]`` (rows global) into ``[C,k_out]``: the best
+    ``k_out`` entries with ``aux >= aux_threshold``.  Returns ``(scores, rows, aux | None, counts,
+    incomplete)``; ``incomplete[c] == 1`` means a truncated shard may hold rows that belong in the
+    result (re-run the shards with a larger ``k_in``)."""
+    G, Cn, k_in = scores.shape
+    k_out = int(k_in if k_out is None else k_out)
     dev = scores.device
-    o_s = torch.empty(Cn, k, dtype=torch.float32, device=dev)
-    o_r = torch.empty(Cn, k, dtype=torch.int64, device=dev)
-    o_a = torch.empty(Cn, k, dtype=torch.float32, device=dev) if aux is not None else None
+    scores, rows, counts = scores.contiguous(), rows.contiguous(), counts.contiguous()
+    aux = None if aux is None else aux.contiguous()
+    truncated = None if truncated is None else truncated.contiguous()
+    o_s = torch.empty(Cn, k_out, dtype=torch.float32, device=dev)
+    o_r = torch.empty(Cn, k_out, dtype=torch.int64, device=dev)
+    o_a = torch.empty(Cn, k_out, dtype=torch.float32, device=dev) if aux is not None else None
     o_c = torch.empty(Cn, dtype=torch.int32, device=dev)
-    _check(load().swat_merge_topk(ctx._h, _ptr(scores.contiguous()), _ptr(rows.contiguous()), _ptr(None if aux is None else aux.contiguous()),
-                                  _ptr(counts.contiguous()), int(G), int(Cn), int(k), _ptr(o_s), _ptr(o_r), _ptr(o_a), _ptr(o_c),
+    o_i = torch.empty(Cn, dtype=torch.int32, device=dev)
+    _check(load().swat_merge_topk(ctx._h, _ptr(scores), _ptr(rows), _ptr(aux), _ptr(counts), _ptr(truncated), int(G), int(Cn),
+                                  int(k_in), k_out, float(aux_threshold), _ptr(o_s), _ptr(o_r), _ptr(o_a), _ptr(o_c), _ptr(o_i),
                                   _stream(ctx.device)))
-    return o_s, o_r, o_a, o_c
+    return o_s, o_r, o_a, o_c, o_i

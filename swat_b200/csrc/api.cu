@@ -218,6 +218,7 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
   if (!ctx || !q || !out) return fail(SWAT_ERR_INVALID, "null argument");
   if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
   if (thr != thr) return fail(SWAT_ERR_INVALID, "threshold is NaN");
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
   CU_OK(cudaSetDevice(ctx->device));
   swat_job* j = new swat_job();
   j->ctx = ctx;
@@ -590,6 +591,7 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   if (n_queries < 1 || n_classes < 1) return fail(SWAT_ERR_INVALID, "need at least one query and one class");
   if (reduce < SWAT_REDUCE_NONE || reduce > SWAT_REDUCE_MIN) return fail(SWAT_ERR_INVALID, "bad reduce mode %d", reduce);
   if (!h_class_of_query && n_queries != n_classes) return fail(SWAT_ERR_INVALID, "class_of_query is required when n_queries != n_classes");
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
   CU_OK(cudaSetDevice(ctx->device));
   std::vector<int32_t> cb(n_classes + 1, 0);
   for (int i = 0; i < n_queries; ++i) {
@@ -670,6 +672,7 @@ int32_t swat_job_create(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, f
 
 int32_t swat_job_reset(swat_job* job, void* stream) {
   if (!job) return fail(SWAT_ERR_INVALID, "null job");
+  (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
   CU_OK(launch_job_reset(job->st, job->q->C, static_cast<cudaStream_t>(stream)));
   job->last_stream = static_cast<cudaStream_t>(stream);
@@ -680,6 +683,7 @@ int32_t swat_job_reset(swat_job* job, void* stream) {
 int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
                       float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, void* stream) {
   if (!job || (!d_bank && n_rows > 0)) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
   return scan_view(job, d_bank, dtype, n_rows, row_base, d_t2i_bank, t2i_threshold, d_row_class, d_exclude, engine, nullptr,
                    static_cast<cudaStream_t>(stream));
@@ -687,6 +691,7 @@ int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t 
 
 int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t* d_counts, int32_t* d_truncated, void* stream) {
   if (!job || !d_scores || !d_rows || !d_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
   CU_OK(launch_select(job->st, job->q->C, 0, d_scores, d_rows, d_counts, d_truncated, static_cast<cudaStream_t>(stream)));
   job->last_stream = static_cast<cudaStream_t>(stream);
@@ -696,6 +701,7 @@ int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t
 
 int32_t swat_job_status(swat_job* job, int32_t* overflowed) {
   if (!job || !overflowed) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
   uint32_t flags = 0;
   CU_OK(cudaMemcpyAsync(&flags, job->st.flags, 4, cudaMemcpyDeviceToHost, job->last_stream));
@@ -720,6 +726,7 @@ int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_ba
   if (!ctx || !q || !d_img_bank || !d_cand_scores || !d_cand_rows || !d_cand_counts || !d_out_scores || !d_out_rows || !d_out_counts)
     return fail(SWAT_ERR_INVALID, "null argument");
   if (k_fetch < 1 || k_fetch > kMaxKFetch || k < 1 || k > k_fetch) return fail(SWAT_ERR_INVALID, "need 1 <= k <= k_fetch <= %d", kMaxKFetch);
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
   CU_OK(cudaSetDevice(ctx->device));
   SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(q->C) * k_fetch * 4));
   T2iArgs t;
@@ -737,14 +744,18 @@ int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_ba
 }
 
 int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
-                        int32_t n_shards, int32_t n_classes, int32_t k, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
-                        int32_t* d_out_counts, void* stream) {
+                        const int32_t* d_truncated, int32_t n_shards, int32_t n_classes, int32_t k_in, int32_t k_out,
+                        float aux_threshold, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts,
+                        int32_t* d_incomplete, void* stream) {
   if (!ctx || !d_scores || !d_rows || !d_counts || !d_out_scores || !d_out_rows || !d_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
-  if (n_shards < 1 || n_classes < 1 || k < 1 || k > kMaxKFetch) return fail(SWAT_ERR_INVALID, "bad merge shape G=%d C=%d k=%d", n_shards, n_classes, k);
+  if (n_shards < 1 || n_classes < 1 || k_in < 1 || k_out < 1 || k_out > kMaxKFetch)
+    return fail(SWAT_ERR_INVALID, "bad merge shape G=%d C=%d k_in=%d k_out=%d", n_shards, n_classes, k_in, k_out);
+  (void)cudaGetLastError();
   CU_OK(cudaSetDevice(ctx->device));
-  SW_OK(ctx->w_keys.ensure(static_cast<size_t>(n_shards) * n_classes * k * 8));
-  CU_OK(launch_merge(d_scores, d_rows, d_aux, d_counts, n_shards, n_classes, k, ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows,
-                     d_out_aux, d_out_counts, static_cast<cudaStream_t>(stream)));
+  SW_OK(ctx->w_keys.ensure(static_cast<size_t>(n_shards) * n_classes * k_in * 8));
+  CU_OK(launch_merge(d_scores, d_rows, d_aux, aux_threshold, d_counts, d_truncated, n_shards, n_classes, k_in, k_out,
+                     ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows, d_out_aux, d_out_counts, d_incomplete,
+                     static_cast<cudaStream_t>(stream)));
   ctx->launches += 2;
   return SWAT_OK;
 }
@@ -752,6 +763,7 @@ int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_r
 int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows, float* d_out,
                           int32_t engine, void* stream) {
   if (!ctx || !q || !d_bank || !d_out) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
   CU_OK(cudaSetDevice(ctx->device));
   swat_job tmp;   // dense mode never touches job state
   tmp.ctx = ctx; tmp.q = q;
@@ -764,6 +776,7 @@ int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, 
                   const uint32_t* d_exclude, float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts,
                   void* stream) {
   if (!ctx || !q || (!d_t2t_bank && n_rows > 0) || !d_out_scores || !d_out_rows || !d_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
   CU_OK(cudaSetDevice(ctx->device));
   BankSrc b;
   b.host = false; b.t2t = d_t2t_bank; b.t2i = d_t2i_bank; b.dtype = dtype; b.n_rows = n_rows; b.row_class = d_row_class; b.exclude = d_exclude;
@@ -775,6 +788,7 @@ int32_t swat_topk_host(swat_ctx* ctx, const swat_queries* q, const void* h_t2t_b
                        int64_t row_offset, int32_t k, float t2t_threshold, float t2i_threshold, const int32_t* h_row_class,
                        const uint32_t* h_exclude, float* h_out_scores, int64_t* h_out_rows, float* h_out_t2i, int32_t* h_out_counts) {
   if (!ctx || !q || (!h_t2t_bank && n_rows > 0) || !h_out_scores || !h_out_rows || !h_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
   CU_OK(cudaSetDevice(ctx->device));
   const size_t C = q->C;
   SW_OK(ctx->w_out_t2i.ensure(C * k * 4));

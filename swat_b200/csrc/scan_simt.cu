@@ -110,6 +110,16 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
       }
     }
     const uint32_t endmask = s_endmask;
+    if (RED != RED_NONE) {
+      // zero-padding columns between Q blocks must not leak into the next class's max / min
+#pragma unroll
+      for (int j = 0; j < kNc; ++j) {
+        if (s_cls[j] < 0) {
+          acc[j] = red_init<RED>();
+          if (DUAL) acc2[DUAL ? j : 0] = red_init<RED>();
+        }
+      }
+    }
     if constexpr (DUAL) {
       process_chunk<kNc, RED, PART, DUAL, DENSE>(a, cx, acc, reinterpret_cast<const float(&)[kNc]>(acc2), 0, endmask);
     } else {

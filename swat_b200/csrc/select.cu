@@ -234,9 +234,11 @@ __global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) 
 }
 
 // ---------------------------------------------------------------------------------- shard merge
+// keys laid out [C][G*k]; absent entries and entries failing the aux (T2I) predicate get key 0,
+// which sorts below every real key
 __global__ void merge_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows,
-                                  const int32_t* __restrict__ counts, int G, int C, int k, uint64_t* __restrict__ keys) {
-  // keys laid out [C][G*k]; absent entries get key 0 (below every real key)
+                                  const float* __restrict__ aux, float aux_thr, const int32_t* __restrict__ counts,
+                                  int G, int C, int k, uint64_t* __restrict__ keys) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(G) * C * k;
   if (i >= total) return;
@@ -244,14 +246,18 @@ __global__ void merge_keys_kernel(const float* __restrict__ scores, const int64_
   const int c = static_cast<int>((i / k) % C);
   const int g = static_cast<int>(i / (static_cast<size_t>(k) * C));
   uint64_t key = 0;
-  if (j < counts[g * C + c]) key = make_key(scores[i] + 0.0f, static_cast<uint32_t>(rows[i]));
+  if (j < counts[g * C + c] && (aux == nullptr || aux[i] >= aux_thr)) key = make_key(scores[i] + 0.0f, static_cast<uint32_t>(rows[i]));
   keys[(static_cast<size_t>(c) * G + g) * k + j] = key;
 }
 
+// Global accept walk over the shards' candidate lists: the k_out best predicate-passing entries
+// under (score desc, row asc).  A shard whose list was truncated may hold unseen rows below its
+// last candidate; the result is proven exact only if it stays at or above every such frontier.
 __global__ void __launch_bounds__(kSelThreads)
-merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ aux, int G, int C, int k,
-             float* __restrict__ out_scores, int64_t* __restrict__ out_rows, float* __restrict__ out_aux,
-             int32_t* __restrict__ out_counts) {
+merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores, const int64_t* __restrict__ rows,
+             const float* __restrict__ aux, const int32_t* __restrict__ counts, const int32_t* __restrict__ truncated,
+             int G, int C, int k, int k_out, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+             float* __restrict__ out_aux, int32_t* __restrict__ out_counts, int32_t* __restrict__ incomplete) {
   __shared__ uint64_t s_keys[kSortCap];
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_misc[4];
@@ -266,19 +272,35 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ aux, i
   if (v) atomicAdd(&s_valid, v);
   __syncthreads();
   const uint32_t valid = s_valid;
-  const uint32_t total = select_sorted(kc, n, static_cast<uint32_t>(k), s_keys, s_hist, s_misc);
-  const uint32_t cnt = min(min(static_cast<uint32_t>(k), total), valid);
-  for (uint32_t i = tid; i < static_cast<uint32_t>(k); i += kSelThreads) {
+  const uint32_t total = select_sorted(kc, n, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
+  const uint32_t cnt = min(min(static_cast<uint32_t>(k_out), total), valid);
+  for (uint32_t i = tid; i < static_cast<uint32_t>(k_out); i += kSelThreads) {
     const bool ok = i < cnt;
     const uint64_t key = ok ? s_keys[i] : 0ull;
-    out_scores[static_cast<size_t>(c) * k + i] = ok ? key_score(key) : 0.0f;
-    out_rows[static_cast<size_t>(c) * k + i] = ok ? static_cast<int64_t>(key_row(key)) : -1;
-    if (out_aux && !ok) out_aux[static_cast<size_t>(c) * k + i] = 0.0f;
+    out_scores[static_cast<size_t>(c) * k_out + i] = ok ? key_score(key) : 0.0f;
+    out_rows[static_cast<size_t>(c) * k_out + i] = ok ? static_cast<int64_t>(key_row(key)) : -1;
+    if (out_aux && !ok) out_aux[static_cast<size_t>(c) * k_out + i] = 0.0f;
   }
-  if (tid == 0) out_counts[c] = static_cast<int32_t>(cnt);
+  if (tid == 0) {
+    out_counts[c] = static_cast<int32_t>(cnt);
+    if (incomplete) {
+      uint64_t frontier = 0;
+      if (truncated) {
+        for (int g = 0; g < G; ++g) {
+          const int m = counts[g * C + c];
+          if (truncated[g * C + c] && m > 0) {
+            const size_t last = (static_cast<size_t>(g) * C + c) * k + (m - 1);
+            const uint64_t fk = make_key(scores[last] + 0.0f, static_cast<uint32_t>(rows[last]));
+            frontier = fk > frontier ? fk : frontier;
+          }
+        }
+      }
+      incomplete[c] = (frontier != 0ull && (cnt < static_cast<uint32_t>(k_out) || s_keys[cnt - 1] < frontier)) ? 1 : 0;
+    }
+  }
   if (out_aux && aux) {
-    // route each surviving entry's aux value (e.g. its T2I score) to its merged position:
-    // keys are unique, binary-search the descending sorted list
+    // route each surviving entry's aux value (its T2I score) to its merged position: keys are
+    // unique, binary-search the descending sorted list
     for (uint32_t i = tid; i < n; i += kSelThreads) {
       const uint64_t key = kc[i];
       if (key == 0ull) continue;
@@ -289,7 +311,7 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ aux, i
       }
       if (lo < cnt && s_keys[lo] == key) {
         const int g = static_cast<int>(i / k), j = static_cast<int>(i % k);
-        out_aux[static_cast<size_t>(c) * k + lo] = aux[(static_cast<size_t>(g) * C + c) * k + j];
+        out_aux[static_cast<size_t>(c) * k_out + lo] = aux[(static_cast<size_t>(g) * C + c) * k + j];
       }
     }
   }
@@ -322,17 +344,19 @@ cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
-                         int n_shards, int n_classes, int k, uint64_t* d_key_scratch, float* d_out_scores,
-                         int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts, cudaStream_t stream) {
+cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, float aux_thr,
+                         const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int n_classes, int k, int k_out,
+                         uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
+                         int32_t* d_out_counts, int32_t* d_incomplete, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(n_shards) * n_classes * k;
   if (total == 0) return cudaSuccess;
-  merge_keys_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(d_scores, d_rows, d_counts, n_shards,
-                                                                                  n_classes, k, d_key_scratch);
+  merge_keys_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(d_scores, d_rows, d_aux, aux_thr, d_counts,
+                                                                                  n_shards, n_classes, k, d_key_scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_aux, n_shards, n_classes, k, d_out_scores,
-                                                      d_out_rows, d_out_aux, d_out_counts);
+  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_scores, d_rows, d_aux, d_counts, d_truncated, n_shards,
+                                                      n_classes, k, k_out, d_out_scores, d_out_rows, d_out_aux, d_out_counts,
+                                                      d_incomplete);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,120 @@
+"""Row-sharded multi-GPU retrieval: one process per GPU, each rank scans its own
+contiguous range of bank rows, then ONE gather of the per-class candidate lists and a merge.
+
+The reference has no distributed code at all (single process, single GPU,
+``sample_retrieval.py:1737``); the sharding follows from the algorithm: rows are independent and the
+per-class top-k under (score desc, row asc) is associative.  For the T2I walk
+(``add_t2t_ranked_t2i_tshd_to_split`` :492-540) the ranks exchange *candidates* (T2T top-k_fetch with
+their T2I score), not locally walked results: the accept walk runs once, globally, in the merge, and
+the merge proves exactness against each truncated shard's frontier.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced split: rank r owns rows [start, end)."""
+    base, rem = divmod(int(n_rows), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_threshold: float = 0.0,
+                     t2i_bank: Optional[torch.Tensor] = None, row_offset: int = 0,
+                     row_class: Optional[torch.Tensor] = None, exclude: Optional[torch.Tensor] = None):
+    """This shard's T2T top-``k_fetch`` per class (global row ids) with the T2I score of every
+    candidate.  Returns ``(scores, rows, t2i | None, counts, truncated)`` on the device."""
+    cap = None
+    for _ in range(6):
+        job = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
+        job.scan(t2t_bank, row_base=0, row_class=row_class, exclude=exclude)
+        scores, rows, counts, trunc = job.select()
+        over = job.overflowed()
+        job.close()
+        if not over:
+            break
+        cap = (cap or 32768) * 4
+        ctx.set_option("cand_cap", cap)
+    else:
+        raise _lib.SwatError(-4, "candidate buffers keep overflowing")
+    if cap is not None:
+        ctx.set_option("cand_cap", 0)
+    t2i = None
+    if t2i_bank is not None:
+        # threshold -inf and k == k_fetch: every candidate is kept in order, we only want its T2I score
+        scores, rows, t2i, counts, _ = _lib.t2i_walk(ctx, queries, t2i_bank, scores, rows, counts, None, k_fetch,
+                                                     float("-inf"), img_row_base=0)
+    rows = torch.where(rows >= 0, rows + int(row_offset), rows)
+    return scores, rows, t2i, counts, trunc
+
+
+def pack(scores, rows, t2i, counts, trunc) -> torch.Tensor:
+    """One int32 buffer per rank so the exchange is a single collective."""
+    parts = [rows.contiguous().view(torch.int32).flatten(), scores.contiguous().view(torch.int32).flatten()]
+    if t2i is not None:
+        parts.append(t2i.contiguous().view(torch.int32).flatten())
+    parts += [counts.to(torch.int32).flatten(), trunc.to(torch.int32).flatten()]
+    return torch.cat(parts)
+
+
+def unpack(buf: torch.Tensor, world: int, n_classes: int, k_fetch: int, with_t2i: bool):
+    buf = buf.view(world, -1)
+    n = n_classes * k_fetch
+    o = 0
+    rows = buf[:, o:o + 2 * n].contiguous().view(torch.int64).view(world, n_classes, k_fetch); o += 2 * n
+    scores = buf[:, o:o + n].contiguous().view(torch.float32).view(world, n_classes, k_fetch); o += n
+    t2i = None
+    if with_t2i:
+        t2i = buf[:, o:o + n].contiguous().view(torch.float32).view(world, n_classes, k_fetch); o += n
+    counts = buf[:, o:o + n_classes].contiguous(); o += n_classes
+    trunc = buf[:, o:o + n_classes].contiguous()
+    return scores, rows, t2i, counts, trunc
+
+
+def gather_merge(local, k: int, t2i_threshold: float, world: int, ctx=None, group=None,
+                 merge_fn: Optional[Callable] = None):
+    """Single all-gather of the packed candidate lists (NCCL over NVLink on GPUs, gloo in the CPU
+    tests), then the merge walk.  ``merge_fn(scores, rows, t2i, counts, trunc, k, thr)`` replaces the
+    CUDA merge in the CPU tests.  Returns ``(scores, rows, t2i | None, counts, incomplete)``."""
+    import torch.distributed as dist
+    scores, rows, t2i, counts, trunc = local
+    n_classes, k_fetch = scores.shape
+    mine = pack(scores, rows, t2i, counts, trunc)
+    if world > 1:
+        out = torch.empty(world * mine.numel(), dtype=torch.int32, device=mine.device)
+        dist.all_gather_into_tensor(out, mine, group=group)
+    else:
+        out = mine
+    g_scores, g_rows, g_t2i, g_counts, g_trunc = unpack(out, world, n_classes, k_fetch, t2i is not None)
+    thr = t2i_threshold if t2i is not None else float("-inf")
+    if merge_fn is not None:
+        return merge_fn(g_scores, g_rows, g_t2i, g_counts, g_trunc, k, thr)
+    return _lib.merge_topk(ctx, g_scores, g_rows, g_counts, aux=g_t2i, truncated=g_trunc, k_out=k, aux_threshold=thr)
+
+
+def topk_sharded(ctx, queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: float = 0.0,
+                 t2i_bank: Optional[torch.Tensor] = None, t2i_threshold: float = 0.25, row_offset: int = 0,
+                 world: int = 1, group=None, k_fetch: Optional[int] = None, max_k_fetch: int = 4096):
+    """Whole multi-GPU pipeline for this rank's shard.  Every rank returns the merged result.
+    Escalates ``k_fetch`` (x4, collectively) while any class is not provably exact."""
+    if k_fetch is None:
+        # T2T only: the merged top-k never reaches below a shard's k-th candidate, k suffices.
+        # T2I walk: over-fetch so that k candidates pass the predicate above every shard's frontier.
+        k_fetch = k if t2i_bank is None else max(1024, 2 * k)
+    k_fetch = max(1, min(int(k_fetch), max_k_fetch))
+    while True:
+        local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset)
+        res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
+        incomplete = int(res[4].sum().item())
+        if incomplete == 0 or k_fetch >= max_k_fetch:
+            if incomplete:
+                raise _lib.SwatError(-5, f"{incomplete} classes not provably exact at k_fetch={k_fetch}; "
+                                         "use the single-GPU in-pass predicate (swat_topk) for this data")
+            return res
+        k_fetch = min(max_k_fetch, k_fetch * 4)

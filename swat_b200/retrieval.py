@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's retrieval hot path, same names / arguments / return
+structures as ``/root/reference/retrieval/sample_retrieval.py`` (file:line below), backed by the
+C-ABI CUDA library.  A SWAT maintainer switches with::
+
+    from swat_b200.retrieval import (t2t_similarity, cal_t2i_similarity, transform_extracted_fea,
+                                     t2t_ranked_sampler, t2t_ranked_t2i_tshd_sampler)
+
+What changes underneath: instead of one GEMV + Python ``sorted`` + walk per class, all classes are
+scored against the whole bank in one tcgen05 scan with the selection fused in, and only the
+<= C*k winners ever come back to the host.  No CPU fallback: without the library or a GPU every
+function raises.
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+import shutil
+from collections import defaultdict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_CTX: Dict[int, "_lib.Context"] = {}
+
+
+def get_context(device: int = 0) -> "_lib.Context":
+    if device not in _CTX:
+        _CTX[device] = _lib.Context(device)
+    return _CTX[device]
+
+
+# ---------------------------------------------------------------------------------------------
+# S1 primitives (kept for drop-in compatibility; they materialise N scores, the samplers do not)
+# ---------------------------------------------------------------------------------------------
+def _dense(class_prompt: torch.Tensor, embeddings: torch.Tensor, reduce: str) -> List[float]:
+    ctx = get_context()
+    q = torch.as_tensor(class_prompt).detach().float()
+    if q.dim() == 1:
+        q = q[None, :]
+    x = torch.as_tensor(embeddings).detach()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if x.dim() == 1:
+        x = x[None, :]
+    R = q.shape[0]
+    qs = _lib.Queries(ctx, q, np.zeros(R, np.int32), 1, reduce if R > 1 else "none")
+    s = _lib.scores_dense(ctx, qs, x.contiguous().cuda(ctx.device))
+    result = s.squeeze().cpu().tolist()
+    if isinstance(result, float):          # single row -> 1-element list (:413-414)
+        result = [result]
+    qs.close()
+    return result
+
+
+def t2t_similarity(class_prompt, caption_embeddings) -> List[float]:
+    """``t2t_similarity`` (:397-416): ``X @ q^T``, mean over prompt rows when R > 1."""
+    return _dense(class_prompt, caption_embeddings, "mean")
+
+
+def cal_t2i_similarity(class_prompt, img_embeddings) -> List[float]:
+    """``cal_t2i_similarity`` (:335-353)."""
+    return _dense(class_prompt, img_embeddings, "mean")
+
+
+def i2i_similarity_p2p(fewshot_embedding, img_embeddings, mode: str) -> List[float]:
+    """``i2i_similarity_p2p`` (:369-394): min / max / mean over the few-shot columns."""
+    if mode not in ("min", "max", "mean"):
+        raise ValueError("Invalid mode type.")
+    f = torch.from_numpy(np.stack(fewshot_embedding)) if not torch.is_tensor(fewshot_embedding) else fewshot_embedding
+    return _dense(f, img_embeddings, mode)
+
+
+# ---------------------------------------------------------------------------------------------
+# loader / regrouper
+# ---------------------------------------------------------------------------------------------
+class RegroupedFeats(dict):
+    """What ``transform_extracted_fea`` returns: ``{str(label): {'file_paths', 'feats',
+    'caption_feats'}}`` with keys in first-appearance order -- built lazily per class -- plus the
+    flat row-major tensors the fused sampler consumes directly (``flat``)."""
+
+    def __init__(self, raw: dict):
+        super().__init__()
+        self.flat = raw
+        labels = torch.as_tensor(raw["labels"]).cpu().long()
+        self.labels = labels
+        order = torch.argsort(labels, stable=True)
+        sorted_labels = labels[order]
+        uniq, counts = torch.unique_consecutive(sorted_labels, return_counts=True)
+        ends = torch.cumsum(counts, 0)
+        starts = ends - counts
+        first_row = order[starts]                       # first appearance of each label (stable sort)
+        appear = torch.argsort(first_row)
+        self._rows = {}
+        for i in appear.tolist():                       # first-appearance order (:1401-1402)
+            key = str(int(uniq[i]))
+            self._rows[key] = order[starts[i]:ends[i]]
+            dict.__setitem__(self, key, None)
+
+    def rows_of(self, key: str) -> torch.Tensor:
+        return self._rows[key]
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if v is None:
+            rows = self._rows[key]
+            paths = self.flat["filepath"]
+            v = {"file_paths": [paths[i] for i in rows.tolist()],
+                 "feats": torch.as_tensor(self.flat["image_features"])[rows],
+                 "caption_feats": torch.as_tensor(self.flat["caption_features"])[rows]}
+            dict.__setitem__(self, key, v)
+        return v
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
+def transform_extracted_fea(pre_extracted_feats: dict) -> RegroupedFeats:
+    """``transform_extracted_fea`` (:1387-1415) without the per-row Python loop: one stable argsort
+    of the labels; per-class entries are materialised only when somebody indexes them."""
+    out = RegroupedFeats(pre_extracted_feats)
+    print("len(collection_dict):", len(out))             # the reference prints this (:1408)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# samplers
+# ---------------------------------------------------------------------------------------------
+def _flatten(pre_extracted_feats, classes: List[str]):
+    """Return (caption [N,512], image [N,512], paths, row_class int32 [N] or None)."""
+    if isinstance(pre_extracted_feats, RegroupedFeats):
+        raw = pre_extracted_feats.flat
+        labels = pre_extracted_feats.labels
+        lut = {int(c): i for i, c in enumerate(classes)}
+        uniq = torch.unique(labels)
+        table = torch.full((int(uniq.max()) + 1 if uniq.numel() else 1,), -1, dtype=torch.int32)
+        neg = uniq[uniq < 0]
+        if neg.numel():
+            raise ValueError("negative labels are not supported")
+        for u in uniq.tolist():
+            table[u] = lut.get(int(u), -1)
+        return (torch.as_tensor(raw["caption_features"]), torch.as_tensor(raw["image_features"]), raw["filepath"],
+                table[labels].contiguous())
+    first = pre_extracted_feats[classes[0]]
+    aliased = all(pre_extracted_feats[c]["caption_feats"] is first["caption_feats"] and
+                  pre_extracted_feats[c]["file_paths"] is first["file_paths"] for c in classes)
+    if aliased:                                           # unpartitioned: every class scans the whole bank
+        return first["caption_feats"], first["feats"], first["file_paths"], None
+    caps, imgs, paths, rc = [], [], [], []
+    for i, c in enumerate(classes):                        # the reference's regrouped dict: concatenate
+        e = pre_extracted_feats[c]
+        if e["file_paths"] is None:
+            continue
+        caps.append(torch.as_tensor(e["caption_feats"])); imgs.append(torch.as_tensor(e["feats"]))
+        paths.extend(e["file_paths"])
+        rc.append(torch.full((len(e["file_paths"]),), i, dtype=torch.int32))
+    return torch.cat(caps), torch.cat(imgs), paths, torch.cat(rc)
+
+
+def _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_images_dict):
+    sets = {}
+    for d in (duplicates_dict, filtered_images_dict):
+        if d:
+            for k, v in d.items():
+                if v:
+                    sets.setdefault(str(k), set()).update(v)
+    if not sets:
+        return None
+    if row_class is None:
+        raise NotImplementedError("per-class exclusion sets need the partitioned layout (one class per row)")
+    index = {p: i for i, p in enumerate(paths)}
+    ex = np.zeros(len(paths), dtype=bool)
+    for k, v in sets.items():
+        for p in v:
+            i = index.get(p)
+            if i is not None and classes[int(row_class[i])] == k:
+                ex[i] = True
+    bits = np.packbits(ex, bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)]).view(np.int32)
+    return torch.from_numpy(bits.copy())
+
+
+def check_caption(caption_map, img_path):
+    """``check_caption`` (:485-490)."""
+    img_cls = img_path.split('/')[-2]
+    img_id = img_path.split('/')[-1].split('.')[0]
+    return caption_map[img_cls][img_id]
+
+
+def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                 filtered_images_dict, with_t2i: bool, t2i_threshold: float = 0.25):
+    classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))          # :734-735
+    cap, img, paths, row_class = _flatten(pre_extracted_feats, classes)
+    bank_dtype = getattr(args, "bank_dtype", None)
+    if bank_dtype in ("bf16", torch.bfloat16):
+        cap = cap.to(torch.bfloat16); img = img.to(torch.bfloat16)
+    elif cap.dtype not in (torch.float32, torch.bfloat16):
+        cap = cap.float(); img = img.float()
+    device = int(getattr(args, "device_index", 0))
+    ctx = get_context(device)
+    q = torch.stack([torch.as_tensor(prompt_tensors[c]["mean"]).detach().float().cpu().reshape(-1) for c in classes])  # :749
+    qs = _lib.Queries(ctx, q)
+    exclude = _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_images_dict)
+    t2i_bank = img if with_t2i else None
+    if cap.is_cuda:
+        res = _lib.topk(ctx, qs, cap.contiguous(), num_samples, threshold, t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(),
+                        t2i_threshold=t2i_threshold, row_class=None if row_class is None else row_class.cuda(device),
+                        exclude=None if exclude is None else exclude.cuda(device))
+        scores, rows, t2i, counts = [None if x is None else x.cpu() for x in res]
+    else:
+        scores, rows, t2i, counts = _lib.topk_host(ctx, qs, cap.contiguous(), num_samples, threshold,
+                                                  t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(),
+                                                  t2i_threshold=t2i_threshold, row_class=row_class, exclude=exclude)
+    qs.close()
+    caption_map = None
+    cmap_path = getattr(args, "caption_map_path", None)
+    if cmap_path is None:
+        try:
+            from .config import CAPTION_MAP_DICT
+            cmap_path = CAPTION_MAP_DICT.get(args.dataset)
+        except Exception:
+            cmap_path = None
+    if cmap_path and os.path.exists(cmap_path):
+        with open(cmap_path, "rb") as f:                                              # :730-732
+            caption_map = pickle.load(f)
+    mined_split = {"feature_list": [], "label_list": [], "file_list": []}
+    num_imgs_sampled_dict = {}
+    sampled_list: List[str] = []
+    img_host = img if not img.is_cuda else None
+    for i, cls in enumerate(classes):
+        n = int(counts[i])
+        num_imgs_sampled_dict[cls] = n
+        if n == 0:
+            continue                                                                  # :472-474
+        r = rows[i, :n]
+        files = [paths[j] for j in r.tolist()]
+        feats = (img_host[r] if img_host is not None else img[r.to(img.device)].cpu()).float()
+        mined_split["feature_list"].append(feats)
+        mined_split["label_list"].append(torch.full((n,), int(cls), dtype=torch.int64))
+        mined_split["file_list"].append(files)
+        sc = scores[i, :n].tolist()
+        ti = t2i[i, :n].tolist() if t2i is not None else None
+        for j, p in enumerate(files):
+            caption = check_caption(caption_map, p) if caption_map is not None else ""
+            if with_t2i:
+                sampled_list.append(f"{round(sc[j], 4)}/{threshold}, {round(ti[j], 4)}/{t2i_threshold}, {p}, {caption}")
+            else:
+                sampled_list.append(f"{round(sc[j], 4)}/{threshold}, {p}, {caption}")
+    logger.info(f"len(sampled_list): {len(sampled_list)}")
+    prefix = "" if with_t2i else f"{args.prefix}_"                                     # :763,768 vs :817,822
+    os.makedirs(args.output_folder, exist_ok=True)
+    with open(f"{args.output_folder}/{prefix}sampled_list.txt", "w") as f:
+        f.write("\n".join(sampled_list))
+    return mined_split, num_imgs_sampled_dict
+
+
+def t2t_ranked_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                       duplicates_dict: defaultdict = defaultdict(set), filtered_images_dict: defaultdict = defaultdict(set)):
+    """``t2t_ranked_sampler`` (:724-771): per class the top ``num_samples`` rows by T2T cosine with
+    ``similarity >= threshold``, ties by lowest row."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=False)
+
+
+def t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                                duplicates_dict: defaultdict = defaultdict(set),
+                                filtered_images_dict: defaultdict = defaultdict(set)):
+    """``t2t_ranked_t2i_tshd_sampler`` (:774-825): walk rows in T2T-descending order, accept iff
+    ``T2T >= threshold`` and ``T2I >= 0.25`` (:511-514), stop at ``num_samples``."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=True, t2i_threshold=0.25)
+
+
+# ---------------------------------------------------------------------------------------------
+# output writer + orchestration tail
+# ---------------------------------------------------------------------------------------------
+def save_sample_file_list(args, final_file_list, label_tensor, logger=None, copy_to: Optional[str] = None):
+    """``save_sample_file_list`` (:1457-1469): ``"<path> <label> 0\\n"`` per accepted row."""
+    fn = f"{args.output_folder}/{args.prefix}.txt"
+    labels = torch.as_tensor(label_tensor).tolist()
+    with open(fn, "w") as f:
+        f.write("".join(f"{p} {l} {0}\n" for p, l in zip(final_file_list, labels)))
+    if logger:
+        logger.info(f"Saved file_list to: {fn}")
+    if copy_to:
+        os.makedirs(copy_to, exist_ok=True)
+        shutil.copy(fn, copy_to)
+        if logger:
+            logger.info(f"Copied file to: {copy_to}")
+    return fn
+
+
+def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=None, copy_to: Optional[str] = None):
+    """The hot part of ``sampling`` (:1471-1670): load + regroup the mined features, dispatch on
+    ``args.sampling_method`` (T2T-rank :1571-1579, T2T-rank-T2I-tshd :1581-1589), write
+    ``{prefix}.txt`` and ``{prefix}_num_imgs_sampled.json``.  Returns ``(file_list_path, sample_ct)``."""
+    if pre_extracted_feats is None:
+        fn = f"{dataset_root}/{args.dataset}_{args.model_cfg}_mined.pth"
+        if not os.path.exists(fn):
+            logger.info(f"Error: Pre-extracted features not found. {fn}")
+            raise NotImplementedError                                               # :1478-1479
+        from .shards import load_mined_pth
+        pre_extracted_feats = load_mined_pth(fn)
+        logger.info(f"Loaded pre-extracted mined features from: {fn}")
+    feats = transform_extracted_fea(pre_extracted_feats) if "labels" in pre_extracted_feats else pre_extracted_feats
+    logger.info(f"Sampling method: {args.sampling_method}, sampling number: {args.num_samples}, "
+                f"sampling threshold: {args.sampling_threshold}")
+    if args.sampling_method == "T2T-rank":
+        mined_split, num_imgs_sampled_dict = t2t_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "T2T-rank-T2I-tshd":
+        mined_split, num_imgs_sampled_dict = t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    else:
+        raise NotImplementedError(f"sampling method {args.sampling_method} is outside the accelerated hot path")
+    final_file_list = [p for fl in mined_split["file_list"] for p in fl]
+    logger.info(f"len(final_file_list): {len(final_file_list)}")
+    labels_tensor = torch.cat(mined_split["label_list"], dim=0) if mined_split["label_list"] else torch.zeros(0, dtype=torch.int64)
+    if mined_split["feature_list"]:
+        feature_tensor = torch.cat(mined_split["feature_list"], dim=0)
+        logger.info(f"feature_tensor.shape: {feature_tensor.shape}")
+    logger.info(f"labels_tensor.shape: {labels_tensor.shape}")
+    file_list_path = save_sample_file_list(args, final_file_list, labels_tensor, logger, copy_to)
+    with open(f"{args.output_folder}/{args.prefix}_num_imgs_sampled.json", "w") as f:
+        json.dump(num_imgs_sampled_dict, f, indent=4)                               # :1666-1668
+    return file_list_path, len(final_file_list)

@@ -212,21 +212,43 @@ def test_host_pipeline_equals_resident(lib, ctx2):
 
 
 def test_merge_and_shard_invariance(lib, ctx2):
-    """Row-sharded scan + merge equals the single-shard result for any shard count."""
-    from swat_b200 import synth
+    """Row-sharded scan + one gather + merge equals the single-shard result for any shard count
+    (SURVEY 8e), bit for bit.  T2T-only shards exchange their top-k; with the T2I walk they exchange
+    candidates and the accept walk runs in the merge (swat_b200/dist.py)."""
+    from swat_b200 import dist, synth
     qc, queries, _ = synth.make_queries(30, 1, seed=41, dtype=torch.bfloat16)
     cap, img, _ = synth.make_bank(90_000, qc, seed=41, dtype=torch.bfloat16, rho=0.2, tie_block=500, chunk=1 << 16)
     qs = lib.Queries(ctx2, queries.float())
     d_cap, d_img = cap.cuda(), img.cuda()
+    full_t2t = lib.topk(ctx2, qs, d_cap, 250, 0.0)
     full = lib.topk(ctx2, qs, d_cap, 250, 0.0, t2i_bank=d_img)
-    for G in (2, 3, 8):
-        bounds = np.linspace(0, 90_000, G + 1).astype(int)
-        parts = [lib.topk(ctx2, qs, d_cap[a:b], 250, 0.0, t2i_bank=d_img[a:b], row_offset=int(a)) for a, b in zip(bounds[:-1], bounds[1:])]
-        s = torch.stack([p[0] for p in parts]); r = torch.stack([p[1] for p in parts])
-        t = torch.stack([p[2] for p in parts]); c = torch.stack([p[3] for p in parts])
-        ms, mr, mt, mc = lib.merge_topk(ctx2, s, r, c, aux=t)
-        assert torch.equal(mr, full[1]) and torch.equal(mc, full[3]), f"G={G}"
+    assert ctx2.last_timing()["escalations"] == 0
+    for G in (1, 2, 3, 8):
+        bounds = [dist.shard_range(90_000, r, G) for r in range(G)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == 90_000 and all(a[1] == b[0] for a, b in zip(bounds[:-1], bounds[1:]))
+        # T2T only
+        parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 250, 0.0, None, row_offset=a) for a, b in bounds]
+        buf = torch.cat([dist.pack(*p) for p in parts])
+        s, r, t, c, tr = dist.unpack(buf, G, 30, 250, False)
+        ms, mr, mt, mc, inc = lib.merge_topk(ctx2, s, r, c, truncated=tr, k_out=250)
+        assert torch.equal(mr, full_t2t[1]) and torch.equal(mc, full_t2t[3]) and torch.equal(ms, full_t2t[0]), f"T2T G={G}"
+        assert int(inc.sum()) == 0
+        # T2I walk over gathered candidates
+        parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 1024, 0.0, d_img[a:b], row_offset=a) for a, b in bounds]
+        buf = torch.cat([dist.pack(*p) for p in parts])
+        s, r, t, c, tr = dist.unpack(buf, G, 30, 1024, True)
+        ms, mr, mt, mc, inc = lib.merge_topk(ctx2, s, r, c, aux=t, truncated=tr, k_out=250, aux_threshold=0.25)
+        assert int(inc.sum()) == 0, f"G={G}"
+        assert torch.equal(mr, full[1]) and torch.equal(mc, full[3]), f"T2I G={G}"
         assert torch.equal(ms, full[0]) and torch.equal(mt, full[2])
+    # a frontier violation must be reported: k_fetch too small to find 250 passing rows
+    parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 64, 0.0, d_img[a:b], row_offset=a) for a, b in bounds]
+    s, r, t, c, tr = dist.unpack(torch.cat([dist.pack(*p) for p in parts]), 8, 30, 64, True)
+    inc = lib.merge_topk(ctx2, s, r, c, aux=t, truncated=tr, k_out=250, aux_threshold=0.25)[4]
+    assert int(inc.sum()) > 0
+    # single-process world: the whole sharded pipeline
+    res = dist.topk_sharded(ctx2, qs, d_cap, 250, 0.0, t2i_bank=d_img, world=1)
+    assert torch.equal(res[1], full[1]) and torch.equal(res[0], full[0])
 
 
 def test_streaming_job_matches_single_view(lib, ctx2):
