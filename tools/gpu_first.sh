@@ -11,4 +11,4 @@ timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -
 echo "exit $?" >> gpurun_out/pytest_dense.log
 timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "not dense" > gpurun_out/pytest_rest.log 2>&1
 echo "exit $?" >> gpurun_out/pytest_rest.log
-tail -5 gpurun_out/first.log gpurun_out/pytest_dense.log gpurun_out/pytest_rest.log
+for f in first pytest_dense pytest_rest; do tail -n 5 gpurun_out/$f.log; done
