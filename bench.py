@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- the retrieval hot path on N B200s (BASELINE.json metric: bank rows scored + top-k'd / s).
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm
+    python bench.py --impl reference [...]                      # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): semi-aves, C = Q = 200 class prompts, full T2T500+T2I0.25
+pipeline over a synthetic 10 M x 512 bf16 caption + image bank PER GPU (weak scaling; rows are
+sharded over the ranks and the per-class candidates merged after one NCCL all-gather).
+One step = one pass of the whole pipeline (scan + select + T2I walk [+ gather + merge]) over the bank.
+
+`value`  : rows/s with the banks resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : rows/s through the C-ABI host entry point (swat_topk_host): banks in pinned host memory,
+           H2D of the caption bank and of the candidates' image rows and D2H of the result inside
+           the timed region.  For N > 1 the shard is copied H2D (both banks) and the resident
+           sharded pipeline runs, all inside the timed region.
+`roofline`: scan kernel, HBM bound for Q <= 209: 1 KB/row over the measured copy
+           bandwidth in MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "bank_rows_scored_topk_per_sec"
+UNIT = "rows/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000, help="bank rows per GPU")
+    ap.add_argument("--classes", type=int, default=200)
+    ap.add_argument("--k", type=int, default=500)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--t2t-only", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a, world):
+    return (f"semi-aves C={a.classes} Q={a.classes} {'T2T' if a.t2t_only else 'T2T+T2I0.25'} top-{a.k}, "
+            f"{a.rows} x 512 bf16 caption+image rows per GPU, {world} GPU(s)")
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(a, n_rows, seed_shift=0):
+    import torch
+    from swat_b200 import synth
+    qc, queries, _ = synth.make_queries(a.classes, 1, seed=a.seed, dtype=torch.bfloat16)
+    cap, img, _ = synth.make_bank(n_rows, qc, seed=a.seed + seed_shift, dtype=torch.bfloat16, chunk=1 << 16,
+                                  tie_block=min(1000, n_rows // 8), with_images=not a.t2t_only)
+    return queries.float().numpy(), cap.float().numpy(), None if img is None else img.float().numpy()
+
+
+def cpu_vectorised(a, budget_s=12.0):
+    """fp32 GEMM + exact tie-aware selection on all host cores (oracle.topk_walk)."""
+    from oracle import swat_oracle as so
+    n = 100_000
+    q, cap, img = cpu_sample(a, n)
+    t0 = time.perf_counter()
+    so.topk_walk(cap[:20_000], q, a.k, 0.0, t2i_bank=None if img is None else img[:20_000])
+    per_row = (time.perf_counter() - t0) / 20_000
+    n_use = int(max(20_000, min(n, budget_s / max(per_row, 1e-9))))
+    t0 = time.perf_counter()
+    so.topk_walk(cap[:n_use], q, a.k, 0.0, t2i_bank=None if img is None else img[:n_use])
+    dt = time.perf_counter() - t0
+    return n_use / dt, f"{n_use} rows x {a.classes} classes, vectorised fp32 GEMM + selection, {dt:.1f} s"
+
+
+def cpu_verbatim(a, n_rows, n_cls=None):
+    """The reference's algorithm as written (per class: GEMV, Python sorted on zipped tuples, accept
+    walk; sample_retrieval.py:774-825), unpartitioned: every class scans the whole sample."""
+    from oracle import swat_oracle as so
+    q, cap, img = cpu_sample(a, n_rows)
+    if img is None:
+        img = cap
+    C = a.classes if n_cls is None else n_cls
+    paths = [f"/s/{i % C}/{i}.jpg" for i in range(n_rows)]
+    feats = {str(c): {"file_paths": paths, "feats": img, "caption_feats": cap} for c in range(C)}
+    prompts = {str(c): {"mean": q[c]} for c in range(C)}
+    fn = so.verbatim_t2t_ranked_sampler if a.t2t_only else so.verbatim_t2t_ranked_t2i_tshd_sampler
+    t0 = time.perf_counter()
+    fn(prompts, a.k, 0.0, feats)
+    dt = time.perf_counter() - t0
+    return dt * (a.classes / C), dt
+
+
+def run_reference(a, rank, world):
+    """--impl reference: the reference's own CPU path for this workload, timed on the host cores.
+    /root/reference is Python + needs open_clip stubs and does not exist on the GPU box, so the arm
+    runs the oracle's verbatim port (kind = "port")."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    total_steps = a.steps + a.warmup
+    budget = 150.0 / max(total_steps, 1)                       # seconds per step
+    n_rows = 2048
+    est, _ = cpu_verbatim(a, n_rows, n_cls=8)                   # calibrate on 8 classes
+    n_rows = int(max(1024, min(200_000, n_rows * budget / max(est, 1e-6))))
+    for _ in range(a.warmup):
+        cpu_verbatim(a, n_rows)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_verbatim(a, n_rows)
+    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    value = n_rows / dt
+    vec, vec_sample = (None, None) if a.no_cpu else cpu_vectorised(a)
+    sample = f"{n_rows} rows x {a.classes} classes per step, unpartitioned, verbatim port of sample_retrieval.py:774-825"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a, a.gpus), "sample_rows": n_rows},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "vectorised_value": vec, "vectorised_sample": vec_sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from swat_b200 import _lib, synth
+    from swat_b200 import dist as sdist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _lib.Context(local_rank)
+    n_local = a.rows
+    row_offset = rank * n_local
+    qc, queries, _ = synth.make_queries(a.classes, 1, seed=a.seed, dtype=torch.bfloat16)
+    cap, img, _ = synth.make_bank(n_local, qc, seed=a.seed, device=dev, dtype=torch.bfloat16, chunk=1 << 20,
+                                  with_images=not a.t2t_only, row_offset=row_offset)
+    qs = _lib.Queries(ctx, queries.float())
+    k = a.k
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        if world == 1:
+            return _lib.topk(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset)
+        return sdist.topk_sharded(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset, world=world)
+
+    for _ in range(max(a.warmup, 3)):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms = []
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        res = step()
+        if world == 1:
+            scan_ms.append(ctx.last_timing()["scan_ms"])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total_rows = n_local * world
+    value = total_rows * a.steps / (ms * 1e-3)
+
+    # ---- scan-kernel roofline (rank 0's kernel; CUDA events on the launching stream)
+    hbm, tf, src = peaks()
+    if not scan_ms:                                     # multi-GPU path: time the scan alone, same stream
+        for _ in range(3):
+            job = _lib.Job(ctx, qs, 1024 if img is not None else k, 0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); job.scan(cap); e1.record(); torch.cuda.synchronize(dev)
+            scan_ms.append(e0.elapsed_time(e1)); job.close()
+    scan_ms.sort()
+    scan = scan_ms[len(scan_ms) // 2]
+    q_cols = a.classes
+    bytes_per_row = 1024.0
+    hbm_time = bytes_per_row / (hbm * 1e9)
+    tc_time = 2.0 * 512 * q_cols / (tf * 1e12)
+    if hbm_time >= tc_time:
+        achieved = n_local * bytes_per_row / (scan * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm}
+    else:
+        achieved = n_local * 2.0 * 512 * q_cols / (scan * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf}
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "scan_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof.update({"traffic": traffic, "peak_source": f"{src} (MEASURED_PEAKS.json burst copy bandwidth)", "kernel": "scan_tc_kernel",
+                 "kernel_ms": scan, "algorithmic_bytes_per_launch": n_local * bytes_per_row})
+
+    # ---- end to end through the C-ABI with host buffers
+    e2e = None
+    if not a.no_e2e:
+        h_cap = torch.empty(cap.shape, dtype=cap.dtype, pin_memory=True); h_cap.copy_(cap)
+        h_img = None
+        if img is not None:
+            h_img = torch.empty(img.shape, dtype=img.dtype, pin_memory=True); h_img.copy_(img)
+        torch.cuda.synchronize(dev)
+        steps_e = max(2, min(a.steps, 5))
+
+        def e2e_step():
+            if world == 1:
+                r = _lib.topk_host(ctx, qs, h_cap, k, 0.0, t2i_bank=h_img, t2i_threshold=0.25, row_offset=row_offset)
+                tm = ctx.last_timing()
+                return r, tm["h2d_bytes"], tm["d2h_bytes"]
+            cap.copy_(h_cap, non_blocking=True)
+            if img is not None:
+                img.copy_(h_img, non_blocking=True)
+            r = sdist.topk_sharded(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset, world=world)
+            out = [x.cpu() for x in r[:4] if x is not None]
+            h2d = cap.numel() * 2 * (2 if img is not None else 1)
+            return r, h2d, sum(x.numel() * x.element_size() for x in out)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps_e):
+            r, h2d, d2h = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_rows * steps_e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": int(d2h) * world, "steps": steps_e,
+               "api": "swat_topk_host (C-ABI, pinned host banks)" if world == 1 else "H2D shard copy + dist.topk_sharded"}
+        del h_cap, h_img
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        vec, vec_sample = cpu_vectorised(a)
+        est, dt8 = cpu_verbatim(a, 4096, n_cls=8)
+        cpu = {"value": vec, "unit": UNIT, "cores": cores, "kind": "port", "sample": vec_sample,
+               "verbatim_value": 4096 / est,
+               "verbatim_sample": f"4096 rows x 8 of {a.classes} classes scaled x{a.classes / 8:.0f}, verbatim port of "
+                                  f"sample_retrieval.py:774-825 ({dt8:.1f} s)"}
+    if rank == 0:
+        counts = res[3]
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "rows_per_gpu": n_local, "classes": a.classes, "k": k,
+                       "l2": "inputs (10 GB per bank per GPU) far larger than the 126 MB L2; no flush needed",
+                       "accepted_rows": int(counts.sum().item()), "escalations": ctx.last_timing()["escalations"]},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world != a.gpus and world == 1 and a.gpus > 1:
+        # launched without torchrun: re-exec under it (one rank per GPU over NCCL)
+        port = 29500 + os.getpid() % 1000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr",
+               "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

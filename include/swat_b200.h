@@ -64,7 +64,9 @@ const char* swat_last_error(void);
 /* One context per device.  Fails with SWAT_ERR_NO_DEVICE when the device is not sm_100. */
 int32_t swat_ctx_create(int32_t device, swat_ctx** out);
 int32_t swat_ctx_destroy(swat_ctx* ctx);
-/* tuning knobs (all optional): "cta_group" (1|2), "max_ctas", "cand_cap", "overfetch", "host_chunk_rows" */
+/* tuning knobs (all optional): "cta_group" (1|2, before swat_queries_create), "max_ctas", "cand_cap"
+ * (per-class candidates kept after the final threshold), "list_entries" (total survivor-list entries),
+ * "overfetch" (first k_fetch of the T2I walk), "host_chunk_rows"; 0 = automatic */
 int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value);
 /* counters since ctx creation: kernels launched by this library (bench.py's gpu_launches claim) */
 int64_t swat_ctx_launch_count(const swat_ctx* ctx);
@@ -101,8 +103,9 @@ int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t 
  * 1 = more than k_fetch rows were eligible, i.e. the list is a strict prefix of the walk). */
 int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t* d_counts,
                         int32_t* d_truncated, void* stream);
-/* Synchronises the stream the job last ran on; *overflowed = 1 if a candidate buffer overflowed
- * (results invalid; re-run with a larger "cand_cap"). */
+/* Synchronises the stream the job last ran on; *overflowed != 0 means the results are invalid:
+ * bit0 = a class candidate buffer overflowed (raise "cand_cap"), bit1 = a survivor list overflowed
+ * (raise "list_entries").  swat_topk / swat_topk_host retry by themselves. */
 int32_t swat_job_status(swat_job* job, int32_t* overflowed);
 int32_t swat_job_destroy(swat_job* job);
 

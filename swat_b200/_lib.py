@@ -217,10 +217,11 @@ class Job:
         _check(load().swat_job_select(self._h, _ptr(scores), _ptr(rows), _ptr(counts), _ptr(trunc), _stream(self.ctx.device)))
         return scores, rows, counts, trunc
 
-    def overflowed(self) -> bool:
+    def overflowed(self) -> int:
+        """0 = fine; bit0 = class candidate buffers ("cand_cap"), bit1 = survivor lists ("list_entries")."""
         o = C.c_int32(0)
         _check(load().swat_job_status(self._h, C.byref(o)))
-        return bool(o.value)
+        return int(o.value)
 
     def close(self):
         if self._h:

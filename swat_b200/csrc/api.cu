@@ -79,7 +79,8 @@ struct swat_ctx {
   // options
   int cta_group = 2;
   int max_ctas = 0;
-  int64_t cand_cap = 0;       // 0 = auto
+  int64_t cand_cap = 0;       // per-class candidate capacity after partition, 0 = auto
+  int64_t list_entries = 0;   // total survivor-list entries, 0 = auto
   int overfetch = 0;          // 0 = auto
   int64_t host_chunk_rows = 1 << 18;
   // stats
@@ -93,6 +94,7 @@ struct swat_ctx {
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_used[3] = {nullptr, nullptr, nullptr};
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
+  swat_job* cached_job = nullptr;   // job buffers are reused across whole-pipeline calls
 };
 
 struct swat_queries {
@@ -102,6 +104,8 @@ struct swat_queries {
   // unpadded (T2I re-score) and padded-by-Q-block (scan kernels) device copies
   float* d_q_f32 = nullptr; uint16_t* d_q_bf16 = nullptr; int32_t* d_class_begin = nullptr;
   float* d_qp_f32 = nullptr; uint16_t* d_qp_bf16 = nullptr; int32_t* d_col_class = nullptr; float* d_col_count = nullptr;
+  int32_t* d_blk_class = nullptr;     // [n_qb+1] first class of each Q block
+  std::vector<float> h_q;             // host copy (sub-query sets for targeted escalation)
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
   CUtensorMap tm_q;
 };
@@ -110,6 +114,7 @@ struct swat_job {
   swat_ctx* ctx = nullptr;
   const swat_queries* q = nullptr;
   JobState st;
+  int n_classes_alloc = 0;
   cudaStream_t last_stream = nullptr;
 };
 
@@ -195,9 +200,12 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     p.n_stages = q->n_stages;
     p.smem_b_bytes = static_cast<uint32_t>(8) * (q->n_blk / q->ctas) * 128;
     p.bank_hint = (q->n_qb == 1) ? 0x12F0000000000000ull /* evict_first: streamed once */ : 0x1000000000000000ull;
+    p.blk_class = q->d_blk_class;
     int grid = ctx->sm_count;
     if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
     grid = std::max(q->ctas, grid / q->ctas * q->ctas);
+    if (dense_out == nullptr && static_cast<uint32_t>(grid) * 4u > job->st.n_lists)
+      return fail(SWAT_ERR_INVALID, "grid of %d CTAs needs %d survivor lists, job has %u", grid, grid * 4, job->st.n_lists);
     CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
   } else {
     const void* qp = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_qp_bf16) : static_cast<const void*>(q->d_qp_f32);
@@ -209,26 +217,19 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
 
 int64_t auto_cap(const swat_ctx* ctx, int k_fetch) {
   if (ctx->cand_cap > 0) return ctx->cand_cap;
-  int64_t cap = 32768;
-  while (cap < 32ll * k_fetch) cap <<= 1;
-  return cap;
+  return 2ll * k_fetch + 4096;          // candidates at/above the final threshold: ~k_fetch + one histogram bin + ties
+}
+int64_t auto_list_entries(const swat_ctx* ctx, int n_classes, int k_fetch) {
+  if (ctx->list_entries > 0) return ctx->list_entries;
+  // survivors over a whole scan: ~k_fetch*(1 + ln(N/first wave)) per class plus the first-wave burst
+  const int64_t per_class = 12ll * std::max(k_fetch, 512) + 16384;
+  return std::max<int64_t>(4ll << 20, per_class * n_classes * 3 / 2);
 }
 
-int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, swat_job** out) {
-  if (!ctx || !q || !out) return fail(SWAT_ERR_INVALID, "null argument");
-  if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
-  if (thr != thr) return fail(SWAT_ERR_INVALID, "threshold is NaN");
-  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
-  CU_OK(cudaSetDevice(ctx->device));
-  swat_job* j = new swat_job();
-  j->ctx = ctx;
-  j->q = q;
-  const size_t C = static_cast<size_t>(q->C);
+void job_set_params(swat_job* j, const swat_queries* q, int32_t k_fetch, float thr) {
   JobState& st = j->st;
-  memset(&st, 0, sizeof(st));
-  st.cap = static_cast<uint32_t>(cap);
+  j->q = q;
   st.k_fetch = static_cast<uint32_t>(k_fetch);
-  st.refresh_every = static_cast<uint32_t>(std::max(32, k_fetch / 4));
   st.thr = thr;
   float lo = std::max(thr, -1.0f);
   float hi = std::max(1.0f, lo + 1.0f / 64.0f);
@@ -236,16 +237,62 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
   st.hist_lo = lo;
   st.hist_scale = static_cast<float>(kHistBins) / (hi - lo);
   st.hist_inv_scale = (hi - lo) / static_cast<float>(kHistBins);
+}
+
+int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, int64_t list_entries,
+                       swat_job** out) {
+  if (!ctx || !q || !out) return fail(SWAT_ERR_INVALID, "null argument");
+  if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
+  if (thr != thr) return fail(SWAT_ERR_INVALID, "threshold is NaN");
+  (void)cudaGetLastError();
+  CU_OK(cudaSetDevice(ctx->device));
+  swat_job* j = new swat_job();
+  j->ctx = ctx;
+  const size_t C = static_cast<size_t>(q->C);
+  j->n_classes_alloc = q->C;
+  JobState& st = j->st;
+  memset(&st, 0, sizeof(st));
+  st.cap = static_cast<uint32_t>(std::min<int64_t>(cap, 0x7fffffff));
+  st.n_lists = 1024;
+  const int64_t private_lists = std::max(1, ctx->sm_count) * 4ll;     // the tcgen05 kernel uses one list per epilogue warp
+  st.list_cap = static_cast<uint32_t>(std::min<int64_t>(((list_entries + private_lists - 1) / private_lists + 255) / 256 * 256, 0x7fffff00));
+  job_set_params(j, q, k_fetch, thr);
   cudaError_t e = cudaMalloc(&st.tau_enc, C * 4);
   if (e == cudaSuccess) e = cudaMalloc(&st.count, C * 4);
   if (e == cudaSuccess) e = cudaMalloc(&st.hist, C * kHistBins * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&st.cand, C * static_cast<size_t>(cap) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&st.cand, C * static_cast<size_t>(st.cap) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&st.list, static_cast<size_t>(st.n_lists) * st.list_cap * sizeof(uint4));
+  if (e == cudaSuccess) e = cudaMalloc(&st.list_count, static_cast<size_t>(st.n_lists) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&st.flags, 16);
   if (e != cudaSuccess) {
     swat_job_destroy(j);
-    return fail(SWAT_ERR_CUDA, "job allocation failed (C=%zu, cap=%lld): %s", C, (long long)cap, cudaGetErrorString(e));
+    return fail(SWAT_ERR_CUDA, "job allocation failed (C=%zu, cap=%lld, list entries=%lld): %s", C, (long long)cap,
+                (long long)list_entries, cudaGetErrorString(e));
   }
   *out = j;
+  return SWAT_OK;
+}
+
+// whole-pipeline calls reuse one job allocation per ctx as long as the sizes fit
+int32_t acquire_job(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, int64_t list_entries, swat_job** out) {
+  swat_job* j = ctx->cached_job;
+  const int64_t private_lists = std::max(1, ctx->sm_count) * 4ll;
+  if (j && j->n_classes_alloc >= q->C && j->st.cap >= cap && static_cast<int64_t>(j->st.list_cap) * private_lists >= list_entries) {
+    if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
+    job_set_params(j, q, k_fetch, thr);
+    *out = j;
+    return SWAT_OK;
+  }
+  if (j) { swat_job_destroy(j); ctx->cached_job = nullptr; }
+  SW_OK(job_create_cap(ctx, q, k_fetch, thr, cap, list_entries, &j));
+  ctx->cached_job = j;
+  *out = j;
+  return SWAT_OK;
+}
+
+int32_t job_flags(swat_job* job, uint32_t* flags) {
+  CU_OK(cudaMemcpyAsync(flags, job->st.flags, 4, cudaMemcpyDeviceToHost, job->last_stream));
+  CU_OK(cudaStreamSynchronize(job->last_stream));
   return SWAT_OK;
 }
 
@@ -326,74 +373,111 @@ int32_t ensure_pinned(swat_ctx* ctx, size_t bytes) {
   return SWAT_OK;
 }
 
+int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
+                     float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream,
+                     int32_t k_fetch_init, int depth);
+
+// Targeted escalation: re-run only the classes whose T2I walk could not be proven exact, with a
+// wider over-fetch (and finally the exact in-pass predicate), then splice their rows into the result.
+int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
+                         const std::vector<int>& classes, int32_t k_fetch_next, float* d_out_scores, int64_t* d_out_rows,
+                         float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream, int depth) {
+  const int n = static_cast<int>(classes.size());
+  std::vector<float> hq;
+  std::vector<int32_t> coq;
+  for (int i = 0; i < n; ++i) {
+    const int c = classes[i];
+    for (int qi = q->class_begin[c]; qi < q->class_begin[c + 1]; ++qi) {
+      hq.insert(hq.end(), q->h_q.begin() + static_cast<size_t>(qi) * kDim, q->h_q.begin() + static_cast<size_t>(qi + 1) * kDim);
+      coq.push_back(i);
+    }
+  }
+  swat_queries* sub = nullptr;
+  SW_OK(swat_queries_create(ctx, hq.data(), static_cast<int32_t>(coq.size()), coq.data(), n, q->reduce, &sub));
+  DevBuf o_s, o_r, o_t, o_c;
+  int32_t rc = o_s.ensure(static_cast<size_t>(n) * k * 4);
+  if (rc == SWAT_OK) rc = o_r.ensure(static_cast<size_t>(n) * k * 8);
+  if (rc == SWAT_OK) rc = o_t.ensure(static_cast<size_t>(n) * k * 4);
+  if (rc == SWAT_OK) rc = o_c.ensure(static_cast<size_t>(n) * 4);
+  if (rc == SWAT_OK)
+    rc = run_pipeline(ctx, sub, b, row_offset, k, thr, t2i_thr, o_s.as<float>(), o_r.as<int64_t>(), d_out_t2i ? o_t.as<float>() : nullptr,
+                      o_c.as<int32_t>(), stream, k_fetch_next, depth + 1);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < n && rc == SWAT_OK && e == cudaSuccess; ++i) {
+    const size_t c = classes[i];
+    e = cudaMemcpyAsync(d_out_scores + c * k, o_s.as<float>() + static_cast<size_t>(i) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_out_rows + c * k, o_r.as<int64_t>() + static_cast<size_t>(i) * k, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess && d_out_t2i) e = cudaMemcpyAsync(d_out_t2i + c * k, o_t.as<float>() + static_cast<size_t>(i) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_out_counts + c, o_c.as<int32_t>() + i, 4, cudaMemcpyDeviceToDevice, stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (rc == SWAT_OK && e != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "splicing escalated classes failed: %s", cudaGetErrorString(e));
+  o_s.release(); o_r.release(); o_t.release(); o_c.release();
+  swat_queries_destroy(sub);
+  return rc;
+}
+
 // The whole pipeline.  Results land in d_out_* (device).  See swat_topk / swat_topk_host.
 int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
-                     float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream) {
+                     float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream,
+                     int32_t k_fetch_init, int depth) {
   if (k < 1 || k > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k must be in [1, %d], got %d", kMaxKFetch, k);
   const int C = q->C;
   const bool want_t2i = b.t2i != nullptr;
-  for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
+  if (depth == 0) for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
   int32_t k_fetch = k;
+  bool dual = false;          // exact in-pass predicate fallback
   if (want_t2i) {
-    k_fetch = ctx->overfetch > 0 ? ctx->overfetch : std::max(2 * k, 1024);
+    if (k_fetch_init > kMaxKFetch) dual = true;   // escalation beyond the widest over-fetch
+    else if (k_fetch_init > 0) k_fetch = k_fetch_init;
+    else k_fetch = ctx->overfetch > 0 ? ctx->overfetch : std::max(2 * k, 1024);
     k_fetch = std::min(std::max(k_fetch, k), kMaxKFetch);
   }
   int64_t cap = auto_cap(ctx, k_fetch);
-  bool dual = false;          // exact in-pass predicate fallback
-  int rounds = 0;
-  CU_OK(cudaEventRecord(ctx->ev[6], stream));
-  for (;; ++rounds) {
-    if (rounds > 12) return fail(SWAT_ERR_OVERFLOW, "retry budget exhausted (cap=%lld k_fetch=%d)", (long long)cap, k_fetch);
-    swat_job* job = nullptr;
-    SW_OK(job_create_cap(ctx, q, dual ? k : k_fetch, thr, cap, &job));
+  int64_t list_entries = auto_list_entries(ctx, C, k_fetch);
+  cudaEvent_t ev_begin = ctx->ev[6];
+  if (depth == 0) CU_OK(cudaEventRecord(ev_begin, stream));
+  for (int rounds = 0;; ++rounds) {
+    if (rounds > 12) return fail(SWAT_ERR_OVERFLOW, "retry budget exhausted (cap=%lld lists=%lld k_fetch=%d)", (long long)cap,
+                                 (long long)list_entries, k_fetch);
     const int32_t kf = dual ? k : k_fetch;
-    int32_t rc = swat_job_reset(job, stream);
-    if (rc == SWAT_OK) rc = (cudaEventRecord(ctx->ev[0], stream) == cudaSuccess) ? SWAT_OK : SWAT_ERR_CUDA;
-    if (rc == SWAT_OK) rc = scan_all(ctx, job, b, dual, t2i_thr, stream);
-    if (rc == SWAT_OK) rc = (cudaEventRecord(ctx->ev[1], stream) == cudaSuccess) ? SWAT_OK : SWAT_ERR_CUDA;
+    swat_job* job = nullptr;
+    SW_OK(acquire_job(ctx, q, kf, thr, cap, list_entries, &job));
+    SW_OK(swat_job_reset(job, stream));
+    CU_OK(cudaEventRecord(ctx->ev[0], stream));
+    SW_OK(scan_all(ctx, job, b, dual, t2i_thr, stream));
+    CU_OK(cudaEventRecord(ctx->ev[1], stream));
     const bool direct = !want_t2i || dual;     // select writes the final result
-    if (rc == SWAT_OK && !direct) {
-      rc = ctx->w_scores.ensure(static_cast<size_t>(C) * kf * 4);
-      if (rc == SWAT_OK) rc = ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8);
-      if (rc == SWAT_OK) rc = ctx->w_counts.ensure(static_cast<size_t>(C) * 4);
-      if (rc == SWAT_OK) rc = ctx->w_trunc.ensure(static_cast<size_t>(C) * 4);
-      if (rc == SWAT_OK) rc = ctx->w_t2i.ensure(static_cast<size_t>(C) * kf * 4);
-      if (rc == SWAT_OK) rc = ctx->w_incomplete.ensure(static_cast<size_t>(C) * 4);
+    if (!direct) {
+      SW_OK(ctx->w_scores.ensure(static_cast<size_t>(C) * kf * 4));
+      SW_OK(ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8));
+      SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
+      SW_OK(ctx->w_trunc.ensure(static_cast<size_t>(C) * 4));
     }
-    if (rc == SWAT_OK) {
-      // resident banks: rows leave the select as global ids (row_offset + shard-local row)
-      cudaError_t se;
-      if (direct) se = launch_select(job->st, C, row_offset, d_out_scores, d_out_rows, d_out_counts, nullptr, stream);
-      else se = launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(),
-                              ctx->w_counts.as<int32_t>(), ctx->w_trunc.as<int32_t>(), stream);
-      if (se != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "select launch failed: %s", cudaGetErrorString(se));
-      job->last_stream = stream;
-      ctx->launches += 1;
-    }
-    if (rc == SWAT_OK) rc = (cudaEventRecord(ctx->ev[2], stream) == cudaSuccess) ? SWAT_OK : SWAT_ERR_CUDA;
-    int32_t overflowed = 0;
-    if (rc == SWAT_OK) rc = swat_job_status(job, &overflowed);
-    if (rc == SWAT_OK) {
+    // resident banks: rows leave the select as global ids (row_offset + shard-local row)
+    if (direct) CU_OK(launch_select(job->st, C, row_offset, d_out_scores, d_out_rows, d_out_counts, nullptr, stream));
+    else CU_OK(launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(),
+                             ctx->w_trunc.as<int32_t>(), stream));
+    job->last_stream = stream;
+    ctx->launches += kSelectLaunches;
+    CU_OK(cudaEventRecord(ctx->ev[2], stream));
+    uint32_t flags = 0;
+    SW_OK(job_flags(job, &flags));
+    {
       float ms = 0;
       cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing[0] += ms;
       cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing[1] += ms;
+      ctx->timing[4] += 1;
     }
-    swat_job_destroy(job);
-    if (rc != SWAT_OK) return rc;
-    if (overflowed) {
-      if (cap >= std::max<int64_t>(b.n_rows, 1 << 16)) return fail(SWAT_ERR_OVERFLOW, "candidate buffer overflow with cap >= n_rows");
-      cap = std::min<int64_t>(cap * 4, std::max<int64_t>(b.n_rows, 1 << 16));
+    if (flags & 3u) {
+      const int64_t limit = std::max<int64_t>(b.n_rows, 1 << 16);
+      if ((flags & 1u) && cap >= limit) return fail(SWAT_ERR_OVERFLOW, "class candidate overflow with cap >= n_rows");
+      if (flags & 1u) cap = std::min<int64_t>(cap * 4, limit);
+      if (flags & 2u) list_entries *= 4;
       ctx->timing[7] += 1;
       continue;
     }
-    if (direct) {
-      if (dual && d_out_t2i) {
-        // in-pass mode proves t2i >= threshold but does not keep the value: re-score the k winners
-        SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(C) * k * 4));
-        SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
-      }
-      if (!(dual && d_out_t2i)) break;
-    }
+    if (direct && !(dual && d_out_t2i)) break;
     // ---- T2I stage on the candidates
     CU_OK(cudaEventRecord(ctx->ev[3], stream));
     T2iArgs t;
@@ -403,6 +487,7 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     t.class_begin = q->d_class_begin;
     t.reduce = q->reduce;
     t.n_classes = C;
+    // in-pass mode proved t2i >= threshold but did not keep the value: re-score the k winners
     t.t2i_thr = direct ? -INFINITY : t2i_thr;
     t.k = k;
     t.k_fetch = direct ? k : kf;
@@ -410,6 +495,7 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     t.cand_rows = direct ? d_out_rows : ctx->w_rows.as<int64_t>();
     t.cand_counts = direct ? d_out_counts : ctx->w_counts.as<int32_t>();
     t.truncated = direct ? nullptr : ctx->w_trunc.as<int32_t>();
+    SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(C) * t.k_fetch * 4));
     t.t2i_scratch = ctx->w_t2i.as<float>();
     SW_OK(ctx->w_out_scores.ensure(static_cast<size_t>(C) * k * 4));
     SW_OK(ctx->w_out_rows.ensure(static_cast<size_t>(C) * k * 8));
@@ -483,24 +569,32 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       ctx->timing[2] += ms;
     }
     if (direct) break;
-    bool any = false;
-    for (int c = 0; c < C; ++c) any = any || inc[c] != 0;
-    if (!any) break;
+    std::vector<int> bad;
+    for (int c = 0; c < C; ++c) if (inc[c] != 0) bad.push_back(c);
+    if (bad.empty()) break;
     // some class ran out of candidates before k passed T2I although more rows were eligible:
-    // widen the over-fetch, then fall back to the exact in-pass predicate
+    // widen the over-fetch for those classes only, finally fall back to the exact in-pass predicate
     ctx->timing[7] += 1;
-    if (k_fetch < kMaxKFetch) {
-      k_fetch = std::min(kMaxKFetch, k_fetch * 4);
+    const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 4) : kMaxKFetch + 1;
+    if (b.row_class == nullptr && static_cast<int>(bad.size()) < C) {
+      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, bad, next, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
+                             stream, depth));
+      break;
+    }
+    if (next > kMaxKFetch) dual = true;
+    else {
+      k_fetch = next;
       cap = std::max(cap, auto_cap(ctx, k_fetch));
-    } else {
-      dual = true;
+      list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
     }
   }
-  CU_OK(cudaEventRecord(ctx->ev[7], stream));
-  CU_OK(cudaStreamSynchronize(stream));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
-  ctx->timing[3] = ms;
+  if (depth == 0) {
+    CU_OK(cudaEventRecord(ctx->ev[7], stream));
+    CU_OK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_begin, ctx->ev[7]);
+    ctx->timing[3] = ms;
+  }
   return SWAT_OK;
 }
 
@@ -556,6 +650,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
                     &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts};
   for (DevBuf* b : bufs) b->release();
+  if (ctx->cached_job) swat_job_destroy(ctx->cached_job);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->work_stream) cudaStreamDestroy(ctx->work_stream);
@@ -571,6 +666,7 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   if (n == "cta_group") { if (value != 1 && value != 2) return fail(SWAT_ERR_INVALID, "cta_group must be 1 or 2"); ctx->cta_group = (int)value; }
   else if (n == "max_ctas") ctx->max_ctas = static_cast<int>(value);
   else if (n == "cand_cap") ctx->cand_cap = value;
+  else if (n == "list_entries") ctx->list_entries = value;
   else if (n == "overfetch") ctx->overfetch = static_cast<int>(value);
   else if (n == "host_chunk_rows") ctx->host_chunk_rows = value;
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
@@ -607,6 +703,7 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   }
   swat_queries* q = new swat_queries();
   q->ctx = ctx; q->Q = n_queries; q->C = n_classes; q->reduce = reduce; q->class_begin = cb; q->ctas = ctx->cta_group;
+  q->h_q.assign(h_queries, h_queries + static_cast<size_t>(n_queries) * kDim);
   const int max_cols = (q->ctas == 2) ? 256 : 144;
   std::vector<int> first;
   if (!plan_blocks(cb, max_cols, q->n_qb, q->n_blk, first)) {
@@ -638,6 +735,8 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   if (e == cudaSuccess) e = cudaMalloc(&q->d_qp_bf16, NC * kDim * 2);
   if (e == cudaSuccess) e = cudaMalloc(&q->d_col_class, NC * 4);
   if (e == cudaSuccess) e = cudaMalloc(&q->d_col_count, NC * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&q->d_blk_class, (q->n_qb + 1) * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_blk_class, first.data(), (q->n_qb + 1) * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(q->d_q_f32, h_queries, Q * kDim * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(q->d_q_bf16, h_bf.data(), Q * kDim * 2, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(q->d_class_begin, cb.data(), (n_classes + 1) * 4, cudaMemcpyHostToDevice);
@@ -659,14 +758,14 @@ int32_t swat_queries_destroy(swat_queries* q) {
   if (!q) return SWAT_OK;
   cudaSetDevice(q->ctx->device);
   cudaFree(q->d_q_f32); cudaFree(q->d_q_bf16); cudaFree(q->d_class_begin);
-  cudaFree(q->d_qp_f32); cudaFree(q->d_qp_bf16); cudaFree(q->d_col_class); cudaFree(q->d_col_count);
+  cudaFree(q->d_qp_f32); cudaFree(q->d_qp_bf16); cudaFree(q->d_col_class); cudaFree(q->d_col_count); cudaFree(q->d_blk_class);
   delete q;
   return SWAT_OK;
 }
 
 int32_t swat_job_create(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float t2t_threshold, swat_job** out) {
   if (!ctx) return fail(SWAT_ERR_INVALID, "null ctx");
-  SW_OK(job_create_cap(ctx, q, k_fetch, t2t_threshold, auto_cap(ctx, k_fetch), out));
+  SW_OK(job_create_cap(ctx, q, k_fetch, t2t_threshold, auto_cap(ctx, k_fetch), auto_list_entries(ctx, q->C, k_fetch), out));
   return swat_job_reset(*out, nullptr);
 }
 
@@ -695,7 +794,7 @@ int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t
   CU_OK(cudaSetDevice(job->ctx->device));
   CU_OK(launch_select(job->st, job->q->C, 0, d_scores, d_rows, d_counts, d_truncated, static_cast<cudaStream_t>(stream)));
   job->last_stream = static_cast<cudaStream_t>(stream);
-  job->ctx->launches += 1;
+  job->ctx->launches += kSelectLaunches;
   return SWAT_OK;
 }
 
@@ -704,9 +803,8 @@ int32_t swat_job_status(swat_job* job, int32_t* overflowed) {
   (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
   uint32_t flags = 0;
-  CU_OK(cudaMemcpyAsync(&flags, job->st.flags, 4, cudaMemcpyDeviceToHost, job->last_stream));
-  CU_OK(cudaStreamSynchronize(job->last_stream));
-  *overflowed = (flags & 1u) ? 1 : 0;
+  SW_OK(job_flags(job, &flags));
+  *overflowed = static_cast<int32_t>(flags & 3u);   // bit0: class candidates ("cand_cap"), bit1: survivor lists ("list_entries")
   return SWAT_OK;
 }
 
@@ -714,6 +812,7 @@ int32_t swat_job_destroy(swat_job* job) {
   if (!job) return SWAT_OK;
   cudaSetDevice(job->ctx->device);
   cudaFree(job->st.tau_enc); cudaFree(job->st.count); cudaFree(job->st.hist); cudaFree(job->st.cand); cudaFree(job->st.flags);
+  cudaFree(job->st.list); cudaFree(job->st.list_count);
   delete job;
   return SWAT_OK;
 }
@@ -781,7 +880,7 @@ int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, 
   BankSrc b;
   b.host = false; b.t2t = d_t2t_bank; b.t2i = d_t2i_bank; b.dtype = dtype; b.n_rows = n_rows; b.row_class = d_row_class; b.exclude = d_exclude;
   return run_pipeline(ctx, q, b, row_offset, k, t2t_threshold, t2i_threshold, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
-                      static_cast<cudaStream_t>(stream));
+                      static_cast<cudaStream_t>(stream), 0, 0);
 }
 
 int32_t swat_topk_host(swat_ctx* ctx, const swat_queries* q, const void* h_t2t_bank, const void* h_t2i_bank, int32_t dtype, int64_t n_rows,
@@ -801,7 +900,7 @@ int32_t swat_topk_host(swat_ctx* ctx, const swat_queries* q, const void* h_t2t_b
   cudaStream_t s = ctx->work_stream;
   if (rc == SWAT_OK)
     rc = run_pipeline(ctx, q, b, 0, k, t2t_threshold, t2i_threshold, o_scores.as<float>(), o_rows.as<int64_t>(),
-                      (h_out_t2i && h_t2i_bank) ? ctx->w_out_t2i.as<float>() : nullptr, o_counts.as<int32_t>(), s);
+                      (h_out_t2i && h_t2i_bank) ? ctx->w_out_t2i.as<float>() : nullptr, o_counts.as<int32_t>(), s, 0, 0);
   if (rc == SWAT_OK) {
     cudaError_t e = cudaMemcpyAsync(h_out_scores, o_scores.p, C * k * 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_out_rows, o_rows.p, C * k * 8, cudaMemcpyDeviceToHost, s);

@@ -39,18 +39,24 @@ __host__ __device__ __forceinline__ float key_score(uint64_t k) { return f32_dec
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~static_cast<uint32_t>(k); }
 
 // ---- running top-k state of one job (device pointers) ----
+// Scan kernels only ever (a) bump the class histogram (fire-and-forget RED) and (b) append
+// {key, class} to a survivor list; nothing in the scan waits on an atomic's return value.  At select
+// time the final class thresholds are derived from the histograms, the lists are partitioned by class
+// (dropping everything below the final threshold) into `cand`, and each class is radix-selected/sorted.
 struct JobState {
-  uint32_t* tau_enc;   // [C]  f32_enc of the class threshold: rows scoring below can never be in the top k_fetch
-  uint32_t* count;     // [C]  entries appended (may exceed cap after an overflow)
-  uint32_t* hist;      // [C * kHistBins] histogram of appended scores
-  uint64_t* cand;      // [C * cap] candidate keys
-  uint32_t* flags;     // [0] bit0 = candidate buffer overflow
+  uint32_t* tau_enc;     // [C]  f32_enc of the class threshold: rows scoring below can never be in the top k_fetch
+  uint32_t* hist;        // [C * kHistBins] histogram of appended scores
+  uint4* list;           // [n_lists * list_cap] survivor entries {key.lo, key.hi, class, 0}
+  uint32_t* list_count;  // [n_lists] entries appended to each list (may exceed list_cap after an overflow)
+  uint32_t* count;       // [C]  candidates per class after partition
+  uint64_t* cand;        // [C * cap] candidate keys after partition
+  uint32_t* flags;       // [0] bit0 = class candidate overflow (partition), bit1 = survivor list overflow (scan)
+  uint32_t n_lists, list_cap;
   uint32_t cap;
   uint32_t k_fetch;
-  uint32_t refresh_every;
-  float thr;           // user T2T threshold (sample_retrieval.py:1576 passes 0.0)
-  float hist_lo;       // histogram covers [hist_lo, 1]
-  float hist_scale;    // bins per unit score
+  float thr;             // user T2T threshold (sample_retrieval.py:1576 passes 0.0)
+  float hist_lo;         // histogram covers [hist_lo, 1]
+  float hist_scale;      // bins per unit score
   float hist_inv_scale;
 };
 

@@ -4,9 +4,11 @@
 // registers.  Columns of one class are adjacent; the last column of a class carries the group size
 // and the class threshold.  The common case -- no lane of the warp beats the class threshold -- costs
 // a compare, a vote and an untaken branch per class.  Survivors (rare after warm-up: about
-// k*ln(N/k) per class over the whole scan) take the slow path: warp-aggregated append to the class
-// candidate buffer, histogram update, and every `refresh_every` appends a threshold refresh from the
-// histogram.  The N x Q score matrix never reaches HBM.
+// k*ln(N/k) per class over the whole scan) take the slow path: a fire-and-forget histogram RED and a
+// plain store into a survivor list.  Nothing on this path waits for an atomic to return, so the
+// epilogue never stalls the TMEM pipeline behind L2 round trips.  Class thresholds are recomputed
+// from the histograms by a dedicated refresher warp (tcgen05 kernel) or by each CTA on entry (SIMT
+// kernel).  The N x Q score matrix never reaches HBM.
 //
 // Replaces, for all classes at once: t2t_similarity -> sorted() -> add_to_split of
 // /root/reference/retrieval/sample_retrieval.py:752-758 (and :804-812 with the in-pass T2I predicate).
@@ -23,12 +25,15 @@ struct EpiCtx {
   bool row_valid;
   int my_cls;              // partitioned mode: class of this row (-1 = none)
   float acc, acc2;         // running group reduce (T2T, in-pass T2I)
+  uint32_t list_id;        // survivor list this warp appends to
+  uint32_t list_pos;       // warp-private lists: next free slot (kept in a register across the kernel)
 };
 
-// Recompute the class threshold from its histogram: the largest bin edge with at least k_fetch
-// appended scores at or above it.  Valid at any time: every counted score belongs to a distinct bank
-// row, so at least k_fetch rows score >= the edge and no row below it can enter the top k_fetch.
-static __device__ __noinline__ void refresh_tau(const JobState& st, int cls, float* tau_slot) {
+// Recompute one class threshold from its histogram (whole warp): the largest bin edge with at least
+// k_fetch appended scores at or above it.  Valid at any time: every counted score belongs to a
+// distinct bank row, so at least k_fetch rows score >= the edge and no row below it can enter the
+// top k_fetch.
+static __device__ __noinline__ void refresh_tau(const JobState& st, int cls) {
   const int lane = threadIdx.x & 31;
   const uint32_t* h = st.hist + static_cast<size_t>(cls) * kHistBins + lane * 32;
   uint32_t v[32];
@@ -50,8 +55,8 @@ static __device__ __noinline__ void refresh_tau(const JobState& st, int cls, flo
   const uint32_t ball = __ballot_sync(0xffffffffu, suf >= K);
   if (ball == 0) return;
   const int L = 31 - __clz(ball);
-  int bin = -1;
   if (lane == L) {
+    int bin = -1;
     uint32_t run = suf - mine;
 #pragma unroll
     for (int j = 31; j >= 0; --j) {
@@ -60,45 +65,44 @@ static __device__ __noinline__ void refresh_tau(const JobState& st, int cls, flo
         if (run >= K) bin = lane * 32 + j;
       }
     }
-  }
-  bin = __shfl_sync(0xffffffffu, bin, L);
-  if (bin >= 1 && lane == 0) {
-    const uint32_t e = f32_enc(hist_edge(st, bin));
-    const uint32_t old = atomicMax(&st.tau_enc[cls], e);
-    *tau_slot = f32_dec(old > e ? old : e);
+    if (bin >= 1) atomicMax(&st.tau_enc[cls], f32_enc(hist_edge(st, bin)));
   }
 }
 
 // Slow path: at least one lane of the warp passed the fast predicate for class `cls`.
-static __device__ __noinline__ void slow_append(const ScanArgs& a, float* tau_slot, int cls, float val, bool pass,
-                                         uint32_t row) {
+// ATOMIC_LIST: lists are shared between warps (SIMT kernel) and slots are reserved with an atomic;
+// otherwise the list is private to this warp and the position lives in a register.
+// Returns the number of entries appended.
+template <bool ATOMIC_LIST>
+static __device__ __noinline__ uint32_t slow_append(const ScanArgs& a, uint32_t list_id, uint32_t list_pos, int cls, float val,
+                                                     bool pass, uint32_t row) {
   const JobState& st = a.st;
   if (pass && a.exclude != nullptr) pass = ((a.exclude[row >> 5] >> (row & 31)) & 1u) == 0u;
   const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-  if (ballot == 0) return;
+  if (ballot == 0) return 0;
   const int lane = threadIdx.x & 31;
   const uint32_t n = __popc(ballot);
-  uint32_t slot0 = 0;
-  if (lane == 0) slot0 = atomicAdd(&st.count[cls], n);
-  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  if (ATOMIC_LIST) {
+    if (lane == 0) list_pos = atomicAdd(&st.list_count[list_id], n);
+    list_pos = __shfl_sync(0xffffffffu, list_pos, 0);
+  }
   if (pass) {
     const float s = val + 0.0f;  // -0.0 -> +0.0: Python compares them equal, the key must too
-    const uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
-    if (slot < st.cap) {
-      st.cand[static_cast<size_t>(cls) * st.cap + slot] = make_key(s, a.row_base + row);
+    const uint32_t slot = list_pos + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < st.list_cap) {
+      const uint64_t key = make_key(s, a.row_base + row);
+      st.list[static_cast<size_t>(list_id) * st.list_cap + slot] =
+          make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(cls), 0u);
     } else {
-      atomicOr(st.flags, 1u);
+      atomicOr(st.flags, 2u);
     }
-    atomicAdd(&st.hist[static_cast<size_t>(cls) * kHistBins + hist_bin(st, s)], 1u);
+    atomicAdd(&st.hist[static_cast<size_t>(cls) * kHistBins + hist_bin(st, s)], 1u);   // result unused -> RED
   }
-  const uint32_t after = slot0 + n;
-  if (after >= st.k_fetch && (slot0 < st.k_fetch || after / st.refresh_every != slot0 / st.refresh_every)) {
-    refresh_tau(st, cls, tau_slot);
-  }
+  return n;
 }
 
 // NC columns starting at block-local column col0.  endmask bit j: column col0+j closes a class.
-template <int NC, int RED, bool PART, bool DUAL, bool DENSE>
+template <int NC, int RED, bool PART, bool DUAL, bool DENSE, bool ATOMIC_LIST>
 __device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, const float (&v)[NC],
                                               const float (&v2)[NC], int col0, uint32_t endmask) {
 #pragma unroll
@@ -119,25 +123,14 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, con
         bool pass = cx.row_valid && (val >= cx.tau_col[col]);
         if (DUAL) pass = pass && (red_fin<RED>(cx.acc2, cx.cnt_col[col]) >= a.t2i_thr);
         if (PART) pass = pass && (cx.my_cls == cx.cls_col[col]);
-        if (__any_sync(0xffffffffu, pass)) slow_append(a, &cx.tau_col[col], cx.cls_col[col], val, pass, cx.row);
+        if (__any_sync(0xffffffffu, pass))
+          cx.list_pos += slow_append<ATOMIC_LIST>(a, cx.list_id, cx.list_pos, cx.cls_col[col], val, pass, cx.row);
       }
       if (RED != RED_NONE) {
         cx.acc = red_init<RED>();
         if (DUAL) cx.acc2 = red_init<RED>();
       }
     }
-  }
-}
-
-// Fill the per-column threshold table of one Q block from the global class thresholds.
-// Called by `nthreads` cooperating threads (tid = 0..nthreads-1) before a tile's epilogue.
-__device__ __forceinline__ void load_tau_table(const JobState& st, float* tau_col, const int32_t* cls_col,
-                                               const float* cnt_col, int ncols, int tid, int nthreads) {
-  for (int c = tid; c < ncols; c += nthreads) {
-    const int cls = cls_col[c];
-    float t = INFINITY;
-    if (cls >= 0 && cnt_col[c] > 0.0f) t = f32_dec(ld_cg_u32(&st.tau_enc[cls]));
-    tau_col[c] = t;
   }
 }
 

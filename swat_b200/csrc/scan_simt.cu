@@ -46,6 +46,10 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
   if (PART && cx.row_valid) cx.my_cls = a.row_class[row];
   cx.acc = red_init<RED>();
   cx.acc2 = red_init<RED>();
+  cx.list_id = (blockIdx.x * 4u + static_cast<uint32_t>(warp)) % a.st.n_lists;   // shared lists: slots reserved atomically
+  cx.list_pos = 0;
+  // every CTA refreshes a few class thresholds from the histograms on entry (round-robin over classes)
+  if (!DENSE) refresh_tau(a.st, static_cast<int>((blockIdx.x * 4u + static_cast<uint32_t>(warp)) % static_cast<uint32_t>(a.n_classes)));
 
   for (int c0 = 0; c0 < a.n_cols; c0 += kNc) {
     if (tid < kNc) {
@@ -121,9 +125,9 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
       }
     }
     if constexpr (DUAL) {
-      process_chunk<kNc, RED, PART, DUAL, DENSE>(a, cx, acc, reinterpret_cast<const float(&)[kNc]>(acc2), 0, endmask);
+      process_chunk<kNc, RED, PART, DUAL, DENSE, true>(a, cx, acc, reinterpret_cast<const float(&)[kNc]>(acc2), 0, endmask);
     } else {
-      process_chunk<kNc, RED, PART, false, DENSE>(a, cx, acc, acc, 0, endmask);
+      process_chunk<kNc, RED, PART, false, DENSE, true>(a, cx, acc, acc, 0, endmask);
     }
     __syncthreads();   // tables of this column pass are dead only after every warp left the epilogue
   }

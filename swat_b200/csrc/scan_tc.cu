@@ -175,6 +175,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;                       // [2]
   uint64_t* q_bar = tempty_bar + 2;                           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+  uint32_t* s_done = tmem_slot + 1;                           // epilogue warps that finished
   float* s_tau = reinterpret_cast<float*>(tail + 256);        // [2][256]
   int32_t* s_cls = reinterpret_cast<int32_t*>(s_tau + 512);   // [256]
   float* s_cnt = reinterpret_cast<float*>(s_cls + 256);       // [256]
@@ -186,6 +187,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4 * kCtas); }
     mbar_init(smem_u32(q_bar), 1);
+    *s_done = 0;
     fence_barrier_init();
   }
   for (int c = threadIdx.x; c < 256; c += 256) {
@@ -252,6 +254,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         umma_commit<kCtas>(smem_u32(&tfull_bar[buf]));
       }
     }
+  } else if (warp == 3) {
+    // ================================================================== threshold refresher
+    // Recomputes the thresholds of this Q block's classes from their histograms, round-robin over the
+    // CTAs serving the block, until this CTA's epilogue is done.  Keeps every returning atomic and
+    // histogram read off the epilogue warps.
+    if (!DENSE) {
+      const int c_lo = p.blk_class[qb], c_hi = p.blk_class[qb + 1];
+      const int n_ctas_qb = pairs_qb * kCtas, my_idx = pair_in_qb * kCtas + static_cast<int>(rank);
+      volatile uint32_t* done = s_done;
+      for (;;) {
+        for (int c = c_lo + my_idx; c < c_hi; c += n_ctas_qb) refresh_tau(p.s.st, c);
+        if (*done >= 4u) break;
+        __nanosleep(2000);
+      }
+    }
   } else if (warp >= 4) {
     // ================================================================== epilogue
     const int ew = warp - 4;
@@ -259,13 +276,28 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     EpiCtx cx;
     cx.cls_col = s_cls;
     cx.cnt_col = s_cnt;
+    cx.list_id = blockIdx.x * 4u + static_cast<uint32_t>(ew);   // private to this warp for the whole launch
+    cx.list_pos = DENSE ? 0u : p.s.st.list_count[cx.list_id];
+    // class thresholds for the NEXT tile are fetched while the current tile is processed
+    float tnext0 = INFINITY, tnext1 = INFINITY;
+    auto prefetch_tau = [&]() {
+      tnext0 = INFINITY; tnext1 = INFINITY;
+      if (!DENSE) {
+        const int c0 = etid, c1 = etid + 128;
+        if (c0 < NB && s_cls[c0] >= 0 && s_cnt[c0] > 0.0f) tnext0 = f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c0]]));
+        if (c1 < NB && s_cls[c1] >= 0 && s_cnt[c1] > 0.0f) tnext1 = f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c1]]));
+      }
+    };
+    prefetch_tau();
     uint32_t it = 0;
     for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
       cx.tau_col = s_tau + buf * 256;
       if (!DENSE) {
-        load_tau_table(p.s.st, cx.tau_col, s_cls, s_cnt, NB, etid, 128);
+        cx.tau_col[etid] = tnext0;
+        cx.tau_col[etid + 128] = tnext1;
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        prefetch_tau();
       }
       const int64_t row = t * kTileRows + rank * 128 + ew * 32 + lane;
       cx.row = static_cast<uint32_t>(row);
@@ -288,16 +320,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_lead);
           }
-          process_chunk<32, RED, PART, false, DENSE>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
+          process_chunk<32, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
         } else {
           float v[16];
           tmem_ld16(taddr + c0, v);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_lead);
-          process_chunk<16, RED, PART, false, DENSE>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
+          process_chunk<16, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
         }
       }
+    }
+    if (lane == 0) {
+      if (!DENSE) p.s.st.list_count[cx.list_id] = cx.list_pos;
+      atomicAdd(s_done, 1u);
     }
   }
 

@@ -11,6 +11,7 @@ struct TcArgs {
   int32_t n_stages;       // bank-tile ring depth
   uint32_t smem_b_bytes;  // per-CTA bytes of the resident query block
   uint64_t bank_hint;     // L2 cache policy for bank tiles
+  const int32_t* blk_class;  // [n_qb+1] first class of each Q block
 };
 
 size_t tc_smem_bytes(int n_blk, int ctas, int n_stages);
@@ -24,8 +25,11 @@ cudaError_t launch_scan_simt(const ScanArgs& a, const void* bank, const void* ba
                              int dtype, int reduce, bool partitioned, bool dense, cudaStream_t stream);
 
 // final per-class select of the k_fetch best candidates
+// final per-class select: final thresholds from the histograms, partition of the survivor lists by
+// class, radix-select + sort of the k_fetch best candidates (3 launches)
 cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
                           int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream);
+constexpr int kSelectLaunches = 3;
 
 struct T2iArgs {
   const void* img_bank; int dtype; int64_t img_rows; int64_t img_row_base; const int64_t* img_index;

@@ -1,5 +1,7 @@
 // Per-class selection kernels: final top-k_fetch of a job, T2I re-score + accept walk, shard merge.
+#include <algorithm>
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "scan_tc.h"
 
 namespace swat {
@@ -97,8 +99,8 @@ select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_sco
   }
   if (threadIdx.x == 0) {
     out_counts[c] = static_cast<int32_t>(cnt);
-    // more eligible rows than k_fetch exist iff more were appended, or the threshold ever rose
-    // (rows below a risen threshold are never appended)
+    // more eligible rows than k_fetch exist iff more than k_fetch candidates survived, or the
+    // threshold ever rose above the user threshold (rows below it were dropped)
     if (out_trunc) out_trunc[c] = (appended > K || st.tau_enc[c] > f32_enc(st.thr)) ? 1 : 0;
   }
 }
@@ -108,7 +110,34 @@ __global__ void reset_kernel(const JobState st, int n_classes) {
   const size_t nh = static_cast<size_t>(n_classes) * kHistBins;
   if (i < nh) st.hist[i] = 0;
   if (i < static_cast<size_t>(n_classes)) { st.count[i] = 0; st.tau_enc[i] = f32_enc(st.thr); }
+  if (i < st.n_lists) st.list_count[i] = 0;
   if (i == 0) st.flags[0] = 0;
+}
+
+// final class thresholds from the complete histograms (one warp per class), and per-class counters
+// zeroed for the partition
+__global__ void __launch_bounds__(256) final_tau_kernel(const JobState st, int n_classes) {
+  const int cls = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cls >= n_classes) return;
+  refresh_tau(st, cls);
+  if ((threadIdx.x & 31) == 0) st.count[cls] = 0;
+}
+
+// survivor lists -> per-class candidate arrays, keeping only entries at or above the final class
+// threshold (about k_fetch plus one histogram bin per class)
+__global__ void __launch_bounds__(256) partition_kernel(const JobState st) {
+  const uint32_t l = blockIdx.x;
+  const uint32_t n = min(st.list_count[l], st.list_cap);
+  const uint4* src = st.list + static_cast<size_t>(l) * st.list_cap;
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+    const uint4 e = src[i];
+    const uint32_t cls = e.z;
+    if (e.y >= st.tau_enc[cls]) {
+      const uint32_t slot = atomicAdd(&st.count[cls], 1u);
+      if (slot < st.cap) st.cand[static_cast<size_t>(cls) * st.cap + slot] = (static_cast<uint64_t>(e.y) << 32) | e.x;
+      else atomicOr(st.flags, 1u);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------- T2I stage
@@ -322,12 +351,18 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
 cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
                           int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream) {
   if (n_classes <= 0) return cudaSuccess;
+  final_tau_kernel<<<(n_classes + 7) / 8, 256, 0, stream>>>(st, n_classes);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  partition_kernel<<<dim3(st.n_lists, 4), 256, 0, stream>>>(st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
   select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated);
   return cudaGetLastError();
 }
 
 cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t stream) {
-  const size_t n = static_cast<size_t>(n_classes) * kHistBins;
+  const size_t n = std::max(static_cast<size_t>(n_classes) * kHistBins, static_cast<size_t>(st.n_lists));
   reset_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(st, n_classes);
   return cudaGetLastError();
 }

@@ -30,8 +30,8 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
                      row_class: Optional[torch.Tensor] = None, exclude: Optional[torch.Tensor] = None):
     """This shard's T2T top-``k_fetch`` per class (global row ids) with the T2I score of every
     candidate.  Returns ``(scores, rows, t2i | None, counts, truncated)`` on the device."""
-    cap = None
-    for _ in range(6):
+    cap, lists = None, None
+    for _ in range(8):
         job = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
         job.scan(t2t_bank, row_base=0, row_class=row_class, exclude=exclude)
         scores, rows, counts, trunc = job.select()
@@ -39,12 +39,18 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
         job.close()
         if not over:
             break
-        cap = (cap or 32768) * 4
-        ctx.set_option("cand_cap", cap)
+        if over & 1:
+            cap = (cap or (2 * k_fetch + 4096)) * 4
+            ctx.set_option("cand_cap", cap)
+        if over & 2:
+            lists = (lists or (4 << 20)) * 4
+            ctx.set_option("list_entries", lists)
     else:
         raise _lib.SwatError(-4, "candidate buffers keep overflowing")
     if cap is not None:
         ctx.set_option("cand_cap", 0)
+    if lists is not None:
+        ctx.set_option("list_entries", 0)
     t2i = None
     if t2i_bank is not None:
         # threshold -inf and k == k_fetch: every candidate is kept in order, we only want its T2I score

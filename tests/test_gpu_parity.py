@@ -174,9 +174,9 @@ def test_exclusion_bitmap_and_threshold(lib, ctx2):
 
 
 def test_overflow_retry_and_t2i_escalation(lib):
-    """Tiny candidate buffers force the overflow retry; a T2I predicate almost nothing passes forces
-    over-fetch escalation and finally the exact in-pass predicate."""
-    ctx = lib.Context(0, cand_cap=4096, overfetch=64)
+    """Tiny survivor lists and class candidate buffers force both overflow retries; a T2I predicate
+    almost nothing passes forces over-fetch escalation and finally the exact in-pass predicate."""
+    ctx = lib.Context(0, cand_cap=48, list_entries=20_000, overfetch=64)
     bank = _rand_unit(60_000, 21, torch.bfloat16)
     img = _rand_unit(60_000, 22, torch.bfloat16)
     q = _rand_unit(24, 23, torch.bfloat16)
