@@ -102,9 +102,35 @@ static __device__ __noinline__ uint32_t slow_append(const ScanArgs& a, uint32_t 
 }
 
 // NC columns starting at block-local column col0.  endmask bit j: column col0+j closes a class.
+//
+// RED_NONE (one query per class, the reference's default ['mean'] prompt): branch-free.  The NC
+// compares are independent and fold into one pass mask; ONE vote decides whether anybody in the warp
+// has a survivor in this chunk.  tau is +inf at padding columns, so they never pass.
+// Grouped reduces (synonym max / mean / min): running reduce along the columns, one vote per class.
 template <int NC, int RED, bool PART, bool DUAL, bool DENSE, bool ATOMIC_LIST>
 __device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, const float (&v)[NC],
                                               const float (&v2)[NC], int col0, uint32_t endmask) {
+  if (RED == RED_NONE && !DENSE) {
+    const float* tau = cx.tau_col + col0;
+    const int32_t* cls = cx.cls_col + col0;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      bool p = cx.row_valid && (v[j] >= tau[j]);
+      if (DUAL) p = p && (v2[j] >= a.t2i_thr);
+      if (PART) p = p && (cx.my_cls == cls[j]);
+      mask |= static_cast<uint32_t>(p) << j;
+    }
+    if (__any_sync(0xffffffffu, mask != 0u)) {
+      const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        if ((any >> j) & 1u)   // warp-uniform
+          cx.list_pos += slow_append<ATOMIC_LIST>(a, cx.list_id, cx.list_pos, cls[j], v[j], (mask >> j) & 1u, cx.row);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     if (RED == RED_NONE) {

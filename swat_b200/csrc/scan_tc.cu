@@ -104,8 +104,8 @@ template <int kCtas> __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  :: "r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
   }
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// issue a 32-column TMEM load (lane = this thread's row); the registers are valid after tmem_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -114,20 +114,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait for outstanding TMEM loads; the registers are in/out operands so that no read of them can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+__device__ __forceinline__ void to_f32x32(const uint32_t (&r)[32], float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
@@ -311,23 +311,30 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256u;
       const uint32_t tempty_a = smem_u32(&tempty_bar[buf]);
       const uint32_t tempty_lead = (kCtas == 2) ? mapa_rank0(tempty_a) : tempty_a;
-      for (int c0 = 0; c0 < NB; c0 += 32) {
-        if (NB - c0 >= 32) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          if (c0 + 32 >= NB) {   // accumulator fully in registers: hand the buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_lead);
-          }
-          process_chunk<32, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
-        } else {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_lead);
-          process_chunk<16, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
+      // 32 columns per TMEM load, double-buffered: the load of chunk i+1 is in flight while chunk i
+      // is processed.  A buffer is 256 columns wide, so a trailing partial chunk simply reads columns
+      // whose threshold is +inf.  The accumulator is handed back to the MMA warp as soon as its last
+      // column sits in registers.
+      auto release_tmem = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_lead);
+      };
+      uint32_t ra[32], rb[32];
+      float v[32];
+      tmem_ld32_issue(taddr, ra);
+      tmem_wait(ra);
+      for (int c0 = 0; c0 < NB; c0 += 64) {
+        const bool has_b = c0 + 32 < NB, has_next = c0 + 64 < NB;
+        if (has_b) tmem_ld32_issue(taddr + c0 + 32, rb); else release_tmem();
+        to_f32x32(ra, v);
+        process_chunk<32, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
+        if (has_b) {
+          tmem_wait(rb);
+          if (has_next) tmem_ld32_issue(taddr + c0 + 64, ra); else release_tmem();
+          to_f32x32(rb, v);
+          process_chunk<32, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0 + 32, s_end[(c0 >> 5) + 1]);
+          if (has_next) tmem_wait(ra);
         }
       }
     }

@@ -1,0 +1,42 @@
+"""Timing probe on the GPU box: scan-only time for several configurations + pipeline breakdown."""
+import json, sys, time
+import torch
+sys.path.insert(0, ".")
+from swat_b200 import _lib, synth
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+dev = torch.device("cuda", 0)
+ctx = _lib.Context(0)
+qc, queries, _ = synth.make_queries(C, 1, seed=0, dtype=torch.bfloat16)
+cap, img, _ = synth.make_bank(N, qc, seed=0, device=dev, dtype=torch.bfloat16, chunk=1 << 20)
+qs = _lib.Queries(ctx, queries.float())
+torch.cuda.synchronize()
+
+def ev_time(fn, reps=5):
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return sorted(out)
+
+for kf in (500, 1024, 4096):
+    job = _lib.Job(ctx, qs, kf, 0.0)
+    def scan():
+        job.reset(); job.scan(cap)
+    t = ev_time(scan)
+    sel = ev_time(lambda: job.select())
+    print(f"scan k_fetch={kf}: {t} ms  -> {N*1024/t[len(t)//2]/1e6:.0f} GB/s ; select {sel} ; overflow={job.overflowed()}")
+    job.close()
+# dense-free "pure GEMM" ceiling: threshold so high nothing survives
+job = _lib.Job(ctx, qs, 500, 0.999)
+t = ev_time(lambda: (job.reset(), job.scan(cap)))
+print(f"scan thr=0.999 (no survivors): {t} ms -> {N*1024/t[len(t)//2]/1e6:.0f} GB/s")
+job.close()
+for name, kw in (("t2t", {}), ("t2t+t2i", {"t2i_bank": img})):
+    for _ in range(2):
+        t0 = time.perf_counter()
+        _lib.topk(ctx, qs, cap, 500, 0.0, **kw)
+        dt = time.perf_counter() - t0
+        print(name, f"wall {dt*1e3:.2f} ms", json.dumps(ctx.last_timing()))
