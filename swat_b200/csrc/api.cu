@@ -204,8 +204,8 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     int grid = ctx->sm_count;
     if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
     grid = std::max(q->ctas, grid / q->ctas * q->ctas);
-    if (dense_out == nullptr && static_cast<uint32_t>(grid) * 4u > job->st.n_lists)
-      return fail(SWAT_ERR_INVALID, "grid of %d CTAs needs %d survivor lists, job has %u", grid, grid * 4, job->st.n_lists);
+    if (dense_out == nullptr && static_cast<uint32_t>(grid) * kTcEpiWarps > job->st.n_lists)
+      return fail(SWAT_ERR_INVALID, "grid of %d CTAs needs %d survivor lists, job has %u", grid, grid * kTcEpiWarps, job->st.n_lists);
     CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
   } else {
     const void* qp = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_qp_bf16) : static_cast<const void*>(q->d_qp_f32);
@@ -253,8 +253,8 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
   JobState& st = j->st;
   memset(&st, 0, sizeof(st));
   st.cap = static_cast<uint32_t>(std::min<int64_t>(cap, 0x7fffffff));
-  st.n_lists = 1024;
-  const int64_t private_lists = std::max(1, ctx->sm_count) * 4ll;     // the tcgen05 kernel uses one list per epilogue warp
+  st.n_lists = 2048;
+  const int64_t private_lists = std::max(1, ctx->sm_count) * static_cast<int64_t>(kTcEpiWarps);   // one list per epilogue warp of the tcgen05 kernel
   st.list_cap = static_cast<uint32_t>(std::min<int64_t>(((list_entries + private_lists - 1) / private_lists + 255) / 256 * 256, 0x7fffff00));
   job_set_params(j, q, k_fetch, thr);
   cudaError_t e = cudaMalloc(&st.tau_enc, C * 4);
@@ -276,7 +276,7 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
 // whole-pipeline calls reuse one job allocation per ctx as long as the sizes fit
 int32_t acquire_job(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, int64_t list_entries, swat_job** out) {
   swat_job* j = ctx->cached_job;
-  const int64_t private_lists = std::max(1, ctx->sm_count) * 4ll;
+  const int64_t private_lists = std::max(1, ctx->sm_count) * static_cast<int64_t>(kTcEpiWarps);
   if (j && j->n_classes_alloc >= q->C && j->st.cap >= cap && static_cast<int64_t>(j->st.list_cap) * private_lists >= list_entries) {
     if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
     job_set_params(j, q, k_fetch, thr);

@@ -25,9 +25,34 @@ struct EpiCtx {
   bool row_valid;
   int my_cls;              // partitioned mode: class of this row (-1 = none)
   float acc, acc2;         // running group reduce (T2T, in-pass T2I)
-  uint32_t list_id;        // survivor list this warp appends to
   uint32_t list_pos;       // warp-private lists: next free slot (kept in a register across the kernel)
 };
+
+// Everything the slow path needs, held in registers and passed BY VALUE: the noinline slow path must
+// not chase pointers into the kernel-parameter struct (each such load is a long-scoreboard stall).
+struct SlowCtx {
+  uint4* list_base;           // this warp's survivor list (ATOMIC_LIST: the shared list of this CTA slot)
+  uint32_t* list_count;       // ATOMIC_LIST only: slot counter of that list
+  uint32_t* hist;             // [C * kHistBins]
+  uint32_t* flags;
+  const uint32_t* exclude;    // nullable
+  uint32_t list_cap;
+  uint32_t row_base;
+  float hist_lo, hist_scale;
+};
+__device__ __forceinline__ SlowCtx make_slow_ctx(const ScanArgs& a, uint32_t list_id) {
+  SlowCtx s;
+  s.list_base = a.st.list + static_cast<size_t>(list_id) * a.st.list_cap;
+  s.list_count = a.st.list_count + list_id;
+  s.hist = a.st.hist;
+  s.flags = a.st.flags;
+  s.exclude = a.exclude;
+  s.list_cap = a.st.list_cap;
+  s.row_base = a.row_base;
+  s.hist_lo = a.st.hist_lo;
+  s.hist_scale = a.st.hist_scale;
+  return s;
+}
 
 // Recompute one class threshold from its histogram (whole warp): the largest bin edge with at least
 // k_fetch appended scores at or above it.  Valid at any time: every counted score belongs to a
@@ -74,29 +99,29 @@ static __device__ __noinline__ void refresh_tau(const JobState& st, int cls) {
 // otherwise the list is private to this warp and the position lives in a register.
 // Returns the number of entries appended.
 template <bool ATOMIC_LIST>
-static __device__ __noinline__ uint32_t slow_append(const ScanArgs& a, uint32_t list_id, uint32_t list_pos, int cls, float val,
-                                                     bool pass, uint32_t row) {
-  const JobState& st = a.st;
-  if (pass && a.exclude != nullptr) pass = ((a.exclude[row >> 5] >> (row & 31)) & 1u) == 0u;
+static __device__ __noinline__ uint32_t slow_append(const SlowCtx sc, uint32_t list_pos, int cls, float val, bool pass, uint32_t row) {
+  if (pass && sc.exclude != nullptr) pass = ((sc.exclude[row >> 5] >> (row & 31)) & 1u) == 0u;
   const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
   if (ballot == 0) return 0;
   const int lane = threadIdx.x & 31;
   const uint32_t n = __popc(ballot);
   if (ATOMIC_LIST) {
-    if (lane == 0) list_pos = atomicAdd(&st.list_count[list_id], n);
+    if (lane == 0) list_pos = atomicAdd(sc.list_count, n);
     list_pos = __shfl_sync(0xffffffffu, list_pos, 0);
   }
   if (pass) {
     const float s = val + 0.0f;  // -0.0 -> +0.0: Python compares them equal, the key must too
     const uint32_t slot = list_pos + __popc(ballot & ((1u << lane) - 1u));
-    if (slot < st.list_cap) {
-      const uint64_t key = make_key(s, a.row_base + row);
-      st.list[static_cast<size_t>(list_id) * st.list_cap + slot] =
-          make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(cls), 0u);
+    if (slot < sc.list_cap) {
+      const uint64_t key = make_key(s, sc.row_base + row);
+      sc.list_base[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(cls), 0u);
     } else {
-      atomicOr(st.flags, 2u);
+      atomicOr(sc.flags, 2u);
     }
-    atomicAdd(&st.hist[static_cast<size_t>(cls) * kHistBins + hist_bin(st, s)], 1u);   // result unused -> RED
+    int b = static_cast<int>((s - sc.hist_lo) * sc.hist_scale);
+    b = b < 0 ? 0 : (b > kHistBins - 1 ? kHistBins - 1 : b);
+    // fire-and-forget reduction (no return value, nothing waits on it)
+    asm volatile("red.global.add.u32 [%0], 1;" :: "l"(sc.hist + static_cast<size_t>(cls) * kHistBins + b) : "memory");
   }
   return n;
 }
@@ -108,7 +133,7 @@ static __device__ __noinline__ uint32_t slow_append(const ScanArgs& a, uint32_t 
 // has a survivor in this chunk.  tau is +inf at padding columns, so they never pass.
 // Grouped reduces (synonym max / mean / min): running reduce along the columns, one vote per class.
 template <int NC, int RED, bool PART, bool DUAL, bool DENSE, bool ATOMIC_LIST>
-__device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, const float (&v)[NC],
+__device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& sc, EpiCtx& cx, const float (&v)[NC],
                                               const float (&v2)[NC], int col0, uint32_t endmask) {
   if (RED == RED_NONE && !DENSE) {
     const float* tau = cx.tau_col + col0;
@@ -126,7 +151,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, con
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         if ((any >> j) & 1u)   // warp-uniform
-          cx.list_pos += slow_append<ATOMIC_LIST>(a, cx.list_id, cx.list_pos, cls[j], v[j], (mask >> j) & 1u, cx.row);
+          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], v[j], (mask >> j) & 1u, cx.row);
       }
     }
     return;
@@ -150,7 +175,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, EpiCtx& cx, con
         if (DUAL) pass = pass && (red_fin<RED>(cx.acc2, cx.cnt_col[col]) >= a.t2i_thr);
         if (PART) pass = pass && (cx.my_cls == cx.cls_col[col]);
         if (__any_sync(0xffffffffu, pass))
-          cx.list_pos += slow_append<ATOMIC_LIST>(a, cx.list_id, cx.list_pos, cx.cls_col[col], val, pass, cx.row);
+          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cx.cls_col[col], val, pass, cx.row);
       }
       if (RED != RED_NONE) {
         cx.acc = red_init<RED>();

@@ -46,8 +46,9 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
   if (PART && cx.row_valid) cx.my_cls = a.row_class[row];
   cx.acc = red_init<RED>();
   cx.acc2 = red_init<RED>();
-  cx.list_id = (blockIdx.x * 4u + static_cast<uint32_t>(warp)) % a.st.n_lists;   // shared lists: slots reserved atomically
   cx.list_pos = 0;
+  // shared lists: slots reserved atomically
+  const SlowCtx sc = make_slow_ctx(a, DENSE ? 0u : (blockIdx.x * 4u + static_cast<uint32_t>(warp)) % a.st.n_lists);
   // every CTA refreshes a few class thresholds from the histograms on entry (round-robin over classes)
   if (!DENSE) refresh_tau(a.st, static_cast<int>((blockIdx.x * 4u + static_cast<uint32_t>(warp)) % static_cast<uint32_t>(a.n_classes)));
 
@@ -125,9 +126,9 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
       }
     }
     if constexpr (DUAL) {
-      process_chunk<kNc, RED, PART, DUAL, DENSE, true>(a, cx, acc, reinterpret_cast<const float(&)[kNc]>(acc2), 0, endmask);
+      process_chunk<kNc, RED, PART, DUAL, DENSE, true>(a, sc, cx, acc, reinterpret_cast<const float(&)[kNc]>(acc2), 0, endmask);
     } else {
-      process_chunk<kNc, RED, PART, false, DENSE, true>(a, cx, acc, acc, 0, endmask);
+      process_chunk<kNc, RED, PART, false, DENSE, true>(a, sc, cx, acc, acc, 0, endmask);
     }
     __syncthreads();   // tables of this column pass are dead only after every warp left the epilogue
   }

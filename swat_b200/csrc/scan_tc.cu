@@ -6,8 +6,10 @@
 //   warp 1   MMA issuer   : one thread, tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM),
 //                           M = 128*ctas, N = padded query columns (<=256), K = 16 per instruction
 //   warp 2   TMEM allocator (512 columns = two accumulator buffers of <=256 columns)
-//   warps 4-7 epilogue    : tcgen05.ld 32 columns at a time -> process_chunk (epilogue.cuh); the
-//                           accumulator buffer is released as soon as its last column is in registers
+//   warp 3   threshold refresher: class thresholds from the score histograms, off the critical path
+//   warps 4-11 epilogue   : two warps per TMEM lane quadrant, interleaved 32-column chunks,
+//                           double-buffered tcgen05.ld -> process_chunk (epilogue.cuh); the accumulator
+//                           buffer is released as soon as a warp's last chunk is in registers
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue).
 //
 // Replaces caption_embeddings.cuda() @ class_prompt.t() + sorted() + walk,
@@ -40,7 +42,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 // arrive on a barrier addressed in the shared::cluster window (own or peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
@@ -146,11 +148,13 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
 }
 
 constexpr int kStageBytes = 128 * 128;   // 128 bank rows x 64 bf16
+constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant, interleaved 32-column chunks
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kTailBytes = 5120;         // barriers + tables
 
 // ---------------------------------------------------------------------------------------- kernel
 template <int kCtas, int RED, bool PART, bool DENSE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constant__ CUtensorMap tm_q, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -176,7 +180,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   uint64_t* q_bar = tempty_bar + 2;                           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
   uint32_t* s_done = tmem_slot + 1;                           // epilogue warps that finished
-  float* s_tau = reinterpret_cast<float*>(tail + 256);        // [2][256]
+  float* s_tau = reinterpret_cast<float*>(tail + 256);        // [256] (+256 spare)
   int32_t* s_cls = reinterpret_cast<int32_t*>(s_tau + 512);   // [256]
   float* s_cnt = reinterpret_cast<float*>(s_cls + 256);       // [256]
   uint32_t* s_end = reinterpret_cast<uint32_t*>(s_cnt + 256); // [8]
@@ -185,17 +189,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     prefetch_tmap(&tm_bank);
     prefetch_tmap(&tm_q);
     for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), 4 * kCtas); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), kEpiWarps * kCtas); }
     mbar_init(smem_u32(q_bar), 1);
     *s_done = 0;
     fence_barrier_init();
   }
-  for (int c = threadIdx.x; c < 256; c += 256) {
+  for (int c = threadIdx.x; c < 256; c += kThreads) {
     const bool in = c < NB;
     s_cls[c] = in ? p.s.col_class[qb * NB + c] : -1;
     s_cnt[c] = in ? p.s.col_count[qb * NB + c] : 0.0f;
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < 256; c += kThreads) {
+    // thresholds by column: +inf at padding / non-closing columns, the class threshold elsewhere.
+    // Every entry is always SOME valid threshold, so the epilogue warps refresh and read this table
+    // without any barrier (a stale value is only more conservative).
+    float t = INFINITY;
+    if (!DENSE && s_cls[c] >= 0 && s_cnt[c] > 0.0f) t = f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c]]));
+    s_tau[c] = t;
+  }
   if (threadIdx.x < 8) {
     uint32_t m = 0;
     for (int j = 0; j < 32; ++j) if (s_cnt[threadIdx.x * 32 + j] > 0.0f) m |= 1u << j;
@@ -265,41 +277,37 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       volatile uint32_t* done = s_done;
       for (;;) {
         for (int c = c_lo + my_idx; c < c_hi; c += n_ctas_qb) refresh_tau(p.s.st, c);
-        if (*done >= 4u) break;
+        if (*done >= static_cast<uint32_t>(kEpiWarps)) break;
         __nanosleep(2000);
       }
     }
   } else if (warp >= 4) {
     // ================================================================== epilogue
-    const int ew = warp - 4;
+    const int ew = warp - 4;          // 0..kEpiWarps-1
+    const int quad = ew & 3;          // TMEM lanes 32*quad .. 32*quad+31 (warp id % 4)
+    const int half = ew >> 2;         // which interleaved set of 32-column chunks
     const int etid = threadIdx.x - 128;
     EpiCtx cx;
     cx.cls_col = s_cls;
     cx.cnt_col = s_cnt;
-    cx.list_id = blockIdx.x * 4u + static_cast<uint32_t>(ew);   // private to this warp for the whole launch
-    cx.list_pos = DENSE ? 0u : p.s.st.list_count[cx.list_id];
-    // class thresholds for the NEXT tile are fetched while the current tile is processed
-    float tnext0 = INFINITY, tnext1 = INFINITY;
-    auto prefetch_tau = [&]() {
-      tnext0 = INFINITY; tnext1 = INFINITY;
-      if (!DENSE) {
-        const int c0 = etid, c1 = etid + 128;
-        if (c0 < NB && s_cls[c0] >= 0 && s_cnt[c0] > 0.0f) tnext0 = f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c0]]));
-        if (c1 < NB && s_cls[c1] >= 0 && s_cnt[c1] > 0.0f) tnext1 = f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c1]]));
-      }
-    };
-    prefetch_tau();
+    const uint32_t list_id = blockIdx.x * static_cast<uint32_t>(kEpiWarps) + static_cast<uint32_t>(ew);   // private to this warp
+    const SlowCtx sc = make_slow_ctx(p.s, DENSE ? 0u : list_id);
+    cx.list_pos = DENSE ? 0u : p.s.st.list_count[list_id];
+    cx.tau_col = s_tau;
+    const bool my_col_live = !DENSE && etid < NB && s_cls[etid] >= 0 && s_cnt[etid] > 0.0f;
+    const uint32_t* my_tau_src = &p.s.st.tau_enc[my_col_live ? s_cls[etid] : 0];
+    // each epilogue thread owns one column of the threshold table: the value for the NEXT tile is
+    // fetched while the current tile is processed
+    uint32_t tnext = 0;
+    if (my_col_live) tnext = ld_cg_u32(my_tau_src);
     uint32_t it = 0;
     for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
-      cx.tau_col = s_tau + buf * 256;
-      if (!DENSE) {
-        cx.tau_col[etid] = tnext0;
-        cx.tau_col[etid + 128] = tnext1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        prefetch_tau();
+      if (my_col_live) {
+        s_tau[etid] = f32_dec(tnext);
+        tnext = ld_cg_u32(my_tau_src);
       }
-      const int64_t row = t * kTileRows + rank * 128 + ew * 32 + lane;
+      const int64_t row = t * kTileRows + rank * 128 + quad * 32 + lane;
       cx.row = static_cast<uint32_t>(row);
       cx.row_valid = row < p.s.n_rows;
       cx.my_cls = -1;
@@ -308,7 +316,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       cx.acc2 = 0.0f;
       mbar_wait(smem_u32(&tfull_bar[buf]), bphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 256u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * 256u;
       const uint32_t tempty_a = smem_u32(&tempty_bar[buf]);
       const uint32_t tempty_lead = (kCtas == 2) ? mapa_rank0(tempty_a) : tempty_a;
       // 32 columns per TMEM load, double-buffered: the load of chunk i+1 is in flight while chunk i
@@ -322,24 +330,33 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       };
       uint32_t ra[32], rb[32];
       float v[32];
-      tmem_ld32_issue(taddr, ra);
-      tmem_wait(ra);
-      for (int c0 = 0; c0 < NB; c0 += 64) {
-        const bool has_b = c0 + 32 < NB, has_next = c0 + 64 < NB;
-        if (has_b) tmem_ld32_issue(taddr + c0 + 32, rb); else release_tmem();
-        to_f32x32(ra, v);
-        process_chunk<32, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0, s_end[c0 >> 5]);
-        if (has_b) {
-          tmem_wait(rb);
-          if (has_next) tmem_ld32_issue(taddr + c0 + 64, ra); else release_tmem();
-          to_f32x32(rb, v);
-          process_chunk<32, RED, PART, false, DENSE, false>(p.s, cx, v, v, c0 + 32, s_end[(c0 >> 5) + 1]);
-          if (has_next) tmem_wait(ra);
+      // this warp's chunks: columns 32*(half + 2*i); grouped reduces need every column in order, so
+      // they keep one warp per quadrant walking all chunks (the second set of warps idles)
+      constexpr bool kSplit = (RED == RED_NONE);
+      const int first = kSplit ? 32 * half : 0;
+      constexpr int kStep = kSplit ? 64 : 32;
+      if (first < NB && (kSplit || half == 0)) {
+        tmem_ld32_issue(taddr + first, ra);
+        tmem_wait(ra);
+        for (int c0 = first; c0 < NB; c0 += 2 * kStep) {
+          const bool has_b = c0 + kStep < NB, has_next = c0 + 2 * kStep < NB;
+          if (has_b) tmem_ld32_issue(taddr + c0 + kStep, rb); else release_tmem();
+          to_f32x32(ra, v);
+          process_chunk<32, RED, PART, false, DENSE, false>(p.s, sc, cx, v, v, c0, s_end[c0 >> 5]);
+          if (has_b) {
+            tmem_wait(rb);
+            if (has_next) tmem_ld32_issue(taddr + c0 + 2 * kStep, ra); else release_tmem();
+            to_f32x32(rb, v);
+            process_chunk<32, RED, PART, false, DENSE, false>(p.s, sc, cx, v, v, c0 + kStep, s_end[(c0 + kStep) >> 5]);
+            if (has_next) tmem_wait(ra);
+          }
         }
+      } else {
+        release_tmem();   // nothing to read for this warp in this tile
       }
     }
     if (lane == 0) {
-      if (!DENSE) p.s.st.list_count[cx.list_id] = cx.list_pos;
+      if (!DENSE) p.s.st.list_count[list_id] = cx.list_pos;
       atomicAdd(s_done, 1u);
     }
   }
@@ -356,7 +373,7 @@ cudaError_t launch_one(const CUtensorMap& tm_bank, const CUtensorMap& tm_q, cons
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -4,6 +4,8 @@
 
 namespace swat {
 
+constexpr int kTcEpiWarps = 8;   // survivor lists per CTA of the tcgen05 kernel
+
 struct TcArgs {
   ScanArgs s;
   int32_t n_qb;           // Q blocks (each keeps <=256 padded query columns resident in shared memory)
