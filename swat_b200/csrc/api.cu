@@ -95,6 +95,11 @@ struct swat_ctx {
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   swat_job* cached_job = nullptr;   // job buffers are reused across whole-pipeline calls
+  // last sub-query set built for a targeted escalation (repeated calls hit the same classes)
+  swat_queries* esc_q = nullptr;
+  const swat_queries* esc_parent = nullptr;
+  std::vector<int> esc_classes;
+  DevBuf e_bufs[4][4];   // per escalation depth: scores, rows, t2i, counts of the sub-run
 };
 
 struct swat_queries {
@@ -105,6 +110,7 @@ struct swat_queries {
   float* d_q_f32 = nullptr; uint16_t* d_q_bf16 = nullptr; int32_t* d_class_begin = nullptr;
   float* d_qp_f32 = nullptr; uint16_t* d_qp_bf16 = nullptr; int32_t* d_col_class = nullptr; float* d_col_count = nullptr;
   int32_t* d_blk_class = nullptr;     // [n_qb+1] first class of each Q block
+  void* d_arena = nullptr;            // one allocation backs every device array above
   std::vector<float> h_q;             // host copy (sub-query sets for targeted escalation)
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
   CUtensorMap tm_q;
@@ -240,7 +246,7 @@ void job_set_params(swat_job* j, const swat_queries* q, int32_t k_fetch, float t
 }
 
 int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, int64_t list_entries,
-                       swat_job** out) {
+                       swat_job** out, int n_classes_alloc = 0) {
   if (!ctx || !q || !out) return fail(SWAT_ERR_INVALID, "null argument");
   if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
   if (thr != thr) return fail(SWAT_ERR_INVALID, "threshold is NaN");
@@ -248,8 +254,8 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
   CU_OK(cudaSetDevice(ctx->device));
   swat_job* j = new swat_job();
   j->ctx = ctx;
-  const size_t C = static_cast<size_t>(q->C);
-  j->n_classes_alloc = q->C;
+  const size_t C = static_cast<size_t>(std::max(q->C, n_classes_alloc));
+  j->n_classes_alloc = static_cast<int>(C);
   JobState& st = j->st;
   memset(&st, 0, sizeof(st));
   st.cap = static_cast<uint32_t>(std::min<int64_t>(cap, 0x7fffffff));
@@ -283,8 +289,15 @@ int32_t acquire_job(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float
     *out = j;
     return SWAT_OK;
   }
-  if (j) { swat_job_destroy(j); ctx->cached_job = nullptr; }
-  SW_OK(job_create_cap(ctx, q, k_fetch, thr, cap, list_entries, &j));
+  int c_alloc = q->C;
+  if (j) {   // grow-only: alternating callers (main pass / escalated sub-pass) must not thrash the allocation
+    c_alloc = std::max(c_alloc, j->n_classes_alloc);
+    cap = std::max<int64_t>(cap, j->st.cap);
+    list_entries = std::max<int64_t>(list_entries, static_cast<int64_t>(j->st.list_cap) * private_lists);
+    swat_job_destroy(j);
+    ctx->cached_job = nullptr;
+  }
+  SW_OK(job_create_cap(ctx, q, k_fetch, thr, cap, list_entries, &j, c_alloc));
   ctx->cached_job = j;
   *out = j;
   return SWAT_OK;
@@ -392,9 +405,17 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
       coq.push_back(i);
     }
   }
+  if (depth > 3) return fail(SWAT_ERR_INCOMPLETE, "escalation nested too deep");
   swat_queries* sub = nullptr;
-  SW_OK(swat_queries_create(ctx, hq.data(), static_cast<int32_t>(coq.size()), coq.data(), n, q->reduce, &sub));
-  DevBuf o_s, o_r, o_t, o_c;
+  const bool cached = depth == 0;   // nested levels own their sub-query set: the cache entry is in use above them
+  if (cached && ctx->esc_q && ctx->esc_parent == q && ctx->esc_classes == classes) {
+    sub = ctx->esc_q;
+  } else {
+    if (cached && ctx->esc_q) { swat_queries_destroy(ctx->esc_q); ctx->esc_q = nullptr; }
+    SW_OK(swat_queries_create(ctx, hq.data(), static_cast<int32_t>(coq.size()), coq.data(), n, q->reduce, &sub));
+    if (cached) { ctx->esc_q = sub; ctx->esc_parent = q; ctx->esc_classes = classes; }
+  }
+  DevBuf &o_s = ctx->e_bufs[depth][0], &o_r = ctx->e_bufs[depth][1], &o_t = ctx->e_bufs[depth][2], &o_c = ctx->e_bufs[depth][3];
   int32_t rc = o_s.ensure(static_cast<size_t>(n) * k * 4);
   if (rc == SWAT_OK) rc = o_r.ensure(static_cast<size_t>(n) * k * 8);
   if (rc == SWAT_OK) rc = o_t.ensure(static_cast<size_t>(n) * k * 4);
@@ -412,8 +433,7 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (rc == SWAT_OK && e != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "splicing escalated classes failed: %s", cudaGetErrorString(e));
-  o_s.release(); o_r.release(); o_t.release(); o_c.release();
-  swat_queries_destroy(sub);
+  if (!cached) swat_queries_destroy(sub);
   return rc;
 }
 
@@ -430,7 +450,9 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
   if (want_t2i) {
     if (k_fetch_init > kMaxKFetch) dual = true;   // escalation beyond the widest over-fetch
     else if (k_fetch_init > 0) k_fetch = k_fetch_init;
-    else k_fetch = ctx->overfetch > 0 ? ctx->overfetch : std::max(2 * k, 1024);
+    // Host banks stream over PCIe (~20x slower than the scan): a second pass costs far more than a
+    // wider first one, so over-fetch 4k there; HBM-resident banks start at 2k.
+    else k_fetch = ctx->overfetch > 0 ? ctx->overfetch : (b.host ? std::max(4 * k, 2048) : std::max(2 * k, 1024));
     k_fetch = std::min(std::max(k_fetch, k), kMaxKFetch);
   }
   int64_t cap = auto_cap(ctx, k_fetch);
@@ -651,6 +673,8 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
                     &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts};
   for (DevBuf* b : bufs) b->release();
   if (ctx->cached_job) swat_job_destroy(ctx->cached_job);
+  if (ctx->esc_q) swat_queries_destroy(ctx->esc_q);
+  for (auto& lvl : ctx->e_bufs) for (auto& bf : lvl) bf.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->work_stream) cudaStreamDestroy(ctx->work_stream);
@@ -728,22 +752,31 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
         if (qi == cb[c + 1] - 1) h_cnt[col] = static_cast<float>(cb[c + 1] - cb[c]);
       }
   }
-  cudaError_t e = cudaMalloc(&q->d_q_f32, Q * kDim * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_q_bf16, Q * kDim * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_class_begin, (n_classes + 1) * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_qp_f32, NC * kDim * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_qp_bf16, NC * kDim * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_col_class, NC * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_col_count, NC * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&q->d_blk_class, (q->n_qb + 1) * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_blk_class, first.data(), (q->n_qb + 1) * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_q_f32, h_queries, Q * kDim * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_q_bf16, h_bf.data(), Q * kDim * 2, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_class_begin, cb.data(), (n_classes + 1) * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_qp_f32, h_pf.data(), NC * kDim * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_qp_bf16, h_pbf.data(), NC * kDim * 2, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_col_class, h_cls.data(), NC * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(q->d_col_count, h_cnt.data(), NC * 4, cudaMemcpyHostToDevice);
+  // one device arena + one staged upload: creating a query set costs one cudaMalloc and one copy
+  auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t o_qf = 0, o_qb = o_qf + up256(Q * kDim * 4), o_cb = o_qb + up256(Q * kDim * 2),
+               o_pf = o_cb + up256((n_classes + 1) * 4), o_pb = o_pf + up256(NC * kDim * 4), o_cc = o_pb + up256(NC * kDim * 2),
+               o_cn = o_cc + up256(NC * 4), o_bc = o_cn + up256(NC * 4), total = o_bc + up256((q->n_qb + 1) * 4);
+  std::vector<char> stage(total, 0);
+  memcpy(&stage[o_qf], h_queries, Q * kDim * 4);
+  memcpy(&stage[o_qb], h_bf.data(), Q * kDim * 2);
+  memcpy(&stage[o_cb], cb.data(), (n_classes + 1) * 4);
+  memcpy(&stage[o_pf], h_pf.data(), NC * kDim * 4);
+  memcpy(&stage[o_pb], h_pbf.data(), NC * kDim * 2);
+  memcpy(&stage[o_cc], h_cls.data(), NC * 4);
+  memcpy(&stage[o_cn], h_cnt.data(), NC * 4);
+  memcpy(&stage[o_bc], first.data(), (q->n_qb + 1) * 4);
+  cudaError_t e = cudaMalloc(&q->d_arena, total);
+  if (e == cudaSuccess) e = cudaMemcpy(q->d_arena, stage.data(), total, cudaMemcpyHostToDevice);
+  char* base = static_cast<char*>(q->d_arena);
+  q->d_q_f32 = reinterpret_cast<float*>(base + o_qf);
+  q->d_q_bf16 = reinterpret_cast<uint16_t*>(base + o_qb);
+  q->d_class_begin = reinterpret_cast<int32_t*>(base + o_cb);
+  q->d_qp_f32 = reinterpret_cast<float*>(base + o_pf);
+  q->d_qp_bf16 = reinterpret_cast<uint16_t*>(base + o_pb);
+  q->d_col_class = reinterpret_cast<int32_t*>(base + o_cc);
+  q->d_col_count = reinterpret_cast<float*>(base + o_cn);
+  q->d_blk_class = reinterpret_cast<int32_t*>(base + o_bc);
   if (e != cudaSuccess) {
     swat_queries_destroy(q);
     return fail(SWAT_ERR_CUDA, "query upload failed: %s", cudaGetErrorString(e));
@@ -756,9 +789,9 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
 
 int32_t swat_queries_destroy(swat_queries* q) {
   if (!q) return SWAT_OK;
+  if (q->ctx->esc_parent == q) q->ctx->esc_parent = nullptr;
   cudaSetDevice(q->ctx->device);
-  cudaFree(q->d_q_f32); cudaFree(q->d_q_bf16); cudaFree(q->d_class_begin);
-  cudaFree(q->d_qp_f32); cudaFree(q->d_qp_bf16); cudaFree(q->d_col_class); cudaFree(q->d_col_count); cudaFree(q->d_blk_class);
+  cudaFree(q->d_arena);
   delete q;
   return SWAT_OK;
 }

@@ -40,3 +40,12 @@ for name, kw in (("t2t", {}), ("t2t+t2i", {"t2i_bank": img})):
         _lib.topk(ctx, qs, cap, 500, 0.0, **kw)
         dt = time.perf_counter() - t0
         print(name, f"wall {dt*1e3:.2f} ms", json.dumps(ctx.last_timing()))
+# which classes need escalation, and how many of the top-1024 T2T candidates pass T2I
+from swat_b200 import dist as sdist
+sc, rows, t2i, counts, trunc = sdist.local_candidates(ctx, qs, cap, 1024, 0.0, img)
+passers = ((t2i >= 0.25) & (torch.arange(1024, device=dev)[None, :] < counts[:, None])).sum(1)
+print("passers among top-1024: min", int(passers.min()), "argmin", int(passers.argmin()), "median", int(passers.median()),
+      "classes below 500:", (passers < 500).nonzero().flatten().tolist())
+for _ in range(3):
+    t0 = time.perf_counter(); _lib.topk(ctx, qs, cap, 500, 0.0, t2i_bank=img); dt = time.perf_counter() - t0
+    print("t2t+t2i", f"wall {dt*1e3:.2f} ms", json.dumps(ctx.last_timing()))
