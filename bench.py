@@ -246,6 +246,7 @@ def run_ours(a, rank, world, local_rank):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
+    escalations = ctx.last_timing()["escalations"] if world == 1 else 0.0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -344,7 +345,7 @@ def run_ours(a, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": workload_name(a, world), "rows_per_gpu": n_local, "classes": a.classes, "k": k,
                        "l2": "inputs (10 GB per bank per GPU) far larger than the 126 MB L2; no flush needed",
-                       "accepted_rows": int(counts.sum().item()), "escalations": ctx.last_timing()["escalations"]},
+                       "accepted_rows": int(counts.sum().item()), "t2i_escalations_per_step": escalations},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()

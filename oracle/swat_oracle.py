@@ -201,7 +201,9 @@ def verbatim_t2t_ranked_sampler(prompt_tensors: dict, num_samples: int, threshol
         caption_embeddings = pre_extracted_feats[cls]["caption_feats"]
         class_prompt = np.asarray(prompt_tensors[cls]["mean"], dtype=np.float32)[None, :]       # :749-750
         sim = similarity(class_prompt, caption_embeddings)
-        items = sorted(list(zip(file_list, sim, range(len(file_list)))), key=lambda x: x[1], reverse=True)
+        embedding_list = [img_embeddings[i] for i in range(len(img_embeddings))]                 # :753 (N row views)
+        items = sorted(list(zip(file_list, sim, range(len(file_list)), embedding_list)), key=lambda x: x[1], reverse=True)
+        items = [(p, s_, r) for p, s_, r, _ in items]
         acc = walk_t2t(items, int(cls), num_samples, threshold,
                        duplicates_dict.get(str(int(cls)), set()) if isinstance(duplicates_dict, dict) else set(),
                        filtered_images_dict.get(str(int(cls)), set()) if isinstance(filtered_images_dict, dict) else set(),
@@ -241,8 +243,10 @@ def verbatim_t2t_ranked_t2i_tshd_sampler(prompt_tensors: dict, num_samples: int,
         caption_embeddings = pre_extracted_feats[cls]["caption_feats"]
         class_prompt = np.asarray(prompt_tensors[cls]["mean"], dtype=np.float32)[None, :]
         sim = similarity(class_prompt, caption_embeddings)
+        embedding_list = [img_embeddings[i] for i in range(len(img_embeddings))]                 # :805 (N row views)
         t2i = similarity(class_prompt, img_embeddings)
-        items = sorted(list(zip(file_list, sim, range(len(file_list)), t2i)), key=lambda x: x[1], reverse=True)
+        items = sorted(list(zip(file_list, sim, range(len(file_list)), t2i, embedding_list)), key=lambda x: x[1], reverse=True)
+        items = [(p, s_, r, t_) for p, s_, r, t_, _ in items]
         acc = walk_t2t_t2i(items, int(cls), num_samples, threshold, t2i_threshold,
                            duplicates_dict.get(str(int(cls)), set()) if isinstance(duplicates_dict, dict) else set(),
                            filtered_images_dict.get(str(int(cls)), set()) if isinstance(filtered_images_dict, dict) else set(),
