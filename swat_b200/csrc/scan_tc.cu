@@ -44,15 +44,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+__device__ __forceinline__ uint64_t globaltimer_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
+  uint64_t t0 = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();   // a hang becomes a launch failure, not a dead GPU
+    if (!done && (++spins & 0xfffu) == 0u) {       // a hang becomes a launch failure after 4 s, not a dead GPU
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   } while (!done);
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
@@ -275,9 +281,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       const int c_lo = p.blk_class[qb], c_hi = p.blk_class[qb + 1];
       const int n_ctas_qb = pairs_qb * kCtas, my_idx = pair_in_qb * kCtas + static_cast<int>(rank);
       volatile uint32_t* done = s_done;
+      const uint64_t t_start = globaltimer_ns();
       for (;;) {
         for (int c = c_lo + my_idx; c < c_hi; c += n_ctas_qb) refresh_tau(p.s.st, c);
         if (*done >= static_cast<uint32_t>(kEpiWarps)) break;
+        if (globaltimer_ns() - t_start > 20000000000ull) __trap();
         __nanosleep(2000);
       }
     }

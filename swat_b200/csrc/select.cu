@@ -9,22 +9,23 @@ namespace {
 
 constexpr int kSelThreads = 1024;
 
-// Exact top-`K` of n unique u64 keys in global memory, sorted descending into s_keys.
-// MSB-first 8-bit radix select narrows the candidate set until it fits the block sort
-// (usually 0-2 passes), then a bitonic sort orders it.  Returns min(n, >=K) sorted entries count
-// `total` (all keys >= the radix prefix); the caller takes the first min(K, total).
-__device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n, uint32_t K, uint64_t* s_keys,
+// Exact top-`K` of the non-zero u64 keys in keys[0..n) (zero = absent entry; real keys are unique),
+// sorted descending into s_keys.  MSB-first 8-bit radix select narrows the candidate set until it fits
+// the block sort (usually 0-2 passes), then a bitonic sort orders it.  `n_valid` = number of non-zero
+// keys.  Returns the number of sorted entries `total` (every key >= the radix prefix); the caller
+// takes the first min(K, total).
+__device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n, uint32_t n_valid, uint32_t K, uint64_t* s_keys,
                                   uint32_t* s_hist, uint32_t* s_misc) {
   const int tid = threadIdx.x;
   uint64_t prefix = 0, mask = 0;
-  uint32_t need = K, m = n, sure = 0;
+  uint32_t need = K, m = n_valid, sure = 0;
   int shift = 56;
-  while (sure + m > static_cast<uint32_t>(kSortCap)) {   // uniform: all values come from shared memory
+  while (sure + m > static_cast<uint32_t>(kSortCap) && shift >= 0) {   // uniform: all values come from shared memory
     for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
     for (uint32_t i = tid; i < n; i += kSelThreads) {
       const uint64_t key = keys[i];
-      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
+      if (key != 0ull && (key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
     }
     __syncthreads();
     if (tid == 0) {
@@ -40,19 +41,19 @@ __device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n,
     }
     __syncthreads();
     sure += s_misc[0];
-    need -= s_misc[0];
+    need -= min(need, s_misc[0]);
     m = s_misc[1];
     prefix |= static_cast<uint64_t>(s_misc[2]) << shift;
     mask |= 0xFFull << shift;
     shift -= 8;
     __syncthreads();
   }
-  // gather every key >= prefix (on the decided digits)
+  // gather every real key >= prefix (on the decided digits)
   if (tid == 0) s_misc[3] = 0;
   __syncthreads();
   for (uint32_t i = tid; i < n; i += kSelThreads) {
     const uint64_t key = keys[i];
-    if ((key & mask) >= prefix) {
+    if (key != 0ull && (key & mask) >= prefix) {
       const uint32_t pos = atomicAdd(&s_misc[3], 1u);
       if (pos < static_cast<uint32_t>(kSortCap)) s_keys[pos] = key;
     }
@@ -89,7 +90,7 @@ select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_sco
   const uint32_t appended = st.count[c];
   const uint32_t n = min(appended, st.cap);
   const uint32_t K = st.k_fetch;
-  const uint32_t total = select_sorted(st.cand + static_cast<size_t>(c) * st.cap, n, K, s_keys, s_hist, s_misc);
+  const uint32_t total = select_sorted(st.cand + static_cast<size_t>(c) * st.cap, n, n, K, s_keys, s_hist, s_misc);
   const uint32_t cnt = min(K, total);
   for (uint32_t i = threadIdx.x; i < K; i += kSelThreads) {
     const bool ok = i < cnt;
@@ -301,8 +302,8 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
   if (v) atomicAdd(&s_valid, v);
   __syncthreads();
   const uint32_t valid = s_valid;
-  const uint32_t total = select_sorted(kc, n, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
-  const uint32_t cnt = min(min(static_cast<uint32_t>(k_out), total), valid);
+  const uint32_t total = select_sorted(kc, n, valid, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
+  const uint32_t cnt = min(static_cast<uint32_t>(k_out), total);
   for (uint32_t i = tid; i < static_cast<uint32_t>(k_out); i += kSelThreads) {
     const bool ok = i < cnt;
     const uint64_t key = ok ? s_keys[i] : 0ull;

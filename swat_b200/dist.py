@@ -11,6 +11,7 @@ the merge proves exactness against each truncated shard's frontier.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -30,13 +31,24 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
                      row_class: Optional[torch.Tensor] = None, exclude: Optional[torch.Tensor] = None):
     """This shard's T2T top-``k_fetch`` per class (global row ids) with the T2I score of every
     candidate.  Returns ``(scores, rows, t2i | None, counts, truncated)`` on the device."""
+    dbg = os.environ.get("SWAT_DEBUG")
     cap, lists = None, None
+    cache = ctx.__dict__.setdefault("_job_cache", {})
     for _ in range(8):
-        job = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
+        key = (id(queries), int(k_fetch), float(t2t_threshold), cap, lists)
+        job = cache.get(key)
+        if job is None:                       # job buffers (survivor lists: ~100s of MB) are reused across calls
+            for old in cache.values():
+                old.close()
+            cache.clear()
+            job = cache[key] = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
+        else:
+            job.reset()
         job.scan(t2t_bank, row_base=0, row_class=row_class, exclude=exclude)
         scores, rows, counts, trunc = job.select()
         over = job.overflowed()
-        job.close()
+        if dbg:
+            print(f"[swat dist] scan+select k_fetch={k_fetch} overflow={over}", flush=True)
         if not over:
             break
         if over & 1:
@@ -57,6 +69,9 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
         scores, rows, t2i, counts, _ = _lib.t2i_walk(ctx, queries, t2i_bank, scores, rows, counts, None, k_fetch,
                                                      float("-inf"), img_row_base=0)
     rows = torch.where(rows >= 0, rows + int(row_offset), rows)
+    if dbg:
+        torch.cuda.synchronize()
+        print("[swat dist] local candidates ready", flush=True)
     return scores, rows, t2i, counts, trunc
 
 
@@ -95,6 +110,9 @@ def gather_merge(local, k: int, t2i_threshold: float, world: int, ctx=None, grou
     if world > 1:
         out = torch.empty(world * mine.numel(), dtype=torch.int32, device=mine.device)
         dist.all_gather_into_tensor(out, mine, group=group)
+        if os.environ.get("SWAT_DEBUG"):
+            torch.cuda.synchronize()
+            print("[swat dist] all_gather done", flush=True)
     else:
         out = mine
     g_scores, g_rows, g_t2i, g_counts, g_trunc = unpack(out, world, n_classes, k_fetch, t2i is not None)
@@ -117,10 +135,15 @@ def topk_sharded(ctx, queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: fl
     while True:
         local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset)
         res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
-        incomplete = int(res[4].sum().item())
-        if incomplete == 0 or k_fetch >= max_k_fetch:
-            if incomplete:
-                raise _lib.SwatError(-5, f"{incomplete} classes not provably exact at k_fetch={k_fetch}; "
-                                         "use the single-GPU in-pass predicate (swat_topk) for this data")
+        incomplete = int(res[4].sum().item())          # identical on every rank: the merge input is the all-gather
+        if incomplete == 0:
             return res
-        k_fetch = min(max_k_fetch, k_fetch * 4)
+        if k_fetch < max_k_fetch:
+            k_fetch = min(max_k_fetch, k_fetch * 4)
+            continue
+        # The walk reaches below the deepest over-fetch of some shard (few rows pass T2I): every shard
+        # computes its exact local top-k of predicate-passing rows (swat_topk falls back to the in-pass
+        # predicate where needed); top-k of passing rows is associative, so a plain merge finishes it.
+        s, r, t, c = _lib.topk(ctx, queries, t2t_bank, k, t2t_threshold, t2i_bank=t2i_bank, t2i_threshold=t2i_threshold,
+                               row_offset=row_offset)
+        return gather_merge((s, r, t, c, torch.zeros_like(c)), k, float("-inf"), world, ctx=ctx, group=group)

@@ -18,7 +18,7 @@ def main():
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(lr)
-    N, C, k = 4_000_000, 200, 500
+    N, C, k = int(os.environ.get('CHECK_ROWS', 4_000_000)), 200, 500
     chunk = 1 << 18
     assert N % (world * chunk) == 0 or world == 1 or True
     qc, queries, _ = synth.make_queries(C, 1, seed=7, dtype=torch.bfloat16)
@@ -30,8 +30,12 @@ def main():
     b = N if rank == world - 1 else (sdist.shard_range(N, rank + 1, world)[0] // chunk * chunk)
     cap, img, _ = synth.make_bank(b - a, qc, seed=7, device=dev, dtype=torch.bfloat16, chunk=chunk, row_offset=a, tie_block=0)
     ok = True
+    def log(*a):
+        print(f'[rank {rank}]', *a, flush=True)
     for t2i in (None, img):
+        log('sharded start', t2i is not None)
         res = sdist.topk_sharded(ctx, qs, cap, k, 0.0, t2i_bank=t2i, row_offset=a, world=world)
+        log('sharded done')
         if rank == 0:
             fcap, fimg, _ = synth.make_bank(N, qc, seed=7, device=dev, dtype=torch.bfloat16, chunk=chunk, tie_block=0)
             full = _lib.topk(ctx, qs, fcap, k, 0.0, t2i_bank=None if t2i is None else fimg)
