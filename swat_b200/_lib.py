@@ -157,6 +157,7 @@ class Queries:
             raise ValueError(f"queries must be [Q, {DIM}]")
         self.ctx = ctx
         self.n_queries = int(q.shape[0])
+        self.host_queries = q                      # kept for building sub-query sets (targeted escalation)
         coq = None
         if class_of_query is not None:
             coq = torch.as_tensor(class_of_query).detach().to("cpu", torch.int32).contiguous()
@@ -164,11 +165,29 @@ class Queries:
                 raise ValueError("class_of_query must have one entry per query")
         self.n_classes = int(n_classes if n_classes is not None else (self.n_queries if coq is None else int(coq.max()) + 1))
         self.reduce = REDUCE[reduce] if isinstance(reduce, str) else int(reduce)
+        self.host_class_of_query = coq if coq is not None else torch.arange(self.n_queries, dtype=torch.int32)
         self._h = C.c_void_p()
         _check(load().swat_queries_create(ctx._h, _ptr(q), self.n_queries, _ptr(coq), self.n_classes, self.reduce,
                                           C.byref(self._h)))
 
+    def subset(self, classes: Sequence[int]) -> "Queries":
+        """Query set restricted to ``classes`` (renumbered 0..len-1, same order); cached per class tuple."""
+        key = tuple(int(c) for c in classes)
+        cache = self.__dict__.setdefault("_subsets", {})
+        if key not in cache:
+            coq = self.host_class_of_query
+            sel = torch.cat([(coq == c).nonzero().flatten() for c in key])
+            new_coq = torch.repeat_interleave(torch.arange(len(key), dtype=torch.int32),
+                                              torch.tensor([int((coq == c).sum()) for c in key]))
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache))).close()
+            cache[key] = Queries(self.ctx, self.host_queries[sel], new_coq, len(key), self.reduce)
+        return cache[key]
+
     def close(self):
+        for sub in self.__dict__.get("_subsets", {}).values():
+            sub.close()
+        self.__dict__["_subsets"] = {}
         if self._h:
             load().swat_queries_destroy(self._h)
             self._h = C.c_void_p()

@@ -38,9 +38,8 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
         key = (id(queries), int(k_fetch), float(t2t_threshold), cap, lists)
         job = cache.get(key)
         if job is None:                       # job buffers (survivor lists: ~100s of MB) are reused across calls
-            for old in cache.values():
-                old.close()
-            cache.clear()
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache))).close()
             job = cache[key] = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
         else:
             job.reset()
@@ -126,24 +125,34 @@ def topk_sharded(ctx, queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: fl
                  t2i_bank: Optional[torch.Tensor] = None, t2i_threshold: float = 0.25, row_offset: int = 0,
                  world: int = 1, group=None, k_fetch: Optional[int] = None, max_k_fetch: int = 4096):
     """Whole multi-GPU pipeline for this rank's shard.  Every rank returns the merged result.
-    Escalates ``k_fetch`` (x4, collectively) while any class is not provably exact."""
+    Classes whose walk is not provably exact are escalated collectively (4x deeper over-fetch for
+    those classes only, finally the exact in-pass predicate)."""
     if k_fetch is None:
         # T2T only: the merged top-k never reaches below a shard's k-th candidate, k suffices.
         # T2I walk: over-fetch so that k candidates pass the predicate above every shard's frontier.
         k_fetch = k if t2i_bank is None else max(1024, 2 * k)
     k_fetch = max(1, min(int(k_fetch), max_k_fetch))
-    while True:
-        local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset)
-        res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
-        incomplete = int(res[4].sum().item())          # identical on every rank: the merge input is the all-gather
-        if incomplete == 0:
-            return res
-        if k_fetch < max_k_fetch:
-            k_fetch = min(max_k_fetch, k_fetch * 4)
-            continue
+    local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset)
+    res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
+    bad = res[4].nonzero().flatten().tolist()          # identical on every rank: the merge input is the all-gather
+    if not bad:
+        return res
+    out_s, out_r, out_t, out_c, _ = res
+    if k_fetch < max_k_fetch:
+        # targeted escalation: only the classes that are not provably exact are re-scanned, 4x deeper
+        sub = queries.subset(bad)
+        r2 = topk_sharded(ctx, sub, t2t_bank, k, t2t_threshold, t2i_bank, t2i_threshold, row_offset, world, group,
+                          k_fetch=min(max_k_fetch, 4 * k_fetch), max_k_fetch=max_k_fetch)
+    else:
         # The walk reaches below the deepest over-fetch of some shard (few rows pass T2I): every shard
         # computes its exact local top-k of predicate-passing rows (swat_topk falls back to the in-pass
         # predicate where needed); top-k of passing rows is associative, so a plain merge finishes it.
-        s, r, t, c = _lib.topk(ctx, queries, t2t_bank, k, t2t_threshold, t2i_bank=t2i_bank, t2i_threshold=t2i_threshold,
+        sub = queries.subset(bad)
+        s, r, t, c = _lib.topk(ctx, sub, t2t_bank, k, t2t_threshold, t2i_bank=t2i_bank, t2i_threshold=t2i_threshold,
                                row_offset=row_offset)
-        return gather_merge((s, r, t, c, torch.zeros_like(c)), k, float("-inf"), world, ctx=ctx, group=group)
+        r2 = gather_merge((s, r, t, c, torch.zeros_like(c)), k, float("-inf"), world, ctx=ctx, group=group)
+    idx = torch.tensor(bad, device=out_s.device)
+    out_s[idx], out_r[idx], out_c[idx] = r2[0], r2[1], r2[3]
+    if out_t is not None:
+        out_t[idx] = r2[2]
+    return out_s, out_r, out_t, out_c, torch.zeros_like(out_c)
