@@ -172,7 +172,7 @@ def run_reference(a, rank, world):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     total_steps = a.steps + a.warmup
-    budget = 150.0 / max(total_steps, 1)                       # seconds per step
+    budget = float(os.environ.get("SWAT_BENCH_REF_BUDGET_S", 150.0)) / max(total_steps, 1)     # seconds per step
     n_rows = 2048
     est, _ = cpu_verbatim(a, n_rows, n_cls=8)                   # calibrate on 8 classes
     n_rows = int(max(1024, min(200_000, n_rows * budget / max(est, 1e-6))))

@@ -1,0 +1,106 @@
+"""Drop-in boundary on the GPU: the host mirror of the reference's samplers and the CLI, against the
+reference's golden outputs and the oracle's verbatim port."""
+import json
+import logging
+import os
+import pickle
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import swat_oracle as so
+from tests.golden_util import assert_walk_equal, load_bank_case, make_paths
+
+pytestmark = pytest.mark.gpu
+TIE_TOL = 2e-5
+
+
+def _case(name):
+    z, meta, cap, img, q = load_bank_case(name)
+    class_ids, labels = z["class_ids"], z["labels"]
+    paths, cmap = make_paths(labels, class_ids)
+    raw = {"caption_features": torch.from_numpy(cap), "image_features": torch.from_numpy(img),
+           "labels": torch.from_numpy(class_ids[labels]), "filepath": paths}
+    prompts = {str(class_ids[c]): {"mean": torch.from_numpy(q[c])} for c in range(len(class_ids))}
+    return z, meta, cap, img, q, raw, prompts, paths, cmap
+
+
+@pytest.mark.parametrize("name,dtype", [("bank_bf16", "bf16"), ("bank_f32", "f32")])
+def test_samplers_match_reference_outputs(tmp_path, name, dtype):
+    """t2t_ranked_sampler / t2t_ranked_t2i_tshd_sampler with the reference's signature and return
+    structure, partitioned (transform_extracted_fea) and unpartitioned (aliased dict)."""
+    from swat_b200 import retrieval
+    z, meta, cap, img, q, raw, prompts, paths, cmap = _case(name)
+    S = so.score_matrix(cap, q)
+    cmap_path = str(tmp_path / "cap.map")
+    pickle.dump(cmap, open(cmap_path, "wb"))
+    args = Namespace(dataset="synthetic", output_folder=str(tmp_path / "out"), prefix="T2T", bank_dtype=dtype, caption_map_path=cmap_path)
+    lg = logging.getLogger("t")
+    path_row = {p: i for i, p in enumerate(paths)}
+    feats_p = retrieval.transform_extracted_fea(raw)
+    feats_u = {k: {"file_paths": paths, "feats": raw["image_features"], "caption_feats": raw["caption_features"]} for k in prompts}
+    for tag, feats in (("part", feats_p), ("unpart", feats_u)):
+        for m, fn in (("t2t", retrieval.t2t_ranked_sampler), ("t2t_t2i", retrieval.t2t_ranked_t2i_tshd_sampler)):
+            ms, nd = fn(args, lg, prompts, int(z["k"]), 0.0, feats)
+            assert nd == meta["counts"][tag][m], f"{name} {tag} {m}"
+            ref_rows, ref_labels = z[f"{tag}_{m}_rows"], z[f"{tag}_{m}_labels"]
+            assert torch.cat(ms["label_list"]).tolist() == ref_labels.tolist()
+            pos = 0
+            for files, labs, feat in zip(ms["file_list"], ms["label_list"], ms["feature_list"]):
+                n = len(files)
+                cid = int(labs[0]); c = int(np.nonzero(z["class_ids"] == cid)[0][0])
+                got = [path_row[p] for p in files]
+                assert_walk_equal(got, ref_rows[pos:pos + n], lambda r, c=c: S[r, c], TIE_TOL, boundary_tol=1e-3, what=f"{name} {tag} {m} {cid}")
+                np.testing.assert_allclose(feat.numpy(), img[got], atol=0)          # feature_list = the image features of the winners
+                pos += n
+            sl = "sampled_list.txt" if m == "t2t_t2i" else "T2T_sampled_list.txt"
+            lines = open(os.path.join(args.output_folder, sl)).read().split("\n")
+            assert len(lines) == sum(nd.values()) and lines[0].split(", ")[-1].startswith("synthetic caption")
+
+
+def test_cli_writes_reference_outputs(tmp_path, monkeypatch):
+    """python sample_retrieval.py --prefix ... : {prefix}.txt, {prefix}_num_imgs_sampled.json, sampling.log,
+    copy into data/{dataset}/ -- compared with the oracle's verbatim port of the reference script."""
+    from swat_b200 import sample_retrieval as cli, shards
+    z, meta, cap, img, q, raw, prompts, paths, cmap = _case("bank_bf16")
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("retrieved/semi-aves"); os.makedirs("data/semi-aves/prompts")
+    pth = "retrieved/semi-aves/semi-aves_vitb32_openclip_laion400m_mined.pth"
+    shards.save_mined_pth(pth, raw["caption_features"], raw["image_features"], raw["labels"], paths)
+    torch.save({"alternates": prompts}, "data/semi-aves/prompts/semi-aves_vitb32_openclip_laion400m_prompt_tensors.pth")
+    pickle.dump(cmap, open("cap.map", "wb"))
+    for method, prefix, key in (("T2T-rank", "T2T40", "t2t"), ("T2T-rank-T2I-tshd", "T2T40+T2I0.25", "t2t_t2i")):
+        fn, n = cli.main(["--prefix", prefix, "--dataset", "semi-aves", "--root", "retrieved", "--num_samples", str(int(z["k"])),
+                          "--sampling_method", method, "--bank_dtype", "bf16", "--data_dir", "data", "--caption_map_path", "cap.map",
+                          "--log_mode", "file"])
+        out = f"output/semi-aves_vitb32_openclip_laion400m_{prefix}"
+        assert fn == f"{out}/{prefix}.txt" and os.path.exists(f"{out}/sampling.log")
+        text = open(fn).read()
+        assert open(f"data/semi-aves/{prefix}.txt").read() == text
+        counts = json.load(open(f"{out}/{prefix}_num_imgs_sampled.json"))
+        assert counts == meta["counts"]["part"][key] and n == sum(counts.values())
+        ref_lines = [f"{paths[r]} {l} 0" for r, l in zip(z[f"part_{key}_rows"].tolist(), z[f"part_{key}_labels"].tolist())]
+        got_lines = text.strip("\n").split("\n")
+        assert len(got_lines) == len(ref_lines)
+        assert [l.split(" ")[1:] for l in got_lines] == [l.split(" ")[1:] for l in ref_lines]      # class-major, labels, source flag
+        same = sum(a == b for a, b in zip(got_lines, ref_lines))
+        assert sorted(got_lines) == sorted(ref_lines) or same >= len(ref_lines) - 8, f"{same}/{len(ref_lines)} lines identical"
+        for line in got_lines:                                                                     # MyDataset's parser (dataset_utils.py:148-154)
+            p, lab, src = line.strip("\n").split(" ")
+            assert int(src) == 0 and int(lab) in z["class_ids"].tolist()
+
+
+def test_s1_primitives_on_gpu():
+    from swat_b200 import retrieval
+    z = np.load("tests/golden/primitives.npz")
+    X, P, F = torch.from_numpy(z["X"]), torch.from_numpy(z["P"]), z["F"]
+    np.testing.assert_allclose(retrieval.t2t_similarity(P, X), z["t2t_R3"], atol=2e-6)
+    np.testing.assert_allclose(retrieval.cal_t2i_similarity(P[:1], X), z["t2t_R1"], atol=2e-6)
+    one = retrieval.t2t_similarity(P[:1], X[:1])
+    assert isinstance(one, list) and len(one) == 1
+    for mode in ("min", "max", "mean"):
+        np.testing.assert_allclose(retrieval.i2i_similarity_p2p([f for f in F], X, mode), z[f"p2p_{mode}"], atol=2e-6)
+    with pytest.raises(ValueError):
+        retrieval.i2i_similarity_p2p([f for f in F], X, "median")
