@@ -110,6 +110,7 @@ struct swat_queries {
   float* d_q_f32 = nullptr; uint16_t* d_q_bf16 = nullptr; int32_t* d_class_begin = nullptr;
   float* d_qp_f32 = nullptr; uint16_t* d_qp_bf16 = nullptr; int32_t* d_col_class = nullptr; float* d_col_count = nullptr;
   int32_t* d_blk_class = nullptr;     // [n_qb+1] first class of each Q block
+  int32_t* d_blk_split = nullptr;     // [n_qb] grouped reduces: first column of the second epilogue warp set
   void* d_arena = nullptr;            // one allocation backs every device array above
   std::vector<float> h_q;             // host copy (sub-query sets for targeted escalation)
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
@@ -207,6 +208,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     p.smem_b_bytes = static_cast<uint32_t>(8) * (q->n_blk / q->ctas) * 128;
     p.bank_hint = (q->n_qb == 1) ? 0x12F0000000000000ull /* evict_first: streamed once */ : 0x1000000000000000ull;
     p.blk_class = q->d_blk_class;
+    p.blk_split = q->d_blk_split;
     int grid = ctx->sm_count;
     if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
     grid = std::max(q->ctas, grid / q->ctas * q->ctas);
@@ -728,12 +730,36 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   swat_queries* q = new swat_queries();
   q->ctx = ctx; q->Q = n_queries; q->C = n_classes; q->reduce = reduce; q->class_begin = cb; q->ctas = ctx->cta_group;
   q->h_q.assign(h_queries, h_queries + static_cast<size_t>(n_queries) * kDim);
-  const int max_cols = (q->ctas == 2) ? 256 : 144;
+  int max_cols = (q->ctas == 2) ? 256 : 144;
+  int max_group = 1;
+  for (int c = 0; c < n_classes; ++c) max_group = std::max(max_group, cb[c + 1] - cb[c]);
+  // grouped reduces: a class may not straddle the column where the second epilogue warp set starts,
+  // which can cost up to max_group-1 padding columns per block
+  if (reduce != SWAT_REDUCE_NONE) max_cols -= (max_group - 1);
   std::vector<int> first;
-  if (!plan_blocks(cb, max_cols, q->n_qb, q->n_blk, first)) {
+  if (max_cols < max_group || !plan_blocks(cb, max_cols, q->n_qb, q->n_blk, first)) {
     delete q;
-    return fail(SWAT_ERR_UNSUPPORTED, "a class has more than %d queries; cannot keep it resident", max_cols);
+    return fail(SWAT_ERR_UNSUPPORTED, "a class has %d queries; cannot keep it resident", max_group);
   }
+  // column layout of every block
+  std::vector<std::vector<std::pair<int, int>>> place(q->n_qb);   // per block: (class, first column)
+  std::vector<int32_t> split(q->n_qb, 0);
+  int widest = 0;
+  for (int b = 0; b < q->n_qb; ++b) {
+    const int cols = cb[first[b + 1]] - cb[first[b]];
+    const int H = (reduce == SWAT_REDUCE_NONE) ? (1 << 30) : ((cols + 1) / 2 + 31) / 32 * 32;
+    int col = 0;
+    for (int c = first[b]; c < first[b + 1]; ++c) {
+      const int R = cb[c + 1] - cb[c];
+      if (col < H && col + R > H) col = H;          // never straddle the split
+      place[b].push_back({c, col});
+      col += R;
+    }
+    split[b] = H;
+    widest = std::max(widest, col);
+  }
+  q->n_blk = std::max(16, (widest + 15) / 16 * 16);
+  for (int b = 0; b < q->n_qb; ++b) split[b] = std::min(split[b], q->n_blk);
   q->n_cols = q->n_qb * q->n_blk;
   q->n_stages = tc_pick_stages(q->n_blk, q->ctas, ctx->smem_optin);
   // host staging: padded layouts
@@ -743,20 +769,23 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   std::vector<int32_t> h_cls(NC, -1);
   for (size_t i = 0; i < Q * kDim; ++i) h_bf[i] = f32_to_bf16_rne(h_queries[i]);
   for (int b = 0; b < q->n_qb; ++b) {
-    int col = b * q->n_blk;
-    for (int c = first[b]; c < first[b + 1]; ++c)
+    for (const auto& pc : place[b]) {
+      const int c = pc.first;
+      int col = b * q->n_blk + pc.second;
       for (int qi = cb[c]; qi < cb[c + 1]; ++qi, ++col) {
         memcpy(&h_pf[static_cast<size_t>(col) * kDim], &h_queries[static_cast<size_t>(qi) * kDim], kDim * 4);
         memcpy(&h_pbf[static_cast<size_t>(col) * kDim], &h_bf[static_cast<size_t>(qi) * kDim], kDim * 2);
         h_cls[col] = c;
         if (qi == cb[c + 1] - 1) h_cnt[col] = static_cast<float>(cb[c + 1] - cb[c]);
       }
+    }
   }
   // one device arena + one staged upload: creating a query set costs one cudaMalloc and one copy
   auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t o_qf = 0, o_qb = o_qf + up256(Q * kDim * 4), o_cb = o_qb + up256(Q * kDim * 2),
                o_pf = o_cb + up256((n_classes + 1) * 4), o_pb = o_pf + up256(NC * kDim * 4), o_cc = o_pb + up256(NC * kDim * 2),
-               o_cn = o_cc + up256(NC * 4), o_bc = o_cn + up256(NC * 4), total = o_bc + up256((q->n_qb + 1) * 4);
+               o_cn = o_cc + up256(NC * 4), o_bc = o_cn + up256(NC * 4), o_bs = o_bc + up256((q->n_qb + 1) * 4),
+               total = o_bs + up256(q->n_qb * 4);
   std::vector<char> stage(total, 0);
   memcpy(&stage[o_qf], h_queries, Q * kDim * 4);
   memcpy(&stage[o_qb], h_bf.data(), Q * kDim * 2);
@@ -766,6 +795,7 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   memcpy(&stage[o_cc], h_cls.data(), NC * 4);
   memcpy(&stage[o_cn], h_cnt.data(), NC * 4);
   memcpy(&stage[o_bc], first.data(), (q->n_qb + 1) * 4);
+  memcpy(&stage[o_bs], split.data(), q->n_qb * 4);
   cudaError_t e = cudaMalloc(&q->d_arena, total);
   if (e == cudaSuccess) e = cudaMemcpy(q->d_arena, stage.data(), total, cudaMemcpyHostToDevice);
   char* base = static_cast<char*>(q->d_arena);
@@ -777,6 +807,7 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   q->d_col_class = reinterpret_cast<int32_t*>(base + o_cc);
   q->d_col_count = reinterpret_cast<float*>(base + o_cn);
   q->d_blk_class = reinterpret_cast<int32_t*>(base + o_bc);
+  q->d_blk_split = reinterpret_cast<int32_t*>(base + o_bs);
   if (e != cudaSuccess) {
     swat_queries_destroy(q);
     return fail(SWAT_ERR_CUDA, "query upload failed: %s", cudaGetErrorString(e));

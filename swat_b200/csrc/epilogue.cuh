@@ -126,61 +126,65 @@ static __device__ __noinline__ uint32_t slow_append(const SlowCtx sc, uint32_t l
   return n;
 }
 
+// Threshold the fast path compares the *accumulated* value of a class against.  For MEAN the
+// accumulator is the sum, so the class threshold is scaled by the group size and loosened by a few ulp:
+// the fast filter may only ever let slightly MORE rows through (the survivor lists are supersets; the
+// exact value sum/R is what gets stored and the partition step filters on it exactly).
+template <int RED> __device__ __forceinline__ float fast_tau(float tau, float cnt) {
+  if (RED != RED_MEAN) return tau;
+  if (!(cnt > 0.0f) || !isfinite(tau)) return tau;
+  const float t = tau * cnt;
+  return t - fabsf(t) * 1.0e-6f - 1.0e-30f;
+}
+
 // NC columns starting at block-local column col0.  endmask bit j: column col0+j closes a class.
 //
-// RED_NONE (one query per class, the reference's default ['mean'] prompt): branch-free.  The NC
-// compares are independent and fold into one pass mask; ONE vote decides whether anybody in the warp
-// has a survivor in this chunk.  tau is +inf at padding columns, so they never pass.
-// Grouped reduces (synonym max / mean / min): running reduce along the columns, one vote per class.
+// Branch-free for every reduce mode: the running reduce is carried along the columns (reset after a
+// closing column by a select on the warp-uniform endmask bit), each column's value is compared with
+// the per-column threshold table -- NaN everywhere except at closing columns -- and the results
+// fold into one pass mask; ONE vote decides whether anybody in the warp has a survivor in the chunk.
 template <int NC, int RED, bool PART, bool DUAL, bool DENSE, bool ATOMIC_LIST>
-__device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& sc, EpiCtx& cx, const float (&v)[NC],
-                                              const float (&v2)[NC], int col0, uint32_t endmask) {
-  if (RED == RED_NONE && !DENSE) {
-    const float* tau = cx.tau_col + col0;
-    const int32_t* cls = cx.cls_col + col0;
-    uint32_t mask = 0;
+__device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& sc, EpiCtx& cx, float (&v)[NC],
+                                              float (&v2)[NC], int col0, uint32_t endmask) {
+  const float* tau = cx.tau_col + col0;
+  const int32_t* cls = cx.cls_col + col0;
+  const float* cnt = cx.cnt_col + col0;
+  if (DENSE) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      bool p = cx.row_valid && (v[j] >= tau[j]);
-      if (DUAL) p = p && (v2[j] >= a.t2i_thr);
-      if (PART) p = p && (cx.my_cls == cls[j]);
-      mask |= static_cast<uint32_t>(p) << j;
-    }
-    if (__any_sync(0xffffffffu, mask != 0u)) {
-      const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        if ((any >> j) & 1u)   // warp-uniform
-          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], v[j], (mask >> j) & 1u, cx.row);
+      cx.acc = (RED == RED_NONE) ? v[j] : red_op<RED>(cx.acc, v[j]);
+      if ((endmask >> j) & 1u) {  // warp-uniform
+        if (cx.row_valid) a.dense_out[static_cast<size_t>(cx.row) * a.n_classes + cls[j]] = red_fin<RED>(cx.acc, cnt[j]);
+        cx.acc = red_init<RED>();
       }
     }
     return;
   }
+  uint32_t mask = 0;
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
-    if (RED == RED_NONE) {
-      cx.acc = v[j];
-      if (DUAL) cx.acc2 = v2[j];
-    } else {
+    if (RED != RED_NONE) {
+      const bool end = (endmask >> j) & 1u;
       cx.acc = red_op<RED>(cx.acc, v[j]);
-      if (DUAL) cx.acc2 = red_op<RED>(cx.acc2, v2[j]);
+      v[j] = cx.acc;                                   // value of the class that closes here (if any)
+      cx.acc = end ? red_init<RED>() : cx.acc;
+      if (DUAL) {
+        cx.acc2 = red_op<RED>(cx.acc2, v2[j]);
+        v2[j] = cx.acc2;
+        cx.acc2 = end ? red_init<RED>() : cx.acc2;
+      }
     }
-    if ((endmask >> j) & 1u) {  // warp-uniform
-      const int col = col0 + j;
-      const float val = red_fin<RED>(cx.acc, cx.cnt_col[col]);
-      if (DENSE) {
-        if (cx.row_valid) a.dense_out[static_cast<size_t>(cx.row) * a.n_classes + cx.cls_col[col]] = val;
-      } else {
-        bool pass = cx.row_valid && (val >= cx.tau_col[col]);
-        if (DUAL) pass = pass && (red_fin<RED>(cx.acc2, cx.cnt_col[col]) >= a.t2i_thr);
-        if (PART) pass = pass && (cx.my_cls == cx.cls_col[col]);
-        if (__any_sync(0xffffffffu, pass))
-          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cx.cls_col[col], val, pass, cx.row);
-      }
-      if (RED != RED_NONE) {
-        cx.acc = red_init<RED>();
-        if (DUAL) cx.acc2 = red_init<RED>();
-      }
+    bool p = cx.row_valid && (v[j] >= tau[j]);
+    if (DUAL) p = p && (red_fin<RED>(v2[j], cnt[j]) >= a.t2i_thr);
+    if (PART) p = p && (cx.my_cls == cls[j]);
+    mask |= static_cast<uint32_t>(p) << j;
+  }
+  if (__any_sync(0xffffffffu, mask != 0u)) {
+    const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if ((any >> j) & 1u)   // warp-uniform
+        cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], red_fin<RED>(v[j], cnt[j]), (mask >> j) & 1u, cx.row);
     }
   }
 }

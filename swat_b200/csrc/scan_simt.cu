@@ -60,8 +60,8 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
       const float cnt = in ? a.col_count[c] : 0.0f;
       s_cls[tid] = cls;
       s_cnt[tid] = cnt;
-      float t = INFINITY;
-      if (!DENSE && cls >= 0 && cnt > 0.0f) t = f32_dec(ld_cg_u32(&a.st.tau_enc[cls]));
+      float t = __int_as_float(0x7fc00000);   // NaN: never passes (see scan_tc.cu)
+      if (!DENSE && cls >= 0 && cnt > 0.0f) t = fast_tau<RED>(f32_dec(ld_cg_u32(&a.st.tau_enc[cls])), cnt);
       s_tau[tid] = t;
       const uint32_t m = __ballot_sync(0xffffffffu, cnt > 0.0f);
       if (tid == 0) s_endmask = m;
@@ -126,7 +126,7 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
       }
     }
     if constexpr (DUAL) {
-      process_chunk<kNc, RED, PART, DUAL, DENSE, true>(a, sc, cx, acc, reinterpret_cast<const float(&)[kNc]>(acc2), 0, endmask);
+      process_chunk<kNc, RED, PART, DUAL, DENSE, true>(a, sc, cx, acc, reinterpret_cast<float(&)[kNc]>(acc2), 0, endmask);
     } else {
       process_chunk<kNc, RED, PART, false, DENSE, true>(a, sc, cx, acc, acc, 0, endmask);
     }

@@ -207,11 +207,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 256; c += kThreads) {
-    // thresholds by column: +inf at padding / non-closing columns, the class threshold elsewhere.
+    // thresholds by column: NaN at padding / non-closing columns, the class threshold elsewhere.
     // Every entry is always SOME valid threshold, so the epilogue warps refresh and read this table
     // without any barrier (a stale value is only more conservative).
-    float t = INFINITY;
-    if (!DENSE && s_cls[c] >= 0 && s_cnt[c] > 0.0f) t = f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c]]));
+    // NaN, not +inf, at padding / non-closing columns: a trailing partial chunk reads uninitialised TMEM
+    // columns and +inf >= +inf would pass, whereas every comparison with NaN is false.
+    float t = __int_as_float(0x7fc00000);
+    if (!DENSE && s_cls[c] >= 0 && s_cnt[c] > 0.0f) t = fast_tau<RED>(f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c]])), s_cnt[c]);
     s_tau[c] = t;
   }
   if (threadIdx.x < 8) {
@@ -304,6 +306,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     cx.tau_col = s_tau;
     const bool my_col_live = !DENSE && etid < NB && s_cls[etid] >= 0 && s_cnt[etid] > 0.0f;
     const uint32_t* my_tau_src = &p.s.st.tau_enc[my_col_live ? s_cls[etid] : 0];
+    const float my_cnt = my_col_live ? s_cnt[etid] : 0.0f;
     // each epilogue thread owns one column of the threshold table: the value for the NEXT tile is
     // fetched while the current tile is processed
     uint32_t tnext = 0;
@@ -312,7 +315,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
       if (my_col_live) {
-        s_tau[etid] = f32_dec(tnext);
+        s_tau[etid] = fast_tau<RED>(f32_dec(tnext), my_cnt);
         tnext = ld_cg_u32(my_tau_src);
       }
       const int64_t row = t * kTileRows + rank * 128 + quad * 32 + lane;
@@ -338,16 +341,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       };
       uint32_t ra[32], rb[32];
       float v[32];
-      // this warp's chunks: columns 32*(half + 2*i); grouped reduces need every column in order, so
-      // they keep one warp per quadrant walking all chunks (the second set of warps idles)
-      constexpr bool kSplit = (RED == RED_NONE);
-      const int first = kSplit ? 32 * half : 0;
-      constexpr int kStep = kSplit ? 64 : 32;
-      if (first < NB && (kSplit || half == 0)) {
+      // One-query-per-class: the two warps of a quadrant take interleaved 32-column chunks.
+      // Grouped reduces walk columns in order, so the block is cut at a class boundary (`split`,
+      // a multiple of 32 chosen by the host) and each warp takes one contiguous part.
+      constexpr bool kInterleave = (RED == RED_NONE);
+      const int split = kInterleave ? NB : p.blk_split[qb];
+      const int first = kInterleave ? 32 * half : (half == 0 ? 0 : split);
+      const int last = kInterleave ? NB : (half == 0 ? split : NB);
+      constexpr int kStep = kInterleave ? 64 : 32;
+      if (first < last) {
         tmem_ld32_issue(taddr + first, ra);
         tmem_wait(ra);
-        for (int c0 = first; c0 < NB; c0 += 2 * kStep) {
-          const bool has_b = c0 + kStep < NB, has_next = c0 + 2 * kStep < NB;
+        for (int c0 = first; c0 < last; c0 += 2 * kStep) {
+          const bool has_b = c0 + kStep < last, has_next = c0 + 2 * kStep < last;
           if (has_b) tmem_ld32_issue(taddr + c0 + kStep, rb); else release_tmem();
           to_f32x32(ra, v);
           process_chunk<32, RED, PART, false, DENSE, false>(p.s, sc, cx, v, v, c0, s_end[c0 >> 5]);

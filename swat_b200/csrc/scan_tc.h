@@ -14,6 +14,7 @@ struct TcArgs {
   uint32_t smem_b_bytes;  // per-CTA bytes of the resident query block
   uint64_t bank_hint;     // L2 cache policy for bank tiles
   const int32_t* blk_class;  // [n_qb+1] first class of each Q block
+  const int32_t* blk_split;  // [n_qb] grouped reduces: column (multiple of 32) where the second epilogue warp set starts
 };
 
 size_t tc_smem_bytes(int n_blk, int ctas, int n_stages);
