@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--t2t-only", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--overfetch", type=int, default=0, help="first k_fetch of the T2I walk (0 = library default)")
     return ap.parse_args()
 
 
@@ -207,6 +208,8 @@ def run_ours(a, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local_rank)
+    if a.overfetch:
+        ctx.set_option("overfetch", a.overfetch)
     n_local = a.rows
     row_offset = rank * n_local
     qc, queries, _ = synth.make_queries(a.classes, 1, seed=a.seed, dtype=torch.bfloat16)

@@ -83,12 +83,13 @@ struct swat_ctx {
   int64_t list_entries = 0;   // total survivor-list entries, 0 = auto
   int overfetch = 0;          // 0 = auto
   int64_t host_chunk_rows = 1 << 18;
+  int64_t bootstrap_rows = 32768;   // dense prefix used to seed thresholds of a fresh job (0 = off)
   // stats
   int64_t launches = 0;
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // workspaces for the whole-pipeline calls
   DevBuf w_scores, w_rows, w_counts, w_trunc, w_t2i, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
-  DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts;
+  DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
   cudaStream_t copy_stream = nullptr, work_stream = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_used[3] = {nullptr, nullptr, nullptr};
@@ -113,6 +114,8 @@ struct swat_queries {
   int32_t* d_blk_split = nullptr;     // [n_qb] grouped reduces: first column of the second epilogue warp set
   void* d_arena = nullptr;            // one allocation backs every device array above
   std::vector<float> h_q;             // host copy (sub-query sets for targeted escalation)
+  mutable int32_t kfetch_hint = 0;    // deepest over-fetch a T2I walk over this query set has needed so far
+  mutable int32_t last_k_fetch = 0;   // over-fetch at which the last pipeline run completed
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
   CUtensorMap tm_q;
 };
@@ -122,6 +125,7 @@ struct swat_job {
   const swat_queries* q = nullptr;
   JobState st;
   int n_classes_alloc = 0;
+  bool fresh = true;                  // no rows folded in since the last reset
   cudaStream_t last_stream = nullptr;
 };
 
@@ -194,14 +198,13 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
   a.exclude = d_exclude;
   a.t2i_thr = t2i_threshold;
   a.dense_out = dense_out;
+  a.dense_ld = q->C;
+  a.dense_transposed = 0;
   a.n_classes = q->C;
   job->last_stream = stream;
   if (engine == SWAT_ENGINE_TC) {
     if (q->n_stages <= 0) return fail(SWAT_ERR_UNSUPPORTED, "query block does not fit in shared memory for the tcgen05 engine");
-    CUtensorMap tm_bank;
-    SW_OK(encode_2d_bf16(ctx, &tm_bank, d_bank, static_cast<uint64_t>(n_rows), 128));
     TcArgs p;
-    p.s = a;
     p.n_qb = q->n_qb;
     p.n_blk = q->n_blk;
     p.n_stages = q->n_stages;
@@ -214,12 +217,44 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     grid = std::max(q->ctas, grid / q->ctas * q->ctas);
     if (dense_out == nullptr && static_cast<uint32_t>(grid) * kTcEpiWarps > job->st.n_lists)
       return fail(SWAT_ERR_INVALID, "grid of %d CTAs needs %d survivor lists, job has %u", grid, grid * kTcEpiWarps, job->st.n_lists);
+    const char* bank = static_cast<const char*>(d_bank);
+    // ---- threshold bootstrap: a fresh job would append every non-negative score of its first waves
+    // (thresholds start at the user threshold).  Dense-score a small prefix with the same kernel, take
+    // its exact top-k_fetch per class, and start the real scan with selective thresholds.
+    int64_t B = 0;
+    if (dense_out == nullptr && job->fresh && ctx->bootstrap_rows > 0 && d_row_class == nullptr && d_exclude == nullptr) {
+      B = std::min<int64_t>(ctx->bootstrap_rows, (512ll << 20) / (4ll * q->C)) / 256 * 256;
+      if (B < 8192 || n_rows < 8 * B || static_cast<uint32_t>(grid) * kTcEpiWarps >= job->st.n_lists) B = 0;
+    }
+    if (B > 0) {
+      SW_OK(ctx->w_boot.ensure(static_cast<size_t>(q->C) * B * 4));
+      CUtensorMap tm_pre;
+      SW_OK(encode_2d_bf16(ctx, &tm_pre, bank, static_cast<uint64_t>(B), 128));
+      TcArgs pd = p;
+      pd.s = a;
+      pd.s.n_rows = B;
+      pd.s.dense_out = ctx->w_boot.as<float>();
+      pd.s.dense_ld = B;
+      pd.s.dense_transposed = 1;
+      pd.bank_hint = 0x1000000000000000ull;
+      CU_OK(launch_scan_tc(&tm_pre, &q->tm_q, pd, q->ctas, q->reduce, false, true, grid, stream));
+      CU_OK(launch_bootstrap(job->st, q->C, ctx->w_boot.as<float>(), static_cast<uint32_t>(B), a.row_base,
+                             static_cast<uint32_t>(grid) * kTcEpiWarps, stream));
+      ctx->launches += 2;
+      bank += static_cast<size_t>(B) * kDim * 2;
+      a.n_rows = n_rows - B;
+      a.row_base += static_cast<uint32_t>(B);
+    }
+    CUtensorMap tm_bank;
+    SW_OK(encode_2d_bf16(ctx, &tm_bank, bank, static_cast<uint64_t>(a.n_rows), 128));
+    p.s = a;
     CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
   } else {
     const void* qp = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_qp_bf16) : static_cast<const void*>(q->d_qp_f32);
     CU_OK(launch_scan_simt(a, d_bank, d_t2i_bank, qp, dtype, q->reduce, d_row_class != nullptr, dense_out != nullptr, stream));
   }
   ctx->launches += 1;
+  if (dense_out == nullptr) job->fresh = false;
   return SWAT_OK;
 }
 
@@ -435,6 +470,7 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (rc == SWAT_OK && e != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "splicing escalated classes failed: %s", cudaGetErrorString(e));
+  q->last_k_fetch = sub->last_k_fetch;
   if (!cached) swat_queries_destroy(sub);
   return rc;
 }
@@ -455,6 +491,9 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     // Host banks stream over PCIe (~20x slower than the scan): a second pass costs far more than a
     // wider first one, so over-fetch 4k there; HBM-resident banks start at 2k.
     else k_fetch = ctx->overfetch > 0 ? ctx->overfetch : (b.host ? std::max(4 * k, 2048) : std::max(2 * k, 1024));
+    // walks over this query set that needed a deeper over-fetch before start there (shards of one
+    // dataset behave alike; an escalation re-reads the whole bank, a deeper first pass costs ~10 %)
+    if (depth == 0 && k_fetch_init == 0) k_fetch = std::max(k_fetch, q->kfetch_hint);
     k_fetch = std::min(std::max(k_fetch, k), kMaxKFetch);
   }
   int64_t cap = auto_cap(ctx, k_fetch);
@@ -599,10 +638,11 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     // some class ran out of candidates before k passed T2I although more rows were eligible:
     // widen the over-fetch for those classes only, finally fall back to the exact in-pass predicate
     ctx->timing[7] += 1;
-    const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 4) : kMaxKFetch + 1;
+    const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 2) : kMaxKFetch + 1;
     if (b.row_class == nullptr && static_cast<int>(bad.size()) < C) {
       SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, bad, next, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
                              stream, depth));
+      k_fetch = std::max(k_fetch, q->last_k_fetch);     // set by escalate_classes from the sub-run
       break;
     }
     if (next > kMaxKFetch) dual = true;
@@ -612,6 +652,8 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
     }
   }
+  q->last_k_fetch = dual ? 0 : k_fetch;
+  if (depth == 0 && want_t2i && !dual && ctx->overfetch == 0) q->kfetch_hint = std::max(q->kfetch_hint, k_fetch);
   if (depth == 0) {
     CU_OK(cudaEventRecord(ctx->ev[7], stream));
     CU_OK(cudaStreamSynchronize(stream));
@@ -672,7 +714,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_t2i, &ctx->w_incomplete, &ctx->w_keys,
                     &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
-                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts};
+                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot};
   for (DevBuf* b : bufs) b->release();
   if (ctx->cached_job) swat_job_destroy(ctx->cached_job);
   if (ctx->esc_q) swat_queries_destroy(ctx->esc_q);
@@ -695,6 +737,7 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   else if (n == "list_entries") ctx->list_entries = value;
   else if (n == "overfetch") ctx->overfetch = static_cast<int>(value);
   else if (n == "host_chunk_rows") ctx->host_chunk_rows = value;
+  else if (n == "bootstrap_rows") ctx->bootstrap_rows = std::max<int64_t>(0, value);
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
   return SWAT_OK;
 }
@@ -838,6 +881,7 @@ int32_t swat_job_reset(swat_job* job, void* stream) {
   (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
   CU_OK(launch_job_reset(job->st, job->q->C, static_cast<cudaStream_t>(stream)));
+  job->fresh = true;
   job->last_stream = static_cast<cudaStream_t>(stream);
   job->ctx->launches += 1;
   return SWAT_OK;

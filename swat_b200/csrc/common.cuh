@@ -71,7 +71,9 @@ struct ScanArgs {
   const int32_t* row_class;   // nullable, [n_rows]
   const uint32_t* exclude;    // nullable, bitmap over view rows
   float t2i_thr;              // dual (in-pass T2I) mode only
-  float* dense_out;           // nullable: write class scores [n_rows, n_classes] instead of selecting
+  float* dense_out;           // nullable: write class scores instead of selecting
+  int64_t dense_ld;           // leading dimension of dense_out
+  int32_t dense_transposed;   // 0: dense_out[row*ld + class], 1: dense_out[class*ld + row] (coalesced)
   int32_t n_classes;
 };
 

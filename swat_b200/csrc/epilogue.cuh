@@ -154,7 +154,9 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& 
     for (int j = 0; j < NC; ++j) {
       cx.acc = (RED == RED_NONE) ? v[j] : red_op<RED>(cx.acc, v[j]);
       if ((endmask >> j) & 1u) {  // warp-uniform
-        if (cx.row_valid) a.dense_out[static_cast<size_t>(cx.row) * a.n_classes + cls[j]] = red_fin<RED>(cx.acc, cnt[j]);
+        if (cx.row_valid)
+          a.dense_out[a.dense_transposed ? static_cast<size_t>(cls[j]) * a.dense_ld + cx.row : static_cast<size_t>(cx.row) * a.dense_ld + cls[j]] =
+              red_fin<RED>(cx.acc, cnt[j]);
         cx.acc = red_init<RED>();
       }
     }

@@ -14,7 +14,21 @@ constexpr int kSelThreads = 1024;
 // the block sort (usually 0-2 passes), then a bitonic sort orders it.  `n_valid` = number of non-zero
 // keys.  Returns the number of sorted entries `total` (every key >= the radix prefix); the caller
 // takes the first min(K, total).
-__device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n, uint32_t n_valid, uint32_t K, uint64_t* s_keys,
+struct GlobalKeys {
+  const uint64_t* keys;
+  __device__ __forceinline__ uint64_t operator()(uint32_t i) const { return keys[i]; }
+};
+// keys made on the fly from a dense score column: rows below the user threshold are absent
+struct ScoreKeys {
+  const float* scores; float thr; uint32_t row_base;
+  __device__ __forceinline__ uint64_t operator()(uint32_t i) const {
+    const float s = scores[i] + 0.0f;
+    return s >= thr ? make_key(s, row_base + i) : 0ull;
+  }
+};
+
+template <typename KeyFn>
+__device__ uint32_t select_sorted(const KeyFn keys, uint32_t n, uint32_t n_valid, uint32_t K, uint64_t* s_keys,
                                   uint32_t* s_hist, uint32_t* s_misc) {
   const int tid = threadIdx.x;
   uint64_t prefix = 0, mask = 0;
@@ -24,7 +38,7 @@ __device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n,
     for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
     for (uint32_t i = tid; i < n; i += kSelThreads) {
-      const uint64_t key = keys[i];
+      const uint64_t key = keys(i);
       if (key != 0ull && (key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFFu], 1u);
     }
     __syncthreads();
@@ -52,7 +66,7 @@ __device__ uint32_t select_sorted(const uint64_t* __restrict__ keys, uint32_t n,
   if (tid == 0) s_misc[3] = 0;
   __syncthreads();
   for (uint32_t i = tid; i < n; i += kSelThreads) {
-    const uint64_t key = keys[i];
+    const uint64_t key = keys(i);
     if (key != 0ull && (key & mask) >= prefix) {
       const uint32_t pos = atomicAdd(&s_misc[3], 1u);
       if (pos < static_cast<uint32_t>(kSortCap)) s_keys[pos] = key;
@@ -90,7 +104,7 @@ select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_sco
   const uint32_t appended = st.count[c];
   const uint32_t n = min(appended, st.cap);
   const uint32_t K = st.k_fetch;
-  const uint32_t total = select_sorted(st.cand + static_cast<size_t>(c) * st.cap, n, n, K, s_keys, s_hist, s_misc);
+  const uint32_t total = select_sorted(GlobalKeys{st.cand + static_cast<size_t>(c) * st.cap}, n, n, K, s_keys, s_hist, s_misc);
   const uint32_t cnt = min(K, total);
   for (uint32_t i = threadIdx.x; i < K; i += kSelThreads) {
     const bool ok = i < cnt;
@@ -139,6 +153,80 @@ __global__ void __launch_bounds__(256) partition_kernel(const JobState st) {
       else atomicOr(st.flags, 1u);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------- bootstrap
+// Seeds a fresh job from the dense class scores of a bank prefix (scores_t[class][row], B rows).
+// Pass 1 builds the class histogram of the prefix in shared memory and finds the highest bin edge
+// with at least k_fetch scores at or above it; pass 2 appends exactly the rows at or above that edge
+// (k_fetch plus about one bin: a superset of the prefix's top k_fetch, which is all the job needs) to
+// a spare survivor list, adds those bins to the global histogram and raises the class threshold to
+// the edge.  The main scan then begins with selective thresholds instead of appending every
+// non-negative score of its first waves.
+__global__ void __launch_bounds__(kSelThreads)
+bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t B, uint32_t row_base, uint32_t first_spare_list) {
+  __shared__ uint32_t s_h[kHistBins];
+  __shared__ uint32_t s_cut, s_total, s_base, s_fill;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const float* sc = scores_t + static_cast<size_t>(c) * B;
+  for (int i = tid; i < kHistBins; i += kSelThreads) s_h[i] = 0;
+  if (tid == 0) s_fill = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < B; i += kSelThreads) {
+    const float s = sc[i] + 0.0f;
+    if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
+  }
+  __syncthreads();
+  if (tid < 32) {   // warp 0: lane l owns bins 32l .. 32l+31; suffix-scan from the top
+    uint32_t mine = 0;
+    for (int b = 0; b < 32; ++b) mine += s_h[lane * 32 + b];
+    uint32_t suf = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, suf, d);
+      if (lane + d < 32) suf += t;
+    }
+    const uint32_t K = st.k_fetch;
+    const uint32_t ball = __ballot_sync(0xffffffffu, suf >= K);
+    int cut = 0;                      // fewer than k_fetch eligible rows: keep them all
+    uint32_t total = __shfl_sync(0xffffffffu, suf, 0);
+    if (ball != 0u) {
+      const int L = 31 - __clz(ball);
+      int bin = 0;
+      uint32_t run = 0, at = 0;
+      if (lane == L) {
+        run = suf - mine;
+        for (int b = 31; b >= 0; --b) {
+          run += s_h[lane * 32 + b];
+          if (run >= K) { bin = lane * 32 + b; at = run; break; }
+        }
+      }
+      cut = __shfl_sync(0xffffffffu, bin, L);
+      total = __shfl_sync(0xffffffffu, at, L);
+    }
+    if (lane == 0) {
+      s_cut = static_cast<uint32_t>(cut);
+      s_total = total;
+      const uint32_t list_id = first_spare_list + static_cast<uint32_t>(c) % (st.n_lists - first_spare_list);
+      s_base = atomicAdd(&st.list_count[list_id], total);
+      if (cut >= 1) atomicMax(&st.tau_enc[c], f32_enc(hist_edge(st, cut)));
+    }
+  }
+  __syncthreads();
+  const int cut = static_cast<int>(s_cut);
+  const uint32_t list_id = first_spare_list + static_cast<uint32_t>(c) % (st.n_lists - first_spare_list);
+  uint4* dst = st.list + static_cast<size_t>(list_id) * st.list_cap;
+  for (uint32_t i = tid; i < B; i += kSelThreads) {
+    const float s = sc[i] + 0.0f;
+    if (s >= st.thr && hist_bin(st, s) >= cut) {
+      const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
+      const uint64_t key = make_key(s, row_base + i);
+      if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
+      else atomicOr(st.flags, 2u);
+    }
+  }
+  for (int b = cut + tid; b < kHistBins; b += kSelThreads)
+    if (s_h[b]) atomicAdd(&st.hist[static_cast<size_t>(c) * kHistBins + b], s_h[b]);
 }
 
 // ---------------------------------------------------------------------------------- T2I stage
@@ -302,7 +390,7 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
   if (v) atomicAdd(&s_valid, v);
   __syncthreads();
   const uint32_t valid = s_valid;
-  const uint32_t total = select_sorted(kc, n, valid, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
+  const uint32_t total = select_sorted(GlobalKeys{kc}, n, valid, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
   const uint32_t cnt = min(static_cast<uint32_t>(k_out), total);
   for (uint32_t i = tid; i < static_cast<uint32_t>(k_out); i += kSelThreads) {
     const bool ok = i < cnt;
@@ -359,6 +447,12 @@ cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset,
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bootstrap(const JobState& st, int n_classes, const float* d_scores_t, uint32_t n_prefix, uint32_t row_base,
+                             uint32_t first_spare_list, cudaStream_t stream) {
+  bootstrap_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, d_scores_t, n_prefix, row_base, first_spare_list);
   return cudaGetLastError();
 }
 

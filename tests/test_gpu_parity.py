@@ -278,3 +278,28 @@ def test_bad_arguments_raise(lib, ctx2):
         lib.topk(ctx2, qs, _rand_unit(64, 2).cuda(), 100000)                   # k beyond the supported maximum
     with pytest.raises((ValueError, TypeError)):
         lib.topk(ctx2, qs, torch.zeros(64, 256).cuda(), 10)
+
+
+@pytest.mark.parametrize("reduce", ["none", "max"])
+def test_threshold_bootstrap_is_exact(lib, reduce):
+    """A fresh job seeds its thresholds from a dense prefix (swat_job_scan bootstrap).  The result must be
+    identical, bit for bit, to the un-bootstrapped scan, and match the oracle."""
+    from swat_b200 import synth
+    sizes = [1] * 48 if reduce == "none" else [1 + i % 4 for i in range(48)]
+    qc, queries, coq = synth.make_queries(48, sizes, seed=61, dtype=torch.bfloat16)
+    cap, img, _ = synth.make_bank(120_000, qc, seed=61, dtype=torch.bfloat16, rho=0.2, tie_block=400, chunk=1 << 16)
+    res = {}
+    for boot in (0, 8192):
+        ctx = lib.Context(0, bootstrap_rows=boot)
+        qs = lib.Queries(ctx, queries.float(), coq, 48, reduce)
+        before = ctx.launch_count
+        res[boot] = [x.cpu() if x is not None else None for x in lib.topk(ctx, qs, cap.cuda(), 300, 0.0, t2i_bank=img.cuda())]
+        res[boot].append(ctx.launch_count - before)
+        qs.close(); ctx.close()
+    assert res[8192][4] > res[0][4]                      # the bootstrap really ran (two extra launches per scan)
+    for a, b in zip(res[0][:4], res[8192][:4]):
+        assert torch.equal(a, b)
+    capf, imgf, qf = cap.float().numpy(), img.float().numpy(), queries.float().numpy()
+    S = so.score_matrix(capf, qf, coq.numpy(), 48, reduce)
+    o = so.topk_walk(capf, qf, 300, 0.0, t2i_bank=imgf, class_of_query=coq.numpy(), n_classes=48, reduce=reduce)
+    check_result(res[8192][0], res[8192][1], res[8192][3], o[0], o[1], o[3], S, TIE_TOL, what=f"bootstrap {reduce}")
