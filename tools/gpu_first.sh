@@ -9,6 +9,6 @@ echo "exit $?" >> gpurun_out/first.log
 echo "=== pytest gpu" >> gpurun_out/first.log
 timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -x -k "dense" > gpurun_out/pytest_dense.log 2>&1
 echo "exit $?" >> gpurun_out/pytest_dense.log
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -q --timeout 600 -k "not dense" > gpurun_out/pytest_rest.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py tests/test_gpu_fullsize.py -m gpu -q --timeout 600 -k "not dense" > gpurun_out/pytest_rest.log 2>&1
 echo "exit $?" >> gpurun_out/pytest_rest.log
 for f in first pytest_dense pytest_rest; do tail -n 5 gpurun_out/$f.log; done
