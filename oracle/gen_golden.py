@@ -63,13 +63,13 @@ def run_samplers(sr, raw, prompt_tensors, k, tmp, dataset, unpartitioned=False):
     lg = logging.getLogger("golden")
     out = {}
     path_to_row = {p: i for i, p in enumerate(paths)}
-    for name, fn in (("t2t", sr.t2t_ranked_sampler), ("t2t_t2i", sr.t2t_ranked_t2i_tshd_sampler)):
+    for name, fn in (("t2t", sr.t2t_ranked_sampler), ("t2t_t2i", sr.t2t_ranked_t2i_tshd_sampler), ("t2i", sr.t2i_ranked_sampler)):
         ms, nd = fn(args, lg, prompt_tensors, k, 0.0, feats)
         files = [p for fl in ms["file_list"] for p in fl]
         labels = torch.cat(ms["label_list"]).numpy() if ms["label_list"] else np.zeros(0, np.int64)
         rows = np.asarray([path_to_row[p] for p in files], dtype=np.int64)
         featsum = torch.cat(ms["feature_list"]).double().sum(dim=1).numpy() if ms["feature_list"] else np.zeros(0)
-        if name == "t2t":
+        if name in ("t2t", "t2i"):
             fl_name, sl_name = f"{tmp}/T2T_filtered_list.txt", f"{tmp}/T2T_sampled_list.txt"   # :763,768
         else:
             fl_name, sl_name = f"{tmp}/filtered_list.txt", f"{tmp}/sampled_list.txt"           # :817,822
@@ -111,7 +111,7 @@ def case_bank(sr, name, n_rows, C, k, seed, dtype, partitioned, rho, tie_block):
     else:
         arrays.update(cap_f32=cap.numpy(), img_f32=img.numpy(), q_f32=qc.numpy())
     for tag, res in (("part", res_p), ("unpart", res_u)):
-        for m in ("t2t", "t2t_t2i"):
+        for m in ("t2t", "t2t_t2i", "t2i"):
             arrays[f"{tag}_{m}_rows"] = res[m]["rows"]
             arrays[f"{tag}_{m}_labels"] = res[m]["labels"]
             arrays[f"{tag}_{m}_featsum"] = res[m]["featsum"]

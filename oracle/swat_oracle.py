@@ -177,7 +177,8 @@ def verbatim_t2t_ranked_sampler(prompt_tensors: dict, num_samples: int, threshol
                                 duplicates_dict: Optional[dict] = None,
                                 filtered_images_dict: Optional[dict] = None,
                                 caption_map: Optional[dict] = None,
-                                classes: Optional[Iterable[str]] = None):
+                                classes: Optional[Iterable[str]] = None,
+                                rank_on_images: bool = False):
     """``t2t_ranked_sampler`` (:724-771).
 
     Per class in ascending int order (:734-735): GEMV scores (:752), Python ``sorted`` on the
@@ -200,7 +201,8 @@ def verbatim_t2t_ranked_sampler(prompt_tensors: dict, num_samples: int, threshol
         img_embeddings = pre_extracted_feats[cls]["feats"]
         caption_embeddings = pre_extracted_feats[cls]["caption_feats"]
         class_prompt = np.asarray(prompt_tensors[cls]["mean"], dtype=np.float32)[None, :]       # :749-750
-        sim = similarity(class_prompt, caption_embeddings)
+        # t2i_ranked_sampler (:1195-1243) is this function with cal_t2i_similarity on the image features (:1224)
+        sim = similarity(class_prompt, img_embeddings if rank_on_images else caption_embeddings)
         embedding_list = [img_embeddings[i] for i in range(len(img_embeddings))]                 # :753 (N row views)
         items = sorted(list(zip(file_list, sim, range(len(file_list)), embedding_list)), key=lambda x: x[1], reverse=True)
         items = [(p, s_, r) for p, s_, r, _ in items]

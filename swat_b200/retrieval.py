@@ -194,9 +194,12 @@ def check_caption(caption_map, img_path):
 
 
 def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
-                 filtered_images_dict, with_t2i: bool, t2i_threshold: float = 0.25):
+                 filtered_images_dict, with_t2i: bool, t2i_threshold: float = 0.25, rank_on_images: bool = False):
     classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))          # :734-735
     cap, img, paths, row_class = _flatten(pre_extracted_feats, classes)
+    feat_bank = img                                          # feature_list always carries the image features (:753, :1225)
+    if rank_on_images:                                       # T2I-rank scores the image bank instead of the captions (:1224)
+        cap = img
     bank_dtype = getattr(args, "bank_dtype", None)
     if bank_dtype in ("bf16", torch.bfloat16):
         cap = cap.to(torch.bfloat16); img = img.to(torch.bfloat16)
@@ -232,6 +235,7 @@ def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extra
     mined_split = {"feature_list": [], "label_list": [], "file_list": []}
     num_imgs_sampled_dict = {}
     sampled_list: List[str] = []
+    img = feat_bank
     img_host = img if not img.is_cuda else None
     for i, cls in enumerate(classes):
         n = int(counts[i])
@@ -253,7 +257,7 @@ def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extra
             else:
                 sampled_list.append(f"{round(sc[j], 4)}/{threshold}, {p}, {caption}")
     logger.info(f"len(sampled_list): {len(sampled_list)}")
-    prefix = "" if with_t2i else f"{args.prefix}_"                                     # :763,768 vs :817,822
+    prefix = "" if with_t2i else f"{args.prefix}_"                                     # :763,768,1236,1241 vs :817,822
     os.makedirs(args.output_folder, exist_ok=True)
     with open(f"{args.output_folder}/{prefix}sampled_list.txt", "w") as f:
         f.write("\n".join(sampled_list))
@@ -277,6 +281,14 @@ def t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, num_samples, thres
                         filtered_images_dict, with_t2i=True, t2i_threshold=0.25)
 
 
+def t2i_ranked_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                       duplicates_dict: defaultdict = defaultdict(set), filtered_images_dict: defaultdict = defaultdict(set)):
+    """``t2i_ranked_sampler`` (:1195-1243): the same ranked walk on the IMAGE features
+    (``cal_t2i_similarity`` :1224) -- the same kernel with the banks swapped."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=False, rank_on_images=True)
+
+
 # ---------------------------------------------------------------------------------------------
 # output writer + orchestration tail
 # ---------------------------------------------------------------------------------------------
@@ -298,7 +310,7 @@ def save_sample_file_list(args, final_file_list, label_tensor, logger=None, copy
 
 def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=None, copy_to: Optional[str] = None):
     """The hot part of ``sampling`` (:1471-1670): load + regroup the mined features, dispatch on
-    ``args.sampling_method`` (T2T-rank :1571-1579, T2T-rank-T2I-tshd :1581-1589), write
+    ``args.sampling_method`` (T2T-rank :1571-1579, T2T-rank-T2I-tshd :1581-1589, T2I-rank :1610-1617), write
     ``{prefix}.txt`` and ``{prefix}_num_imgs_sampled.json``.  Returns ``(file_list_path, sample_ct)``."""
     if pre_extracted_feats is None:
         fn = f"{dataset_root}/{args.dataset}_{args.model_cfg}_mined.pth"
@@ -315,6 +327,8 @@ def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=Non
         mined_split, num_imgs_sampled_dict = t2t_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
     elif args.sampling_method == "T2T-rank-T2I-tshd":
         mined_split, num_imgs_sampled_dict = t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "T2I-rank":                                         # :1610-1617
+        mined_split, num_imgs_sampled_dict = t2i_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
     else:
         raise NotImplementedError(f"sampling method {args.sampling_method} is outside the accelerated hot path")
     final_file_list = [p for fl in mined_split["file_list"] for p in fl]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Drop-in for ``python retrieval/sample_retrieval.py`` (reference CLI at ``sample_retrieval.py:1673-1747``)
-for the two sampling methods on the accelerated path: ``T2T-rank`` and ``T2T-rank-T2I-tshd``.
+for the sampling methods on the accelerated path: ``T2T-rank``, ``T2T-rank-T2I-tshd`` and ``T2I-rank``.
 
 Same flags and defaults, same outputs: ``output/{dataset}_{model_cfg}_{prefix}/{prefix}.txt``
 (``"<path> <label> 0"`` per accepted row, class-major), ``{prefix}_num_imgs_sampled.json``,
@@ -72,7 +72,7 @@ def build_parser():
 def main(argv=None):
     time_start = time()
     args = build_parser().parse_args(argv)
-    if args.sampling_method not in ("T2T-rank", "T2T-rank-T2I-tshd"):
+    if args.sampling_method not in ("T2T-rank", "T2T-rank-T2I-tshd", "T2I-rank"):
         raise NotImplementedError(f"--sampling_method {args.sampling_method} is outside the accelerated hot path; "
                                   "use the reference script for it")
     if args.zeroshot_img_filter or args.image_dedup:

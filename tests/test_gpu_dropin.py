@@ -33,7 +33,7 @@ def test_samplers_match_reference_outputs(tmp_path, name, dtype):
     structure, partitioned (transform_extracted_fea) and unpartitioned (aliased dict)."""
     from swat_b200 import retrieval
     z, meta, cap, img, q, raw, prompts, paths, cmap = _case(name)
-    S = so.score_matrix(cap, q)
+    S_cap, S_img = so.score_matrix(cap, q), so.score_matrix(img, q)
     cmap_path = str(tmp_path / "cap.map")
     pickle.dump(cmap, open(cmap_path, "wb"))
     args = Namespace(dataset="synthetic", output_folder=str(tmp_path / "out"), prefix="T2T", bank_dtype=dtype, caption_map_path=cmap_path)
@@ -42,7 +42,9 @@ def test_samplers_match_reference_outputs(tmp_path, name, dtype):
     feats_p = retrieval.transform_extracted_fea(raw)
     feats_u = {k: {"file_paths": paths, "feats": raw["image_features"], "caption_feats": raw["caption_features"]} for k in prompts}
     for tag, feats in (("part", feats_p), ("unpart", feats_u)):
-        for m, fn in (("t2t", retrieval.t2t_ranked_sampler), ("t2t_t2i", retrieval.t2t_ranked_t2i_tshd_sampler)):
+        for m, fn in (("t2t", retrieval.t2t_ranked_sampler), ("t2t_t2i", retrieval.t2t_ranked_t2i_tshd_sampler),
+                      ("t2i", retrieval.t2i_ranked_sampler)):
+            S = S_img if m == "t2i" else S_cap
             ms, nd = fn(args, lg, prompts, int(z["k"]), 0.0, feats)
             assert nd == meta["counts"][tag][m], f"{name} {tag} {m}"
             ref_rows, ref_labels = z[f"{tag}_{m}_rows"], z[f"{tag}_{m}_labels"]
