@@ -114,7 +114,7 @@ struct swat_queries {
   int32_t* d_blk_split = nullptr;     // [n_qb] grouped reduces: first column of the second epilogue warp set
   void* d_arena = nullptr;            // one allocation backs every device array above
   std::vector<float> h_q;             // host copy (sub-query sets for targeted escalation)
-  mutable int32_t kfetch_hint = 0;    // deepest over-fetch a T2I walk over this query set has needed so far
+  mutable std::vector<int32_t> kclass_hint;   // per class: deepest over-fetch its T2I walk has needed so far (0 = default)
   mutable int32_t last_k_fetch = 0;   // over-fetch at which the last pipeline run completed
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
   CUtensorMap tm_q;
@@ -126,6 +126,7 @@ struct swat_job {
   JobState st;
   int n_classes_alloc = 0;
   bool fresh = true;                  // no rows folded in since the last reset
+  uint32_t* d_k_class = nullptr;      // [n_classes_alloc] per-class k_fetch, used when the depths differ
   cudaStream_t last_stream = nullptr;
 };
 
@@ -273,6 +274,7 @@ void job_set_params(swat_job* j, const swat_queries* q, int32_t k_fetch, float t
   JobState& st = j->st;
   j->q = q;
   st.k_fetch = static_cast<uint32_t>(k_fetch);
+  st.k_class = nullptr;
   st.thr = thr;
   float lo = std::max(thr, -1.0f);
   float hi = std::max(1.0f, lo + 1.0f / 64.0f);
@@ -307,6 +309,7 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
   if (e == cudaSuccess) e = cudaMalloc(&st.list, static_cast<size_t>(st.n_lists) * st.list_cap * sizeof(uint4));
   if (e == cudaSuccess) e = cudaMalloc(&st.list_count, static_cast<size_t>(st.n_lists) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&st.flags, 16);
+  if (e == cudaSuccess) e = cudaMalloc(&j->d_k_class, C * 4);
   if (e != cudaSuccess) {
     swat_job_destroy(j);
     return fail(SWAT_ERR_CUDA, "job allocation failed (C=%zu, cap=%lld, list entries=%lld): %s", C, (long long)cap,
@@ -491,10 +494,22 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     // Host banks stream over PCIe (~20x slower than the scan): a second pass costs far more than a
     // wider first one, so over-fetch 4k there; HBM-resident banks start at 2k.
     else k_fetch = ctx->overfetch > 0 ? ctx->overfetch : (b.host ? std::max(4 * k, 2048) : std::max(2 * k, 1024));
-    // walks over this query set that needed a deeper over-fetch before start there (shards of one
-    // dataset behave alike; an escalation re-reads the whole bank, a deeper first pass costs ~10 %)
-    if (depth == 0 && k_fetch_init == 0) k_fetch = std::max(k_fetch, q->kfetch_hint);
     k_fetch = std::min(std::max(k_fetch, k), kMaxKFetch);
+  }
+  // Classes whose walk needed a deeper over-fetch before start there: the depth is per class (one class
+  // with a block of duplicates should not make the other 199 collect four times the candidates).
+  // Shards of one dataset behave alike; an escalation re-reads the whole bank.
+  std::vector<uint32_t> k_class;
+  const bool use_hint = want_t2i && !dual && depth == 0 && k_fetch_init == 0 && ctx->overfetch == 0 &&
+                        static_cast<int>(q->kclass_hint.size()) == C;
+  if (use_hint) {
+    int32_t deepest = k_fetch;
+    for (int c = 0; c < C; ++c) deepest = std::max(deepest, q->kclass_hint[c]);
+    if (deepest > k_fetch) {
+      k_class.resize(C);
+      for (int c = 0; c < C; ++c) k_class[c] = static_cast<uint32_t>(std::max(k_fetch, q->kclass_hint[c]));
+      k_fetch = deepest;
+    }
   }
   int64_t cap = auto_cap(ctx, k_fetch);
   int64_t list_entries = auto_list_entries(ctx, C, k_fetch);
@@ -506,6 +521,10 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     const int32_t kf = dual ? k : k_fetch;
     swat_job* job = nullptr;
     SW_OK(acquire_job(ctx, q, kf, thr, cap, list_entries, &job));
+    if (!dual && !k_class.empty()) {
+      CU_OK(cudaMemcpyAsync(job->d_k_class, k_class.data(), static_cast<size_t>(C) * 4, cudaMemcpyHostToDevice, stream));
+      job->st.k_class = job->d_k_class;
+    }
     SW_OK(swat_job_reset(job, stream));
     CU_OK(cudaEventRecord(ctx->ev[0], stream));
     SW_OK(scan_all(ctx, job, b, dual, t2i_thr, stream));
@@ -640,11 +659,18 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     ctx->timing[7] += 1;
     const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 2) : kMaxKFetch + 1;
     if (b.row_class == nullptr && static_cast<int>(bad.size()) < C) {
-      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, bad, next, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
+      int32_t from = k_fetch;                           // the escalated classes were walked to this depth
+      if (!k_class.empty()) { from = kMaxKFetch; for (int c : bad) from = std::min<int32_t>(from, static_cast<int32_t>(k_class[c])); }
+      const int32_t nxt = (from < kMaxKFetch) ? std::min(kMaxKFetch, from * 2) : kMaxKFetch + 1;
+      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, bad, nxt, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
                              stream, depth));
-      k_fetch = std::max(k_fetch, q->last_k_fetch);     // set by escalate_classes from the sub-run
+      if (depth == 0 && ctx->overfetch == 0 && q->last_k_fetch > 0) {      // remember the depth that worked, per class
+        if (static_cast<int>(q->kclass_hint.size()) != C) q->kclass_hint.assign(C, 0);
+        for (int c : bad) q->kclass_hint[c] = std::max(q->kclass_hint[c], q->last_k_fetch);
+      }
       break;
     }
+    k_class.clear();
     if (next > kMaxKFetch) dual = true;
     else {
       k_fetch = next;
@@ -653,7 +679,6 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     }
   }
   q->last_k_fetch = dual ? 0 : k_fetch;
-  if (depth == 0 && want_t2i && !dual && ctx->overfetch == 0) q->kfetch_hint = std::max(q->kfetch_hint, k_fetch);
   if (depth == 0) {
     CU_OK(cudaEventRecord(ctx->ev[7], stream));
     CU_OK(cudaStreamSynchronize(stream));
@@ -920,7 +945,7 @@ int32_t swat_job_destroy(swat_job* job) {
   if (!job) return SWAT_OK;
   cudaSetDevice(job->ctx->device);
   cudaFree(job->st.tau_enc); cudaFree(job->st.count); cudaFree(job->st.hist); cudaFree(job->st.cand); cudaFree(job->st.flags);
-  cudaFree(job->st.list); cudaFree(job->st.list_count);
+  cudaFree(job->st.list); cudaFree(job->st.list_count); cudaFree(job->d_k_class);
   delete job;
   return SWAT_OK;
 }

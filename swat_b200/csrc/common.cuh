@@ -51,6 +51,7 @@ struct JobState {
   uint32_t* count;       // [C]  candidates per class after partition
   uint64_t* cand;        // [C * cap] candidate keys after partition
   uint32_t* flags;       // [0] bit0 = class candidate overflow (partition), bit1 = survivor list overflow (scan)
+  const uint32_t* k_class;  // nullable [C]: per-class k_fetch (<= k_fetch); classes whose T2I walk needs depth get more
   uint32_t n_lists, list_cap;
   uint32_t cap;
   uint32_t k_fetch;
@@ -76,6 +77,8 @@ struct ScanArgs {
   int32_t dense_transposed;   // 0: dense_out[row*ld + class], 1: dense_out[class*ld + row] (coalesced)
   int32_t n_classes;
 };
+
+__device__ __forceinline__ uint32_t class_k(const JobState& st, int cls) { return st.k_class ? st.k_class[cls] : st.k_fetch; }
 
 __device__ __forceinline__ int hist_bin(const JobState& st, float s) {
   float x = (s - st.hist_lo) * st.hist_scale;

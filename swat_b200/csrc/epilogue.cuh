@@ -76,7 +76,7 @@ static __device__ __noinline__ void refresh_tau(const JobState& st, int cls) {
     uint32_t t = __shfl_down_sync(0xffffffffu, suf, d);
     if (lane + d < 32) suf += t;
   }
-  const uint32_t K = st.k_fetch;
+  const uint32_t K = class_k(st, cls);
   const uint32_t ball = __ballot_sync(0xffffffffu, suf >= K);
   if (ball == 0) return;
   const int L = 31 - __clz(ball);

@@ -103,14 +103,15 @@ select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_sco
   const int c = blockIdx.x;
   const uint32_t appended = st.count[c];
   const uint32_t n = min(appended, st.cap);
-  const uint32_t K = st.k_fetch;
+  const uint32_t K = class_k(st, c);          // this class's depth
+  const uint32_t stride = st.k_fetch;         // output row pitch = the deepest class
   const uint32_t total = select_sorted(GlobalKeys{st.cand + static_cast<size_t>(c) * st.cap}, n, n, K, s_keys, s_hist, s_misc);
   const uint32_t cnt = min(K, total);
-  for (uint32_t i = threadIdx.x; i < K; i += kSelThreads) {
+  for (uint32_t i = threadIdx.x; i < stride; i += kSelThreads) {
     const bool ok = i < cnt;
     const uint64_t key = ok ? s_keys[i] : 0ull;
-    out_scores[static_cast<size_t>(c) * K + i] = ok ? key_score(key) : 0.0f;
-    out_rows[static_cast<size_t>(c) * K + i] = ok ? static_cast<int64_t>(key_row(key)) + row_offset : -1;
+    out_scores[static_cast<size_t>(c) * stride + i] = ok ? key_score(key) : 0.0f;
+    out_rows[static_cast<size_t>(c) * stride + i] = ok ? static_cast<int64_t>(key_row(key)) + row_offset : -1;
   }
   if (threadIdx.x == 0) {
     out_counts[c] = static_cast<int32_t>(cnt);
@@ -186,7 +187,7 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
       const uint32_t t = __shfl_down_sync(0xffffffffu, suf, d);
       if (lane + d < 32) suf += t;
     }
-    const uint32_t K = st.k_fetch;
+    const uint32_t K = class_k(st, c);
     const uint32_t ball = __ballot_sync(0xffffffffu, suf >= K);
     int cut = 0;                      // fewer than k_fetch eligible rows: keep them all
     uint32_t total = __shfl_sync(0xffffffffu, suf, 0);
