@@ -516,7 +516,7 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
   cudaEvent_t ev_begin = ctx->ev[6];
   if (depth == 0) CU_OK(cudaEventRecord(ev_begin, stream));
   for (int rounds = 0;; ++rounds) {
-    if (rounds > 12) return fail(SWAT_ERR_OVERFLOW, "retry budget exhausted (cap=%lld lists=%lld k_fetch=%d)", (long long)cap,
+    if (rounds > 24) return fail(SWAT_ERR_OVERFLOW, "retry budget exhausted (cap=%lld lists=%lld k_fetch=%d)", (long long)cap,
                                  (long long)list_entries, k_fetch);
     const int32_t kf = dual ? k : k_fetch;
     swat_job* job = nullptr;
@@ -657,7 +657,8 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     // some class ran out of candidates before k passed T2I although more rows were eligible:
     // widen the over-fetch for those classes only, finally fall back to the exact in-pass predicate
     ctx->timing[7] += 1;
-    const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 2) : kMaxKFetch + 1;
+    // whole-set escalation (every class short, or partitioned data): x4 per round; targeted sub-passes go x2
+    const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 4) : kMaxKFetch + 1;
     if (b.row_class == nullptr && static_cast<int>(bad.size()) < C) {
       int32_t from = k_fetch;                           // the escalated classes were walked to this depth
       if (!k_class.empty()) { from = kMaxKFetch; for (int c : bad) from = std::min<int32_t>(from, static_cast<int32_t>(k_class[c])); }

@@ -212,7 +212,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     // without any barrier (a stale value is only more conservative).
     // NaN, not +inf, at padding / non-closing columns: a trailing partial chunk reads uninitialised TMEM
     // columns and +inf >= +inf would pass, whereas every comparison with NaN is false.
-    float t = __int_as_float(0x7fc00000);
+    float t = (RED == RED_NONE) ? INFINITY : __int_as_float(0x7fc00000);   // sign-test path: +inf fails too (scores are finite)
     if (!DENSE && s_cls[c] >= 0 && s_cnt[c] > 0.0f) t = fast_tau<RED>(f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c]])), s_cnt[c]);
     s_tau[c] = t;
   }
@@ -356,11 +356,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           const bool has_b = c0 + kStep < last, has_next = c0 + 2 * kStep < last;
           if (has_b) tmem_ld32_issue(taddr + c0 + kStep, rb); else release_tmem();
           to_f32x32(ra, v);
+          if (NB - c0 == 16) {   // trailing half chunk: columns the MMA never wrote must not look like scores
+#pragma unroll
+            for (int j = 16; j < 32; ++j) v[j] = 0.0f;
+          }
           process_chunk<32, RED, PART, false, DENSE, false>(p.s, sc, cx, v, v, c0, s_end[c0 >> 5]);
           if (has_b) {
             tmem_wait(rb);
             if (has_next) tmem_ld32_issue(taddr + c0 + 2 * kStep, ra); else release_tmem();
             to_f32x32(rb, v);
+            if (NB - (c0 + kStep) == 16) {
+#pragma unroll
+              for (int j = 16; j < 32; ++j) v[j] = 0.0f;
+            }
             process_chunk<32, RED, PART, false, DENSE, false>(p.s, sc, cx, v, v, c0 + kStep, s_end[(c0 + kStep) >> 5]);
             if (has_next) tmem_wait(ra);
           }
