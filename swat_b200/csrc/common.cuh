@@ -103,9 +103,11 @@ __device__ __forceinline__ uint4 ld_cg_u32x4(const uint32_t* p) {
   return v;
 }
 
+// finite identities: the epilogue tests the sign of (value - threshold) and +-inf would turn
+// inf - inf into NaN
 template <int RED> __device__ __forceinline__ float red_init() {
-  if (RED == RED_MAX) return -INFINITY;
-  if (RED == RED_MIN) return INFINITY;
+  if (RED == RED_MAX) return -3.402823466e+38f;
+  if (RED == RED_MIN) return 3.402823466e+38f;
   return 0.0f;
 }
 template <int RED> __device__ __forceinline__ float red_op(float a, float x) {

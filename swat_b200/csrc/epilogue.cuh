@@ -133,8 +133,7 @@ static __device__ __noinline__ uint32_t slow_append(const SlowCtx sc, uint32_t l
 template <int RED> __device__ __forceinline__ float fast_tau(float tau, float cnt) {
   // one-query-per-class mode tests the SIGN of (score - tau): a threshold of +0.0 becomes -0.0 so that a
   // score of -0.0 still passes, as it does in the reference (Python: -0.0 >= 0.0)
-  if (RED == RED_NONE) return tau == 0.0f ? -0.0f : tau;
-  if (RED != RED_MEAN) return tau;
+  if (RED != RED_MEAN) return tau == 0.0f ? -0.0f : tau;
   if (!(cnt > 0.0f) || !isfinite(tau)) return tau;
   const float t = tau * cnt;
   return t - fabsf(t) * 1.0e-6f - 1.0e-30f;
@@ -165,18 +164,25 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& 
     }
     return;
   }
-  if (RED == RED_NONE && !DUAL && !PART && NC == 32) {
-    // Leanest form (the default mode): d = score - tau, sign bits collected with a funnel shift --
-    // two instructions per column.  tau is +inf at padding columns (d = -inf: fails) and every score
-    // is finite, so no NaN can reach the sign test.
+  if (!DUAL && !PART && NC == 32) {
+    // Leanest form: d = value - tau, sign bits collected with a funnel shift -- two instructions per
+    // column plus the running reduce.  tau is +inf at padding / non-closing columns (d = -inf: fails);
+    // scores and reduce identities are finite, so no NaN can reach the sign test.
     uint32_t fail = 0;
 #pragma unroll
     for (int j4 = 0; j4 < NC / 4; ++j4) {
       const float4 t = *reinterpret_cast<const float4*>(tau + 4 * j4);
-      fail = __funnelshift_l(__float_as_uint(v[4 * j4 + 0] - t.x), fail, 1);
-      fail = __funnelshift_l(__float_as_uint(v[4 * j4 + 1] - t.y), fail, 1);
-      fail = __funnelshift_l(__float_as_uint(v[4 * j4 + 2] - t.z), fail, 1);
-      fail = __funnelshift_l(__float_as_uint(v[4 * j4 + 3] - t.w), fail, 1);
+      const float tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 4 * j4 + i;
+        if (RED != RED_NONE) {
+          cx.acc = red_op<RED>(cx.acc, v[j]);
+          v[j] = cx.acc;                                   // value of the class that closes here (if any)
+          cx.acc = ((endmask >> j) & 1u) ? red_init<RED>() : cx.acc;
+        }
+        fail = __funnelshift_l(__float_as_uint(v[j] - tt[i]), fail, 1);
+      }
     }
     const uint32_t mask = cx.row_valid ? ~__brev(fail) : 0u;
     if (__any_sync(0xffffffffu, mask != 0u)) {
@@ -184,7 +190,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& 
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         if ((any >> j) & 1u)   // warp-uniform
-          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], v[j], (mask >> j) & 1u, cx.row);
+          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], red_fin<RED>(v[j], cnt[j]), (mask >> j) & 1u, cx.row);
       }
     }
     return;

@@ -60,7 +60,7 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
       const float cnt = in ? a.col_count[c] : 0.0f;
       s_cls[tid] = cls;
       s_cnt[tid] = cnt;
-      float t = (RED == RED_NONE) ? INFINITY : __int_as_float(0x7fc00000);   // never passes (see scan_tc.cu)
+      float t = (PART || DUAL) ? __int_as_float(0x7fc00000) : INFINITY;   // never passes (see scan_tc.cu)
       if (!DENSE && cls >= 0 && cnt > 0.0f) t = fast_tau<RED>(f32_dec(ld_cg_u32(&a.st.tau_enc[cls])), cnt);
       s_tau[tid] = t;
       const uint32_t m = __ballot_sync(0xffffffffu, cnt > 0.0f);

@@ -212,7 +212,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     // without any barrier (a stale value is only more conservative).
     // NaN, not +inf, at padding / non-closing columns: a trailing partial chunk reads uninitialised TMEM
     // columns and +inf >= +inf would pass, whereas every comparison with NaN is false.
-    float t = (RED == RED_NONE) ? INFINITY : __int_as_float(0x7fc00000);   // sign-test path: +inf fails too (scores are finite)
+    float t = PART ? __int_as_float(0x7fc00000) : INFINITY;   // sign-test path: +inf fails (values are finite); compare path: NaN
     if (!DENSE && s_cls[c] >= 0 && s_cnt[c] > 0.0f) t = fast_tau<RED>(f32_dec(ld_cg_u32(&p.s.st.tau_enc[s_cls[c]])), s_cnt[c]);
     s_tau[c] = t;
   }
