@@ -13,8 +13,8 @@ One step = one pass of the whole pipeline (scan + select + T2I walk [+ gather + 
 `value`  : rows/s with the banks resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : rows/s through the C-ABI host entry point (swat_topk_host): banks in pinned host memory,
            H2D of the caption bank and of the candidates' image rows and D2H of the result inside
-           the timed region.  For N > 1 the shard is copied H2D (both banks) and the resident
-           sharded pipeline runs, all inside the timed region.
+           the timed region.  For N > 1 every rank does that for its own host shard, then the [C,k]
+           results are all-gathered and merged, all inside the timed region.
 `roofline`: scan kernel, HBM bound for Q <= 209: 1 KB/row over the measured copy
            bandwidth in MEASURED_PEAKS.json.
 """
@@ -310,13 +310,15 @@ def run_ours(a, rank, world, local_rank):
                 r = _lib.topk_host(ctx, qs, h_cap, k, 0.0, t2i_bank=h_img, t2i_threshold=0.25, row_offset=row_offset)
                 tm = ctx.last_timing()
                 return r, tm["h2d_bytes"], tm["d2h_bytes"]
-            cap.copy_(h_cap, non_blocking=True)
-            if img is not None:
-                img.copy_(h_img, non_blocking=True)
-            r = sdist.topk_sharded(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset, world=world)
-            out = [x.cpu() for x in r[:4] if x is not None]
-            h2d = cap.numel() * 2 * (2 if img is not None else 1)
-            return r, h2d, sum(x.numel() * x.element_size() for x in out)
+            # every rank streams ITS shard from pinned host memory through the C-ABI host entry point (exact local
+            # walk), then one all-gather of the [C,k] results and an associative merge
+            s, r, t, c = _lib.topk_host(ctx, qs, h_cap, k, 0.0, t2i_bank=h_img, t2i_threshold=0.25, row_offset=row_offset)
+            tm = ctx.last_timing()
+            local = (s.cuda(dev), r.cuda(dev), None if t is None else t.cuda(dev), c.cuda(dev), torch.zeros_like(c).cuda(dev))
+            res_m = sdist.gather_merge(local, k, float("-inf"), world, ctx=ctx)
+            out = [x.cpu() for x in res_m[:4] if x is not None]
+            return res_m, tm["h2d_bytes"] + sum(x.numel() * x.element_size() for x in local if x is not None), \
+                tm["d2h_bytes"] + sum(x.numel() * x.element_size() for x in out)
 
         e2e_step()
         barrier()
@@ -330,7 +332,8 @@ def run_ours(a, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_rows * steps_e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "steps": steps_e,
-               "api": "swat_topk_host (C-ABI, pinned host banks)" if world == 1 else "H2D shard copy + dist.topk_sharded"}
+               "api": "swat_topk_host (C-ABI, pinned host banks)" if world == 1 else
+                      "swat_topk_host per rank on its pinned host shard + one NCCL all-gather + swat_merge_topk"}
         del h_cap, h_img
 
     cpu = None

@@ -87,6 +87,10 @@ int32_t swat_queries_destroy(swat_queries* q);
 int32_t swat_job_create(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float t2t_threshold,
                         swat_job** out);
 int32_t swat_job_reset(swat_job* job, void* stream);
+/* Per-class depth: class c keeps its best h_depth[c] rows (1 <= h_depth[c] <= k_fetch) instead of
+ * k_fetch; NULL restores the uniform depth.  Lets a T2I walk over-fetch deeply only for the classes
+ * that need it.  Call before the first swat_job_scan after a reset. */
+int32_t swat_job_set_class_depth(swat_job* job, const int32_t* h_depth, void* stream);
 /* Score one bank view (rows [row_base, row_base+n_rows) of the shard) against every query and fold
  * it into the job.  d_bank: [n_rows,512] row-major, 16-byte aligned, dtype bf16|f32.
  * d_t2i_bank (nullable): same rows of the image bank; when given, the predicate

@@ -23,7 +23,7 @@ DIM = 512
 EXPORTS = [
     "swat_version", "swat_last_error", "swat_ctx_create", "swat_ctx_destroy", "swat_ctx_set_option",
     "swat_ctx_launch_count", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
-    "swat_job_scan", "swat_job_select", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
+    "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
     "swat_scores_dense", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
 ]
 
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
         "swat_queries_destroy": [vp],
         "swat_job_create": [vp, vp, i32, f32, C.POINTER(vp)],
         "swat_job_reset": [vp, vp],
+        "swat_job_set_class_depth": [vp, vp, vp],
         "swat_job_scan": [vp, vp, i32, i64, i64, vp, f32, vp, vp, i32, vp],
         "swat_job_select": [vp, vp, vp, vp, vp, vp],
         "swat_job_status": [vp, C.POINTER(i32)],
@@ -209,6 +210,11 @@ class Job:
 
     def reset(self):
         _check(load().swat_job_reset(self._h, _stream(self.ctx.device)))
+
+    def set_class_depth(self, depth=None):
+        """Per-class depth (host int32 ``[C]``, each in ``[1, k_fetch]``); ``None`` = uniform ``k_fetch``."""
+        d = None if depth is None else torch.as_tensor(depth).detach().to("cpu", torch.int32).contiguous()
+        _check(load().swat_job_set_class_depth(self._h, _ptr(d), _stream(self.ctx.device)))
 
     def scan(self, bank: torch.Tensor, row_base: int = 0, t2i_bank: Optional[torch.Tensor] = None,
              t2i_threshold: float = 0.25, row_class: Optional[torch.Tensor] = None,

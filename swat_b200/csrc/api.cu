@@ -913,6 +913,24 @@ int32_t swat_job_reset(swat_job* job, void* stream) {
   return SWAT_OK;
 }
 
+int32_t swat_job_set_class_depth(swat_job* job, const int32_t* h_depth, void* stream) {
+  if (!job) return fail(SWAT_ERR_INVALID, "null job");
+  (void)cudaGetLastError();
+  CU_OK(cudaSetDevice(job->ctx->device));
+  if (!h_depth) { job->st.k_class = nullptr; return SWAT_OK; }
+  const int C = job->q->C;
+  std::vector<uint32_t> d(C);
+  for (int c = 0; c < C; ++c) {
+    if (h_depth[c] < 1 || static_cast<uint32_t>(h_depth[c]) > job->st.k_fetch)
+      return fail(SWAT_ERR_INVALID, "class depth %d of class %d outside [1, k_fetch=%u]", h_depth[c], c, job->st.k_fetch);
+    d[c] = static_cast<uint32_t>(h_depth[c]);
+  }
+  CU_OK(cudaMemcpyAsync(job->d_k_class, d.data(), static_cast<size_t>(C) * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  CU_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));     // d is pageable and dies here
+  job->st.k_class = job->d_k_class;
+  return SWAT_OK;
+}
+
 int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
                       float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, void* stream) {
   if (!job || (!d_bank && n_rows > 0)) return fail(SWAT_ERR_INVALID, "null argument");

@@ -28,7 +28,8 @@ def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
 
 def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_threshold: float = 0.0,
                      t2i_bank: Optional[torch.Tensor] = None, row_offset: int = 0,
-                     row_class: Optional[torch.Tensor] = None, exclude: Optional[torch.Tensor] = None):
+                     row_class: Optional[torch.Tensor] = None, exclude: Optional[torch.Tensor] = None,
+                     class_depth: Optional[torch.Tensor] = None):
     """This shard's T2T top-``k_fetch`` per class (global row ids) with the T2I score of every
     candidate.  Returns ``(scores, rows, t2i | None, counts, truncated)`` on the device."""
     dbg = os.environ.get("SWAT_DEBUG")
@@ -43,6 +44,7 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
             job = cache[key] = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
         else:
             job.reset()
+        job.set_class_depth(class_depth)
         job.scan(t2t_bank, row_base=0, row_class=row_class, exclude=exclude)
         scores, rows, counts, trunc = job.select()
         over = job.overflowed()
@@ -127,27 +129,41 @@ def topk_sharded(ctx, queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: fl
     """Whole multi-GPU pipeline for this rank's shard.  Every rank returns the merged result.
     Classes whose walk is not provably exact are escalated collectively (4x deeper over-fetch for
     those classes only, finally the exact in-pass predicate)."""
+    base = k if t2i_bank is None else max(1024, 2 * k)
     if k_fetch is None:
         # T2T only: the merged top-k never reaches below a shard's k-th candidate, k suffices.
-        # T2I walk: over-fetch so that k candidates pass the predicate above every shard's frontier.
-        k_fetch = k if t2i_bank is None else max(1024, 2 * k)
+        # T2I walk: over-fetch so that k candidates pass the predicate above every shard's frontier;
+        # classes whose walk needed more depth before start deeper (per class, remembered on `queries`).
+        k_fetch, depth = base, None
+        hint = queries.__dict__.get("_depth_hint")
+        if t2i_bank is not None and hint is not None and int(hint.max()) > base:
+            depth = torch.clamp(hint, min=base, max=max_k_fetch).to(torch.int32)
+            k_fetch = int(depth.max())
+    else:
+        depth = None
     k_fetch = max(1, min(int(k_fetch), max_k_fetch))
-    local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset)
+    local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset, class_depth=depth)
     res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
     bad = res[4].nonzero().flatten().tolist()          # identical on every rank: the merge input is the all-gather
     if not bad:
         return res
     out_s, out_r, out_t, out_c, _ = res
-    if k_fetch < max_k_fetch:
-        # targeted escalation: only the classes that are not provably exact are re-scanned, 4x deeper
-        sub = queries.subset(bad)
+    sub = queries.subset(bad)
+    was = k_fetch if depth is None else int(depth[bad].min())
+    if was < max_k_fetch:
+        # targeted escalation: only the classes that are not provably exact are re-scanned, 2x deeper
+        nxt = min(max_k_fetch, 2 * was)
         r2 = topk_sharded(ctx, sub, t2t_bank, k, t2t_threshold, t2i_bank, t2i_threshold, row_offset, world, group,
-                          k_fetch=min(max_k_fetch, 4 * k_fetch), max_k_fetch=max_k_fetch)
+                          k_fetch=nxt, max_k_fetch=max_k_fetch)
+        reached = max(nxt, int(sub.__dict__.get("_reached", nxt)))
+        queries.__dict__["_reached"] = reached
+        if queries.__dict__.get("_depth_hint") is None:
+            queries.__dict__["_depth_hint"] = torch.zeros(queries.n_classes, dtype=torch.int32)
+        queries.__dict__["_depth_hint"][bad] = torch.maximum(queries.__dict__["_depth_hint"][bad], torch.tensor(reached, dtype=torch.int32))
     else:
         # The walk reaches below the deepest over-fetch of some shard (few rows pass T2I): every shard
         # computes its exact local top-k of predicate-passing rows (swat_topk falls back to the in-pass
         # predicate where needed); top-k of passing rows is associative, so a plain merge finishes it.
-        sub = queries.subset(bad)
         s, r, t, c = _lib.topk(ctx, sub, t2t_bank, k, t2t_threshold, t2i_bank=t2i_bank, t2i_threshold=t2i_threshold,
                                row_offset=row_offset)
         r2 = gather_merge((s, r, t, c, torch.zeros_like(c)), k, float("-inf"), world, ctx=ctx, group=group)

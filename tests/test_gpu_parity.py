@@ -303,3 +303,25 @@ def test_threshold_bootstrap_is_exact(lib, reduce):
     S = so.score_matrix(capf, qf, coq.numpy(), 48, reduce)
     o = so.topk_walk(capf, qf, 300, 0.0, t2i_bank=imgf, class_of_query=coq.numpy(), n_classes=48, reduce=reduce)
     check_result(res[8192][0], res[8192][1], res[8192][3], o[0], o[1], o[3], S, TIE_TOL, what=f"bootstrap {reduce}")
+
+
+def test_per_class_depth_job(lib, ctx2):
+    """swat_job_set_class_depth: each class keeps its own number of best rows; the deep classes' lists are
+    prefixes-compatible with a uniform deep job."""
+    bank = _rand_unit(50_000, 71, torch.bfloat16).cuda()
+    q = _rand_unit(12, 72, torch.bfloat16)
+    qs = lib.Queries(ctx2, q.float())
+    depth = torch.tensor([64, 512, 64, 64, 300, 64, 64, 64, 64, 64, 512, 1], dtype=torch.int32)
+    job = lib.Job(ctx2, qs, 512, 0.0)
+    job.set_class_depth(depth)
+    job.scan(bank)
+    s, r, c, tr = job.select(); assert not job.overflowed()
+    job.reset(); job.set_class_depth(None); job.scan(bank)
+    s2, r2, c2, _ = job.select(); assert not job.overflowed()
+    job.close()
+    assert c.tolist() == depth.tolist() and int(c2.min()) == 512
+    for i, d in enumerate(depth.tolist()):
+        assert torch.equal(r[i, :d], r2[i, :d]) and torch.equal(s[i, :d], s2[i, :d])
+        assert bool((r[i, d:] == -1).all()) and int(tr[i]) == 1
+    with pytest.raises(lib.SwatError):
+        j = lib.Job(ctx2, qs, 100, 0.0); j.set_class_depth(torch.full((12,), 101, dtype=torch.int32))
