@@ -168,11 +168,57 @@ def case_primitives(sr):
     np.savez_compressed(os.path.join(OUT, "primitives.npz"), **arrays)
 
 
+def case_fewshot(sr):
+    """The four few-shot samplers (i2i_ranked_sampler_p2p, i2t_rank_sampler, t2t_rank_i2t_tshd_sampler,
+    t2t_rank_i2i_tshd_sampler) on a partitioned bank whose relevant rows are close enough to the
+    few-shot vectors for the 0.25 / 0.65 thresholds to split them."""
+    C, N, k, seed = 5, 1200, 30, 21
+    g = torch.Generator().manual_seed(seed)
+    unit = lambda x: torch.nn.functional.normalize(x.float(), dim=-1)
+    qc = unit(torch.randn(C, 512, generator=g)).to(torch.bfloat16)
+    few = {c: [unit(qc[c].float() + 0.45 * unit(torch.randn(512, generator=g))).to(torch.bfloat16).float() for _ in range(16)] for c in range(C)}
+    labels = torch.randint(0, C, (N,), generator=g)
+    a = torch.rand(N, generator=g) * 0.9
+    b = torch.rand(N, generator=g) * 0.95
+    base = qc[labels].float()
+    cap = unit(a[:, None] * base + torch.sqrt(1 - a * a)[:, None] * unit(torch.randn(N, 512, generator=g))).to(torch.bfloat16)
+    img = unit(b[:, None] * base + torch.sqrt(1 - b * b)[:, None] * unit(torch.randn(N, 512, generator=g))).to(torch.bfloat16)
+    cap[700:716] = cap[13]; img[700:716] = img[13]; labels[700:716] = labels[13]          # ties
+    class_ids = list(range(C))                                                             # fewshot_fea is keyed by int(cls)
+    paths, cmap = synth.make_paths(labels, class_ids=class_ids)
+    tmp = tempfile.mkdtemp()
+    with open(tmp + "/cap.map", "wb") as f:
+        pickle.dump(cmap, f)
+    sr.CAPTION_MAP_DICT["fewshot"] = tmp + "/cap.map"
+    sr.get_fewshot_features = lambda dataset: {c: [x.numpy() for x in few[c]] for c in range(C)}
+    raw = {"caption_features": cap.float(), "image_features": img.float(), "labels": labels, "filepath": paths}
+    feats = sr.transform_extracted_fea(raw)
+    prompts = {str(c): {"mean": qc[c].float()} for c in range(C)}
+    args = Namespace(dataset="fewshot", output_folder=tmp, prefix="FS")
+    lg = logging.getLogger("golden")
+    path_to_row = {p: i for i, p in enumerate(paths)}
+    arrays = dict(cap_bf16=bf16_bits(cap), img_bf16=bf16_bits(img), q_bf16=bf16_bits(qc), labels=labels.numpy(), k=np.int64(k),
+                  few_bf16=bf16_bits(torch.stack([torch.stack(few[c]) for c in range(C)]).to(torch.bfloat16)))
+    counts = {}
+    for name, fn in (("i2i_rank", sr.i2i_ranked_sampler_p2p), ("i2t_rank", sr.i2t_rank_sampler),
+                     ("t2t_i2t", sr.t2t_rank_i2t_tshd_sampler), ("t2t_i2i", sr.t2t_rank_i2i_tshd_sampler)):
+        ms, nd = fn(args, lg, prompts, k, 0.0, feats)
+        files = [p for fl in ms["file_list"] for p in fl]
+        arrays[f"{name}_rows"] = np.asarray([path_to_row[p] for p in files], dtype=np.int64)
+        arrays[f"{name}_labels"] = torch.cat(ms["label_list"]).numpy() if ms["label_list"] else np.zeros(0, np.int64)
+        counts[name] = nd
+        print("fewshot", name, nd)
+    np.savez_compressed(os.path.join(OUT, "bank_fewshot.npz"), **arrays)
+    with open(os.path.join(OUT, "bank_fewshot.json"), "w") as f:
+        json.dump({"counts": counts, "C": C, "N": N, "k": k}, f, indent=1, sort_keys=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sr = import_reference()
     torch.set_num_threads(8)
     case_primitives(sr)
+    case_fewshot(sr)
     case_bank(sr, "bank_bf16", n_rows=1536, C=6, k=40, seed=11, dtype=torch.bfloat16, partitioned=True,
               rho=0.5, tie_block=96)
     case_bank(sr, "bank_f32", n_rows=640, C=4, k=24, seed=12, dtype=torch.float32, partitioned=True,

@@ -178,7 +178,7 @@ def verbatim_t2t_ranked_sampler(prompt_tensors: dict, num_samples: int, threshol
                                 filtered_images_dict: Optional[dict] = None,
                                 caption_map: Optional[dict] = None,
                                 classes: Optional[Iterable[str]] = None,
-                                rank_on_images: bool = False):
+                                rank_on_images: bool = False, rank_fewshot: Optional[dict] = None):
     """``t2t_ranked_sampler`` (:724-771).
 
     Per class in ascending int order (:734-735): GEMV scores (:752), Python ``sorted`` on the
@@ -201,8 +201,12 @@ def verbatim_t2t_ranked_sampler(prompt_tensors: dict, num_samples: int, threshol
         img_embeddings = pre_extracted_feats[cls]["feats"]
         caption_embeddings = pre_extracted_feats[cls]["caption_feats"]
         class_prompt = np.asarray(prompt_tensors[cls]["mean"], dtype=np.float32)[None, :]       # :749-750
-        # t2i_ranked_sampler (:1195-1243) is this function with cal_t2i_similarity on the image features (:1224)
-        sim = similarity(class_prompt, img_embeddings if rank_on_images else caption_embeddings)
+        # t2i_ranked_sampler (:1195-1243) is this function with cal_t2i_similarity on the image features (:1224);
+        # i2i_ranked_sampler_p2p (:1016-1076) / i2t_rank_sampler (:1079-1133) rank by the mean over the few-shot vectors
+        if rank_fewshot is not None:
+            sim = similarity_p2p(np.stack(rank_fewshot[int(cls)]), img_embeddings if rank_on_images else caption_embeddings, "mean")
+        else:
+            sim = similarity(class_prompt, img_embeddings if rank_on_images else caption_embeddings)
         embedding_list = [img_embeddings[i] for i in range(len(img_embeddings))]                 # :753 (N row views)
         items = sorted(list(zip(file_list, sim, range(len(file_list)), embedding_list)), key=lambda x: x[1], reverse=True)
         items = [(p, s_, r) for p, s_, r, _ in items]
@@ -226,7 +230,8 @@ def verbatim_t2t_ranked_t2i_tshd_sampler(prompt_tensors: dict, num_samples: int,
                                          filtered_images_dict: Optional[dict] = None,
                                          caption_map: Optional[dict] = None,
                                          t2i_threshold: float = 0.25,
-                                         classes: Optional[Iterable[str]] = None):
+                                         classes: Optional[Iterable[str]] = None,
+                                         pred_fewshot: Optional[dict] = None, pred_on_captions: bool = False):
     """``t2t_ranked_t2i_tshd_sampler`` (:774-825): as above plus T2I scores (:806); tuples are
     sorted by T2T only (:807-808) and walked with the two-threshold predicate."""
     duplicates_dict = duplicates_dict if duplicates_dict is not None else defaultdict(set)
@@ -246,7 +251,10 @@ def verbatim_t2t_ranked_t2i_tshd_sampler(prompt_tensors: dict, num_samples: int,
         class_prompt = np.asarray(prompt_tensors[cls]["mean"], dtype=np.float32)[None, :]
         sim = similarity(class_prompt, caption_embeddings)
         embedding_list = [img_embeddings[i] for i in range(len(img_embeddings))]                 # :805 (N row views)
-        t2i = similarity(class_prompt, img_embeddings)
+        if pred_fewshot is not None:       # t2t_rank_i2t_tshd_sampler :869 (captions, 0.25) / t2t_rank_i2i_tshd_sampler :929 (images, 0.65)
+            t2i = similarity_p2p(np.stack(pred_fewshot[int(cls)]), caption_embeddings if pred_on_captions else img_embeddings, "max")
+        else:
+            t2i = similarity(class_prompt, img_embeddings)
         items = sorted(list(zip(file_list, sim, range(len(file_list)), t2i, embedding_list)), key=lambda x: x[1], reverse=True)
         items = [(p, s_, r, t_) for p, s_, r, t_, _ in items]
         acc = walk_t2t_t2i(items, int(cls), num_samples, threshold, t2i_threshold,

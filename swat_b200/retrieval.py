@@ -193,33 +193,82 @@ def check_caption(caption_map, img_path):
     return caption_map[img_cls][img_id]
 
 
+def _fewshot_queries(fewshot_fea, classes):
+    """``fewshot_fea[int(cls)]`` = list of few-shot image embeddings (``get_fewshot_features`` :997-1014)
+    -> stacked query rows, class_of_query."""
+    rows, coq = [], []
+    for i, c in enumerate(classes):
+        f = fewshot_fea[int(c)]
+        f = torch.stack([torch.as_tensor(x).detach().float().cpu().reshape(-1) for x in f])
+        rows.append(f)
+        coq.extend([i] * f.shape[0])
+    return torch.cat(rows), torch.tensor(coq, dtype=torch.int32)
+
+
 def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
-                 filtered_images_dict, with_t2i: bool, t2i_threshold: float = 0.25, rank_on_images: bool = False):
+                 filtered_images_dict, with_t2i: bool, t2i_threshold: float = 0.25, rank_on_images: bool = False,
+                 rank_fewshot=None, pred_fewshot=None, pred_on_captions: bool = False, file_prefix: Optional[bool] = None):
+    """One engine for every ranked sampler of the reference:
+
+    rank stage   -- class prompt (``['mean']``) or the mean over a class's few-shot vectors (``rank_fewshot``),
+                    against the caption bank or the image bank;
+    predicate    -- none, the same prompt against the image bank (T2T-rank-T2I-tshd), or the max over the
+                    few-shot vectors (``pred_fewshot``) against the image / caption bank, ``>= t2i_threshold``.
+    """
     classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))          # :734-735
     cap, img, paths, row_class = _flatten(pre_extracted_feats, classes)
     feat_bank = img                                          # feature_list always carries the image features (:753, :1225)
-    if rank_on_images:                                       # T2I-rank scores the image bank instead of the captions (:1224)
-        cap = img
     bank_dtype = getattr(args, "bank_dtype", None)
     if bank_dtype in ("bf16", torch.bfloat16):
         cap = cap.to(torch.bfloat16); img = img.to(torch.bfloat16)
     elif cap.dtype not in (torch.float32, torch.bfloat16):
         cap = cap.float(); img = img.float()
+    rank_bank = img if rank_on_images else cap               # T2I-rank / I2I-rank score the image bank (:1224, :1049)
     device = int(getattr(args, "device_index", 0))
     ctx = get_context(device)
-    q = torch.stack([torch.as_tensor(prompt_tensors[c]["mean"]).detach().float().cpu().reshape(-1) for c in classes])  # :749
-    qs = _lib.Queries(ctx, q)
-    exclude = _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_images_dict)
-    t2i_bank = img if with_t2i else None
-    if cap.is_cuda:
-        res = _lib.topk(ctx, qs, cap.contiguous(), num_samples, threshold, t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(),
-                        t2i_threshold=t2i_threshold, row_class=None if row_class is None else row_class.cuda(device),
-                        exclude=None if exclude is None else exclude.cuda(device))
-        scores, rows, t2i, counts = [None if x is None else x.cpu() for x in res]
+    if rank_fewshot is not None:                             # I2I-rank / I2T-rank: mean over the few-shot columns (:1049, :1112)
+        fq, fcoq = _fewshot_queries(rank_fewshot, classes)
+        qs = _lib.Queries(ctx, fq, fcoq, len(classes), "mean")
     else:
-        scores, rows, t2i, counts = _lib.topk_host(ctx, qs, cap.contiguous(), num_samples, threshold,
-                                                  t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(),
-                                                  t2i_threshold=t2i_threshold, row_class=row_class, exclude=exclude)
+        q = torch.stack([torch.as_tensor(prompt_tensors[c]["mean"]).detach().float().cpu().reshape(-1) for c in classes])  # :749
+        qs = _lib.Queries(ctx, q)
+    exclude = _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_images_dict)
+    if pred_fewshot is None:
+        t2i_bank = img if with_t2i else None
+        if rank_bank.is_cuda:
+            res = _lib.topk(ctx, qs, rank_bank.contiguous(), num_samples, threshold,
+                            t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(), t2i_threshold=t2i_threshold,
+                            row_class=None if row_class is None else row_class.cuda(device),
+                            exclude=None if exclude is None else exclude.cuda(device))
+            scores, rows, t2i, counts = [None if x is None else x.cpu() for x in res]
+        else:
+            scores, rows, t2i, counts = _lib.topk_host(ctx, qs, rank_bank.contiguous(), num_samples, threshold,
+                                                      t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(),
+                                                      t2i_threshold=t2i_threshold, row_class=row_class, exclude=exclude)
+    else:
+        # predicate with its own query set: max over the class's few-shot vectors (:869, :929), on the
+        # caption bank (I2T) or the image bank (I2I).  Composed from the job / walk entry points; the
+        # over-fetch deepens until every class is provably exact (candidate list not truncated, or k accepted).
+        from . import dist as _dist
+        pq, pcoq = _fewshot_queries(pred_fewshot, classes)
+        qs_pred = _lib.Queries(ctx, pq, pcoq, len(classes), "max")
+        d_rank = rank_bank.contiguous().cuda(device)
+        d_pred = (cap if pred_on_captions else img).contiguous().cuda(device)
+        d_rc = None if row_class is None else row_class.cuda(device)
+        d_ex = None if exclude is None else exclude.cuda(device)
+        kf = min(4096, max(1024, 2 * num_samples))
+        while True:
+            sc, rw, _, cn, tr = _dist.local_candidates(ctx, qs, d_rank, kf, threshold, None, 0, d_rc, d_ex)
+            o_s, o_r, o_t, o_c, o_i = _lib.t2i_walk(ctx, qs_pred, d_pred, sc, rw, cn, tr, num_samples, t2i_threshold)
+            if int(o_i.sum()) == 0:
+                break
+            if kf >= 4096:
+                raise _lib.SwatError(-5, "few-shot predicate walk not provably exact at k_fetch=4096 "
+                                         "(more than 4096 eligible rows in a class and fewer than k pass)")
+            kf = min(4096, kf * 2)
+        scores, rows, t2i, counts = o_s.cpu(), o_r.cpu(), o_t.cpu(), o_c.cpu()
+        qs_pred.close()
+        with_t2i = True
     qs.close()
     caption_map = None
     cmap_path = getattr(args, "caption_map_path", None)
@@ -257,7 +306,8 @@ def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extra
             else:
                 sampled_list.append(f"{round(sc[j], 4)}/{threshold}, {p}, {caption}")
     logger.info(f"len(sampled_list): {len(sampled_list)}")
-    prefix = "" if with_t2i else f"{args.prefix}_"                                     # :763,768,1236,1241 vs :817,822
+    prefixed = (not with_t2i) if file_prefix is None else file_prefix                 # :763,768,1236,1241 vs :817,822
+    prefix = f"{args.prefix}_" if prefixed else ""
     os.makedirs(args.output_folder, exist_ok=True)
     with open(f"{args.output_folder}/{prefix}sampled_list.txt", "w") as f:
         f.write("\n".join(sampled_list))
@@ -287,6 +337,52 @@ def t2i_ranked_sampler(args, logger, prompt_tensors, num_samples, threshold, pre
     (``cal_t2i_similarity`` :1224) -- the same kernel with the banks swapped."""
     return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
                         filtered_images_dict, with_t2i=False, rank_on_images=True)
+
+
+def _load_fewshot(args):
+    fs = getattr(args, "fewshot_features", None)
+    if fs is not None:
+        return fs
+    fn = getattr(args, "fewshot_path", None) or \
+        f"../data/{args.dataset}/pre_extracted/{args.dataset}_probing_vitb32_openclip_laion400m_1_train_features.pth"
+    fea = torch.load(fn, map_location="cpu", weights_only=False)                      # get_fewshot_features :997-1014
+    out: Dict[int, list] = {}
+    for f, l in zip(fea["image_features"], fea["labels"].tolist()):
+        out.setdefault(int(l), []).append(f)
+    return out
+
+
+def i2i_ranked_sampler_p2p(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                           duplicates_dict: defaultdict = defaultdict(set), filtered_images_dict: defaultdict = defaultdict(set)):
+    """``i2i_ranked_sampler_p2p`` (:1016-1076): rank by the MEAN cosine between a row's image feature and
+    the class's 16 few-shot image features (``i2i_similarity_p2p(..., 'mean')`` :1049)."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=False, rank_on_images=True, rank_fewshot=_load_fewshot(args))
+
+
+def i2t_rank_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                     duplicates_dict: defaultdict = defaultdict(set), filtered_images_dict: defaultdict = defaultdict(set)):
+    """``i2t_rank_sampler`` (:1079-1133): the same ranking against the CAPTION features (:1112)."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=False, rank_on_images=False, rank_fewshot=_load_fewshot(args))
+
+
+def t2t_rank_i2t_tshd_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                              duplicates_dict: defaultdict = defaultdict(set), filtered_images_dict: defaultdict = defaultdict(set)):
+    """``t2t_rank_i2t_tshd_sampler`` (:831-890): T2T ranking; accept iff the MAX cosine between the row's
+    caption feature and the class's few-shot image features is >= 0.25 (:869, default threshold :499)."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=True, t2i_threshold=0.25, pred_fewshot=_load_fewshot(args),
+                        pred_on_captions=True, file_prefix=False)
+
+
+def t2t_rank_i2i_tshd_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                              duplicates_dict: defaultdict = defaultdict(set), filtered_images_dict: defaultdict = defaultdict(set)):
+    """``t2t_rank_i2i_tshd_sampler`` (:893-953): T2T ranking; accept iff the MAX cosine between the row's
+    image feature and the class's few-shot image features is >= 0.65 (:929, :939)."""
+    return _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
+                        filtered_images_dict, with_t2i=True, t2i_threshold=0.65, pred_fewshot=_load_fewshot(args),
+                        pred_on_captions=False, file_prefix=False)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -329,6 +425,14 @@ def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=Non
         mined_split, num_imgs_sampled_dict = t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
     elif args.sampling_method == "T2I-rank":                                         # :1610-1617
         mined_split, num_imgs_sampled_dict = t2i_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "I2I-rank":                                         # :1538-1551
+        mined_split, num_imgs_sampled_dict = i2i_ranked_sampler_p2p(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "I2T-rank":                                         # :1553-1560
+        mined_split, num_imgs_sampled_dict = i2t_rank_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "T2T-rank-I2T-tshd":                                # :1591-1598
+        mined_split, num_imgs_sampled_dict = t2t_rank_i2t_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "T2T-rank-I2I-tshd":                                # :1600-1607
+        mined_split, num_imgs_sampled_dict = t2t_rank_i2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
     else:
         raise NotImplementedError(f"sampling method {args.sampling_method} is outside the accelerated hot path")
     final_file_list = [p for fl in mined_split["file_list"] for p in fl]

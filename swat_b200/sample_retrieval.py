@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Drop-in for ``python retrieval/sample_retrieval.py`` (reference CLI at ``sample_retrieval.py:1673-1747``)
-for the sampling methods on the accelerated path: ``T2T-rank``, ``T2T-rank-T2I-tshd`` and ``T2I-rank``.
+for the ranked sampling methods: ``T2T-rank``, ``T2T-rank-T2I-tshd``, ``T2I-rank``, ``I2I-rank``, ``I2T-rank``,
+``T2T-rank-I2T-tshd``, ``T2T-rank-I2I-tshd``.
 
 Same flags and defaults, same outputs: ``output/{dataset}_{model_cfg}_{prefix}/{prefix}.txt``
 (``"<path> <label> 0"`` per accepted row, class-major), ``{prefix}_num_imgs_sampled.json``,
@@ -64,6 +65,7 @@ def build_parser():
     p.add_argument("--mined_pth", type=str, default=None)
     p.add_argument("--flat_shard", type=str, default=None)
     p.add_argument("--caption_map_path", type=str, default=None)
+    p.add_argument("--fewshot_path", type=str, default=None, help="few-shot feature .pth (default: the reference's ../data/{ds}/pre_extracted/...)")
     p.add_argument("--data_dir", type=str, default="../data", help="where the split txt is copied to (../data/{dataset}/)")
     p.add_argument("--device_index", type=int, default=0)
     return p
@@ -72,7 +74,8 @@ def build_parser():
 def main(argv=None):
     time_start = time()
     args = build_parser().parse_args(argv)
-    if args.sampling_method not in ("T2T-rank", "T2T-rank-T2I-tshd", "T2I-rank"):
+    if args.sampling_method not in ("T2T-rank", "T2T-rank-T2I-tshd", "T2I-rank", "I2I-rank", "I2T-rank", "T2T-rank-I2T-tshd",
+                                    "T2T-rank-I2I-tshd"):
         raise NotImplementedError(f"--sampling_method {args.sampling_method} is outside the accelerated hot path; "
                                   "use the reference script for it")
     if args.zeroshot_img_filter or args.image_dedup:

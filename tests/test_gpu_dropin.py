@@ -106,3 +106,37 @@ def test_s1_primitives_on_gpu():
         np.testing.assert_allclose(retrieval.i2i_similarity_p2p([f for f in F], X, mode), z[f"p2p_{mode}"], atol=2e-6)
     with pytest.raises(ValueError):
         retrieval.i2i_similarity_p2p([f for f in F], X, "median")
+
+
+def test_fewshot_samplers_match_reference_outputs(tmp_path):
+    """The four few-shot samplers of the reference on the GPU: rank by the mean over 16 few-shot vectors
+    (I2I-rank, I2T-rank) and T2T ranking with a max-over-few-shot predicate (>= 0.25 captions, >= 0.65 images)."""
+    from swat_b200 import retrieval
+    from tests.test_oracle_golden import _fewshot_case
+    z, meta, cap, img, q, few, raw, prompts, fewshot, paths, cmap = _fewshot_case()
+    k = int(z["k"]); labels = z["labels"]; C = q.shape[0]
+    cmap_path = str(tmp_path / "cap.map"); pickle.dump(cmap, open(cmap_path, "wb"))
+    raw_t = {"caption_features": torch.from_numpy(cap), "image_features": torch.from_numpy(img),
+             "labels": torch.from_numpy(labels), "filepath": paths}
+    prompts_t = {c: {"mean": torch.from_numpy(v["mean"])} for c, v in prompts.items()}
+    args = Namespace(dataset="fewshot", output_folder=str(tmp_path / "out"), prefix="FS", bank_dtype="bf16", caption_map_path=cmap_path,
+                     fewshot_features={c: [torch.from_numpy(x) for x in v] for c, v in fewshot.items()})
+    feats = retrieval.transform_extracted_fea(raw_t)
+    path_row = {p: i for i, p in enumerate(paths)}
+    fmean = few.mean(axis=1)
+    rank_scores = {"i2i_rank": (img @ few.reshape(-1, 512).T).reshape(len(img), C, -1).mean(-1),
+                   "i2t_rank": (cap @ few.reshape(-1, 512).T).reshape(len(cap), C, -1).mean(-1),
+                   "t2t_i2t": so.score_matrix(cap, q), "t2t_i2i": so.score_matrix(cap, q)}
+    fns = {"i2i_rank": retrieval.i2i_ranked_sampler_p2p, "i2t_rank": retrieval.i2t_rank_sampler,
+           "t2t_i2t": retrieval.t2t_rank_i2t_tshd_sampler, "t2t_i2i": retrieval.t2t_rank_i2i_tshd_sampler}
+    for name, fn in fns.items():
+        ms, nd = fn(args, logging.getLogger("t"), prompts_t, k, 0.0, feats)
+        assert nd == meta["counts"][name], name
+        ref_rows, S = z[f"{name}_rows"], rank_scores[name]
+        pos = 0
+        for files, labs in zip(ms["file_list"], ms["label_list"]):
+            n = len(files); c = int(labs[0])
+            assert_walk_equal([path_row[p] for p in files], ref_rows[pos:pos + n], lambda r, c=c: S[r, c], TIE_TOL, boundary_tol=1e-3,
+                              what=f"{name} class {c}")
+            pos += n
+        assert torch.cat(ms["label_list"]).tolist() == z[f"{name}_labels"].tolist()

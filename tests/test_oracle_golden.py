@@ -133,3 +133,39 @@ def test_merge_is_shard_count_invariant():
         for c in range(3):
             assert r[c].tolist() == full_rows[c].tolist()
             np.testing.assert_array_equal(s_[c], S[full_rows[c], c])
+
+
+def _fewshot_case():
+    import json
+    from tests.golden_util import bf16_bits_to_f32
+    z = np.load(f"{GOLDEN}/bank_fewshot.npz")
+    meta = json.load(open(f"{GOLDEN}/bank_fewshot.json"))
+    cap, img, q = bf16_bits_to_f32(z["cap_bf16"]), bf16_bits_to_f32(z["img_bf16"]), bf16_bits_to_f32(z["q_bf16"])
+    few = bf16_bits_to_f32(z["few_bf16"])                       # [C,16,512]
+    labels = z["labels"]; C = q.shape[0]
+    paths, cmap = make_paths(labels, np.arange(C))
+    raw = {"caption_features": cap, "image_features": img, "labels": labels, "filepath": paths}
+    prompts = {str(c): {"mean": q[c]} for c in range(C)}
+    fewshot = {c: [few[c, i] for i in range(few.shape[1])] for c in range(C)}
+    return z, meta, cap, img, q, few, raw, prompts, fewshot, paths, cmap
+
+
+def test_fewshot_samplers_match_reference():
+    """i2i_ranked_sampler_p2p, i2t_rank_sampler, t2t_rank_i2t_tshd_sampler, t2t_rank_i2i_tshd_sampler
+    (reference :1016-1133, :831-953) -- verbatim port vs the reference's outputs."""
+    z, meta, cap, img, q, few, raw, prompts, fewshot, paths, cmap = _fewshot_case()
+    k = int(z["k"])
+    feats = so.transform_extracted_fea(raw)
+    runs = {
+        "i2i_rank": lambda: so.verbatim_t2t_ranked_sampler(prompts, k, 0.0, feats, rank_on_images=True, rank_fewshot=fewshot),
+        "i2t_rank": lambda: so.verbatim_t2t_ranked_sampler(prompts, k, 0.0, feats, rank_on_images=False, rank_fewshot=fewshot),
+        "t2t_i2t": lambda: so.verbatim_t2t_ranked_t2i_tshd_sampler(prompts, k, 0.0, feats, t2i_threshold=0.25, pred_fewshot=fewshot, pred_on_captions=True),
+        "t2t_i2i": lambda: so.verbatim_t2t_ranked_t2i_tshd_sampler(prompts, k, 0.0, feats, t2i_threshold=0.65, pred_fewshot=fewshot, pred_on_captions=False),
+    }
+    for name, fn in runs.items():
+        ms, nd, _ = fn()
+        assert nd == meta["counts"][name], name
+        got = np.concatenate([feats[str(int(l[0]))]["row_ids"][r] for r, l in zip(ms["row_list"], ms["label_list"])])
+        assert got.tolist() == z[f"{name}_rows"].tolist(), name
+        assert np.concatenate(ms["label_list"]).tolist() == z[f"{name}_labels"].tolist()
+    assert z["t2t_i2i_rows"].tolist() != z["t2t_i2t_rows"].tolist()      # the two predicates really select differently
