@@ -144,6 +144,15 @@ int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_r
 int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype,
                           int64_t n_rows, float* d_out, int32_t engine, void* stream);
 
+/* ---- exclusion-set producer: remove_near_duplicates2 (:237-275) --------------------------------- */
+/* d_order [n]: bank row ids grouped by class (file order kept inside a class), d_class_start [C+1]:
+ * first position of each class in d_order.  d_dup [n] (by position in d_order) is set to 1 for every
+ * row that has an EARLIER row of its class with cosine > threshold (the reference uses 0.9, :257).
+ * The caller zeroes d_dup. */
+int32_t swat_near_duplicates(swat_ctx* ctx, const void* d_bank, int32_t dtype, int64_t n_rows, const int64_t* d_order,
+                             const int32_t* d_class_start, int32_t n_classes, int32_t max_class_rows, float threshold,
+                             uint8_t* d_dup, void* stream);
+
 /* ---- whole pipeline on HBM-resident banks ------------------------------------------------------ */
 /* t2t_ranked_sampler (:724-771) when d_t2i_bank == NULL, t2t_ranked_t2i_tshd_sampler (:774-825)
  * otherwise, for all classes at once.  Outputs [C,k] (d_out_t2i nullable), rows are

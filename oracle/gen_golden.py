@@ -96,7 +96,11 @@ def case_bank(sr, name, n_rows, C, k, seed, dtype, partitioned, rho, tie_block):
            "labels": torch.tensor([class_ids[int(l)] for l in labels.tolist()]), "filepath": paths}
     prompts = {str(class_ids[c]): {"mean": qc[c].float()} for c in range(C)}
     res_p, feats = run_samplers(sr, raw, prompts, k, tmp, name, unpartitioned=False)
+    path_to_row_tmp = {p: i for i, p in enumerate(paths)}
     res_u, _ = run_samplers(sr, raw, prompts, k, tmp, name, unpartitioned=True)
+    # near-duplicate removal (remove_near_duplicates2 :237-275) on the regrouped dict
+    dd, frac, avg = sr.remove_near_duplicates2(feats)
+    dup_fixture = {"dict": {kk: sorted(path_to_row_tmp[p] for p in v) for kk, v in dd.items() if v}, "fractions": frac, "avg": avg}
     # regroup fixture: key order + per-class original rows
     path_to_row = {p: i for i, p in enumerate(paths)}
     regroup_keys = list(feats.keys())
@@ -119,7 +123,7 @@ def case_bank(sr, name, n_rows, C, k, seed, dtype, partitioned, rho, tie_block):
         arrays[f"regroup_rows_{i}"] = regroup_rows[i]
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
     meta = dict(name=name, n_rows=n_rows, C=C, k=k, seed=seed, dtype=str(dtype), partitioned=partitioned,
-                regroup_keys=regroup_keys,
+                regroup_keys=regroup_keys, near_dup=dup_fixture,
                 counts={tag: {m: res[m]["counts"] for m in res} for tag, res in (("part", res_p), ("unpart", res_u))},
                 diag={tag: {m: {x: res[m][x] for x in ("filtered_sha", "sampled_sha", "sampled_head", "n_filtered")}
                             for m in res} for tag, res in (("part", res_p), ("unpart", res_u))})

@@ -112,6 +112,36 @@ def transform_extracted_fea(pre_extracted_feats: dict) -> dict:
 
 
 # --------------------------------------------------------------------------------------
+# exclusion-set producer
+# --------------------------------------------------------------------------------------
+def near_duplicate_positions(img_embeddings: np.ndarray, threshold: float = 0.9) -> np.ndarray:
+    """Positions j with an earlier row i < j whose cosine exceeds the threshold
+    (``np.triu(X @ X^T, k=1) > 0.9`` -> ``j_indices``, :254-259)."""
+    x = np.asarray(img_embeddings, dtype=np.float32)
+    sim = x @ x.T
+    _, j = np.where(np.triu(sim, k=1) > threshold)
+    return np.unique(j)
+
+
+def remove_near_duplicates2(pre_extracted_feats: dict, threshold: float = 0.9, positional: bool = False):
+    """``remove_near_duplicates2`` (:237-275), including its file-id-vs-position comparison (:262-267)."""
+    classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))
+    dup = defaultdict(set)
+    fractions = []
+    for cls in classes:
+        files = pre_extracted_feats[cls]["file_paths"]
+        if files is None:
+            continue
+        to_remove = set(near_duplicate_positions(pre_extracted_feats[cls]["feats"], threshold).tolist())
+        for pos, f in enumerate(files):
+            key = pos if positional else int(f.split("/")[-1].split(".")[0])
+            if key in to_remove:
+                dup[cls].add(f)
+        fractions.append(len(to_remove) / len(files))
+    return dup, fractions, sum(fractions) / len(fractions)
+
+
+# --------------------------------------------------------------------------------------
 # accept / walk
 # --------------------------------------------------------------------------------------
 def check_caption(caption_map: dict, img_path: str) -> str:

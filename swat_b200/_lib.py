@@ -24,7 +24,7 @@ EXPORTS = [
     "swat_version", "swat_last_error", "swat_ctx_create", "swat_ctx_destroy", "swat_ctx_set_option",
     "swat_ctx_launch_count", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
     "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
-    "swat_scores_dense", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
+    "swat_scores_dense", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
 ]
 
 
@@ -68,6 +68,7 @@ def load() -> C.CDLL:
         "swat_t2i_walk": [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_merge_topk": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_scores_dense": [vp, vp, vp, i32, i64, vp, i32, vp],
+        "swat_near_duplicates": [vp, vp, i32, i64, vp, vp, i32, i32, f32, vp, vp],
         "swat_topk": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
         "swat_topk_host": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp],
     }
@@ -267,6 +268,21 @@ def scores_dense(ctx: Context, queries: Queries, bank: torch.Tensor, engine="aut
     _check(load().swat_scores_dense(ctx._h, queries._h, _ptr(bank), _dtype_code(bank), int(bank.shape[0]), _ptr(out),
                                     ENGINE[engine], _stream(ctx.device)))
     return out
+
+
+def near_duplicates(ctx: Context, bank: torch.Tensor, order: torch.Tensor, class_start: torch.Tensor, threshold: float = 0.9) -> torch.Tensor:
+    """``dup[p] = 1`` iff row ``order[p]`` has an earlier row of its class with cosine > threshold."""
+    _bank_ok(bank, "bank", True)
+    dev = bank.device
+    order = order.to(dev, torch.int64).contiguous()
+    cs = class_start.to(torch.int32).cpu()
+    n_classes = int(cs.numel()) - 1
+    max_rows = int((cs[1:] - cs[:-1]).max()) if n_classes > 0 else 0
+    d_cs = cs.to(dev)
+    dup = torch.zeros(order.numel(), dtype=torch.uint8, device=dev)
+    _check(load().swat_near_duplicates(ctx._h, _ptr(bank), _dtype_code(bank), int(bank.shape[0]), _ptr(order), _ptr(d_cs), n_classes,
+                                       max_rows, float(threshold), _ptr(dup), _stream(ctx.device)))
+    return dup
 
 
 def topk(ctx: Context, queries: Queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: float = 0.0,

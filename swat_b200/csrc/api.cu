@@ -1011,6 +1011,19 @@ int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_r
   return SWAT_OK;
 }
 
+int32_t swat_near_duplicates(swat_ctx* ctx, const void* d_bank, int32_t dtype, int64_t n_rows, const int64_t* d_order,
+                             const int32_t* d_class_start, int32_t n_classes, int32_t max_class_rows, float threshold,
+                             uint8_t* d_dup, void* stream) {
+  if (!ctx || !d_bank || !d_order || !d_class_start || !d_dup) return fail(SWAT_ERR_INVALID, "null argument");
+  if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
+  if (n_rows < 0 || n_classes < 0 || max_class_rows < 0 || n_classes > 65535) return fail(SWAT_ERR_INVALID, "bad shape");
+  (void)cudaGetLastError();
+  CU_OK(cudaSetDevice(ctx->device));
+  CU_OK(launch_near_dup(d_bank, dtype, d_order, d_class_start, n_classes, max_class_rows, threshold, d_dup, static_cast<cudaStream_t>(stream)));
+  ctx->launches += 1;
+  return SWAT_OK;
+}
+
 int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows, float* d_out,
                           int32_t engine, void* stream) {
   if (!ctx || !q || !d_bank || !d_out) return fail(SWAT_ERR_INVALID, "null argument");

@@ -52,6 +52,9 @@ cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const flo
                          int32_t* d_out_counts, int32_t* d_incomplete, cudaStream_t stream);
 
 cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t stream);
+// per class: flag rows that have an earlier row of the class with cosine > threshold (select.cu)
+cudaError_t launch_near_dup(const void* bank, int dtype, const int64_t* d_order, const int32_t* d_class_start, int n_classes,
+                            int max_class_rows, float threshold, uint8_t* d_dup, cudaStream_t stream);
 // seed a fresh job from dense prefix scores [C][n_prefix] (see select.cu)
 cudaError_t launch_bootstrap(const JobState& st, int n_classes, const float* d_scores_t, uint32_t n_prefix, uint32_t row_base,
                              uint32_t first_spare_list, cudaStream_t stream);

@@ -436,7 +436,52 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
   }
 }
 
+// ---------------------------------------------------------------------------------- near duplicates
+// remove_near_duplicates2 (sample_retrieval.py:237-275): inside a class, row j is a duplicate iff some
+// EARLIER row i of the class has <x_i, x_j> > threshold (np.triu(sim, k=1) > 0.9, j indices).  Rows are
+// addressed through `order` (bank rows sorted by class, file order kept inside a class).  One CTA per
+// (class, block of 32 j rows): 32 x 32 threads, thread (ty, tx) owns the pair (i-block row ty, j row tx).
+template <typename T>
+__global__ void __launch_bounds__(1024)
+near_dup_kernel(const T* __restrict__ bank, const int64_t* __restrict__ order, const int32_t* __restrict__ class_start,
+                float threshold, uint8_t* __restrict__ dup) {
+  __shared__ float sA[32][33], sB[32][33];
+  const int c = blockIdx.y;
+  const int s = class_start[c], e = class_start[c + 1];
+  const int jb = blockIdx.x;
+  if (s + jb * 32 >= e) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int j = s + jb * 32 + tx;
+  const int jl = s + jb * 32 + ty;                       // the j row this thread stages
+  const int64_t rj = jl < e ? order[jl] : -1;
+  bool flag = false;
+  for (int ib = 0; ib <= jb; ++ib) {
+    const int i = s + ib * 32 + ty;
+    const int64_t ri = i < e ? order[i] : -1;
+    float dot = 0.0f;
+    for (int k0 = 0; k0 < kDim; k0 += 32) {
+      sA[ty][tx] = ri >= 0 ? static_cast<float>(bank[ri * kDim + k0 + tx]) : 0.0f;
+      sB[ty][tx] = rj >= 0 ? static_cast<float>(bank[rj * kDim + k0 + tx]) : 0.0f;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) dot = fmaf(sA[ty][kk], sB[tx][kk], dot);
+      __syncthreads();
+    }
+    if (i < j && i < e && j < e && dot > threshold) flag = true;
+  }
+  if (flag) dup[j] = 1;      // every writer stores the same value
+}
+
 }  // namespace
+
+cudaError_t launch_near_dup(const void* bank, int dtype, const int64_t* d_order, const int32_t* d_class_start, int n_classes,
+                            int max_class_rows, float threshold, uint8_t* d_dup, cudaStream_t stream) {
+  if (n_classes <= 0 || max_class_rows <= 0) return cudaSuccess;
+  const dim3 grid((max_class_rows + 31) / 32, n_classes), block(32, 32);
+  if (dtype == 0) near_dup_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), d_order, d_class_start, threshold, d_dup);
+  else near_dup_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(bank), d_order, d_class_start, threshold, d_dup);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
                           int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream) {

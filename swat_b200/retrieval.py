@@ -130,6 +130,51 @@ def transform_extracted_fea(pre_extracted_feats: dict) -> RegroupedFeats:
 
 
 # ---------------------------------------------------------------------------------------------
+# exclusion-set producer
+# ---------------------------------------------------------------------------------------------
+def remove_near_duplicates2(pre_extracted_feats, threshold: float = 0.9, positional: bool = False, device: int = 0):
+    """``remove_near_duplicates2`` (:237-275): per class, image rows whose cosine to an EARLIER row of the
+    class exceeds 0.9 are duplicates.  Returns ``(duplicate_images_dict, dup_images_fraction,
+    avg_dup_images_fraction)`` like the reference.
+
+    The reference then keeps the files whose *file id* (``<id>.jpg``) equals one of the duplicate
+    *positions* (:262-267) -- it compares names with indices.  That is reproduced by default because the
+    resulting ``duplicates_dict`` is what its samplers consume; ``positional=True`` marks the duplicate
+    rows themselves."""
+    ctx = get_context(device)
+    classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))
+    if isinstance(pre_extracted_feats, RegroupedFeats):
+        img = torch.as_tensor(pre_extracted_feats.flat["image_features"])
+        rows = [pre_extracted_feats.rows_of(c) for c in classes]
+        files = [[pre_extracted_feats.flat["filepath"][i] for i in r.tolist()] for r in rows]
+        order = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64)
+    else:
+        feats = [torch.as_tensor(pre_extracted_feats[c]["feats"]) for c in classes]
+        files = [pre_extracted_feats[c]["file_paths"] for c in classes]
+        img = torch.cat(feats)
+        order = torch.arange(img.shape[0], dtype=torch.int64)
+    if img.dtype not in (torch.float32, torch.bfloat16):
+        img = img.float()
+    sizes = torch.tensor([len(f) for f in files], dtype=torch.int64)
+    class_start = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(sizes, 0)])
+    dup = _lib.near_duplicates(ctx, img.contiguous().cuda(device), order, class_start, threshold).cpu().numpy().astype(bool)
+    duplicate_images_dict = defaultdict(set)
+    dup_images_fraction = []
+    for ci, cls in enumerate(classes):
+        s0, s1 = int(class_start[ci]), int(class_start[ci + 1])
+        if s1 == s0:
+            continue
+        to_remove = set(np.nonzero(dup[s0:s1])[0].tolist())                  # positions inside the class (:259)
+        for pos, f in enumerate(files[ci]):
+            key = pos if positional else int(f.split('/')[-1].split('.')[0])   # :264-266
+            if key in to_remove:
+                duplicate_images_dict[cls].add(f)
+        dup_images_fraction.append(len(to_remove) / len(files[ci]))
+    avg = sum(dup_images_fraction) / len(dup_images_fraction) if dup_images_fraction else 0.0
+    return duplicate_images_dict, dup_images_fraction, avg
+
+
+# ---------------------------------------------------------------------------------------------
 # samplers
 # ---------------------------------------------------------------------------------------------
 def _flatten(pre_extracted_feats, classes: List[str]):

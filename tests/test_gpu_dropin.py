@@ -140,3 +140,33 @@ def test_fewshot_samplers_match_reference_outputs(tmp_path):
                               what=f"{name} class {c}")
             pos += n
         assert torch.cat(ms["label_list"]).tolist() == z[f"{name}_labels"].tolist()
+
+
+@pytest.mark.parametrize("name", ["bank_bf16", "bank_f32"])
+def test_near_duplicate_removal_matches_reference(name):
+    """remove_near_duplicates2 on the GPU (triangular Gram kernel) vs the reference's outputs, and its result
+    used as the samplers' exclusion set."""
+    from swat_b200 import retrieval
+    z, meta, cap, img, q, raw, prompts, paths, cmap = _case(name)
+    feats = retrieval.transform_extracted_fea(raw)
+    dd, frac, avg = retrieval.remove_near_duplicates2(feats)
+    ref = meta["near_dup"]
+    np.testing.assert_allclose(frac, ref["fractions"], atol=1e-12)
+    row = {p: i for i, p in enumerate(paths)}
+    assert {k: sorted(row[p] for p in v) for k, v in dd.items() if v} == ref["dict"]
+    # positional variant: flagged rows really have an earlier near-identical row of their class
+    dp, _, _ = retrieval.remove_near_duplicates2(feats, positional=True)
+    o_dd, _, _ = so.remove_near_duplicates2(so.transform_extracted_fea({k: (v.numpy() if torch.is_tensor(v) else v) for k, v in raw.items()}), positional=True)
+    assert {k: sorted(v) for k, v in dp.items()} == {k: sorted(v) for k, v in o_dd.items()}
+    # as exclusion set of the sampler: no excluded path may be sampled, counts follow the oracle
+    import logging
+    from argparse import Namespace
+    args = Namespace(dataset="synthetic", output_folder="/tmp/swat_dedup_out", prefix="D", bank_dtype="bf16" if name == "bank_bf16" else "f32",
+                     caption_map_path="/nonexistent")
+    ms, nd = retrieval.t2t_ranked_sampler(args, logging.getLogger("t"), prompts, int(z["k"]), 0.0, feats, duplicates_dict=dp)
+    sampled = {p for fl in ms["file_list"] for p in fl}
+    assert not (sampled & {p for v in dp.values() for p in v})
+    o_ms, o_nd, _ = so.verbatim_t2t_ranked_sampler({k: {"mean": v["mean"].numpy()} for k, v in prompts.items()}, int(z["k"]), 0.0,
+                                                  so.transform_extracted_fea({k: (v.numpy() if torch.is_tensor(v) else v) for k, v in raw.items()}),
+                                                  duplicates_dict={k: set(v) for k, v in o_dd.items()})
+    assert nd == o_nd

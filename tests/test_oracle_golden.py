@@ -169,3 +169,19 @@ def test_fewshot_samplers_match_reference():
         assert got.tolist() == z[f"{name}_rows"].tolist(), name
         assert np.concatenate(ms["label_list"]).tolist() == z[f"{name}_labels"].tolist()
     assert z["t2t_i2i_rows"].tolist() != z["t2t_i2t_rows"].tolist()      # the two predicates really select differently
+
+
+@pytest.mark.parametrize("name", ["bank_bf16", "bank_f32"])
+def test_near_duplicates_match_reference(name):
+    """remove_near_duplicates2 (:237-275): duplicate fractions per class and the (file-id keyed) dict."""
+    z, meta, cap, img, q = load_bank_case(name)
+    class_ids, labels = z["class_ids"], z["labels"]
+    paths, _ = make_paths(labels, class_ids)
+    raw = {"caption_features": cap, "image_features": img, "labels": class_ids[labels], "filepath": paths}
+    feats = so.transform_extracted_fea(raw)
+    dd, frac, avg = so.remove_near_duplicates2(feats)
+    ref = meta["near_dup"]
+    np.testing.assert_allclose(frac, ref["fractions"], atol=1e-12)
+    assert abs(avg - ref["avg"]) < 1e-12 and max(frac) > 0
+    row = {p: i for i, p in enumerate(paths)}
+    assert {k: sorted(row[p] for p in v) for k, v in dd.items() if v} == ref["dict"]
