@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <numeric>
 #include <vector>
 
 #include "../../include/swat_b200.h"
@@ -83,6 +84,7 @@ struct swat_ctx {
   int64_t list_entries = 0;   // total survivor-list entries, 0 = auto
   int overfetch = 0;          // 0 = auto
   int64_t host_chunk_rows = 1 << 18;
+  bool unit_plan = true;            // several Q blocks: balanced (Q block x tile range) units over several launches
   int64_t bootstrap_rows = 32768;   // dense prefix used to seed thresholds of a fresh job (0 = off)
   // stats
   int64_t launches = 0;
@@ -205,7 +207,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
   job->last_stream = stream;
   if (engine == SWAT_ENGINE_TC) {
     if (q->n_stages <= 0) return fail(SWAT_ERR_UNSUPPORTED, "query block does not fit in shared memory for the tcgen05 engine");
-    TcArgs p;
+    TcArgs p{};
     p.n_qb = q->n_qb;
     p.n_blk = q->n_blk;
     p.n_stages = q->n_stages;
@@ -249,7 +251,25 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     CUtensorMap tm_bank;
     SW_OK(encode_2d_bf16(ctx, &tm_bank, bank, static_cast<uint64_t>(a.n_rows), 128));
     p.s = a;
-    CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
+    // Several Q blocks rarely divide the CTA pairs evenly (74 pairs: 4 blocks leave 2 idle, 16 leave 10, 21 leave 11) and
+    // blocks served by different numbers of pairs drift apart, so the bank is re-read from HBM per block.  The unit
+    // plan cuts the work into lcm(n_qb, pairs) equal (Q block x tile range) units, `pairs` per launch.
+    const int pairs = grid / q->ctas;
+    const int64_t tiles = (a.n_rows + 128 * q->ctas - 1) / (128 * q->ctas);
+    int launches = 1;
+    if (ctx->unit_plan && dense_out == nullptr && q->n_qb > 1 && pairs % q->n_qb != 0) {
+      const int g = std::gcd(q->n_qb, pairs);
+      const int per_pair = q->n_qb / g, ranges = pairs / g;        // units per pair, tile ranges
+      if (per_pair <= 64 && tiles >= 16ll * ranges) {              // units of >= 16 tiles, else one launch does
+        launches = per_pair;
+        p.n_ranges = ranges;
+      }
+    }
+    for (int i = 0; i < launches; ++i) {
+      p.unit_base = i * pairs;
+      CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
+    }
+    ctx->launches += launches - 1;
   } else {
     const void* qp = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_qp_bf16) : static_cast<const void*>(q->d_qp_f32);
     CU_OK(launch_scan_simt(a, d_bank, d_t2i_bank, qp, dtype, q->reduce, d_row_class != nullptr, dense_out != nullptr, stream));
@@ -763,6 +783,7 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   else if (n == "list_entries") ctx->list_entries = value;
   else if (n == "overfetch") ctx->overfetch = static_cast<int>(value);
   else if (n == "host_chunk_rows") ctx->host_chunk_rows = value;
+  else if (n == "unit_plan") ctx->unit_plan = value != 0;
   else if (n == "bootstrap_rows") ctx->bootstrap_rows = std::max<int64_t>(0, value);
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
   return SWAT_OK;

@@ -168,13 +168,26 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int pair_id = blockIdx.x / kCtas, n_pairs = gridDim.x / kCtas;
-  const int qb = pair_id % p.n_qb;
-  const int pair_in_qb = pair_id / p.n_qb;
-  const int pairs_qb = (n_pairs - qb + p.n_qb - 1) / p.n_qb;
+  // Work decomposition.  Legacy (n_ranges == 0): Q block = pair % n_qb, tiles strided by the pairs of that block.
+  // Unit plan (n_ranges > 0, several launches): unit u = unit_base + pair covers Q block u % n_qb and the tiles
+  // r, r + R, r + 2R, ... of range r = u / n_qb.  The n_qb pairs of one range run in the same launch and walk the
+  // same tiles in step (one HBM read, the rest L2 hits), and every pair gets the same number of equal units.
+  const int unit = p.unit_base + pair_id;
+  const int qb = unit % p.n_qb;
+  const int pair_in_qb = (p.n_ranges > 0) ? unit / p.n_qb : pair_id / p.n_qb;
+  const int pairs_qb = (p.n_ranges > 0) ? p.n_ranges : (n_pairs - qb + p.n_qb - 1) / p.n_qb;
   const int NB = p.n_blk, NBC = NB / kCtas;
   const uint32_t b_chunk_bytes = static_cast<uint32_t>(NBC) * 128u;
   constexpr int kTileRows = 128 * kCtas;
   const int64_t n_tiles = (p.s.n_rows + kTileRows - 1) / kTileRows;
+  const int64_t t_first = (pair_in_qb < pairs_qb) ? pair_in_qb : n_tiles;
+  // CTAs serving this Q block in this launch (the refresher warps split the block's classes among them)
+  int qb_peers = pairs_qb, qb_rank = pair_in_qb;
+  if (p.n_ranges > 0) {
+    const int first_u = p.unit_base + ((qb - p.unit_base) % p.n_qb + p.n_qb) % p.n_qb;
+    qb_peers = (p.unit_base + n_pairs - 1 - first_u) / p.n_qb + 1;
+    qb_rank = (unit - first_u) / p.n_qb;
+  }
 
   uint8_t* sB = smem;
   uint8_t* sA = smem + p.smem_b_bytes;
@@ -237,7 +250,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
                            0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
       uint32_t stage = 0, phase = 0;
-      for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb) {
+      for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
         const int row0 = static_cast<int>(t * kTileRows + rank * 128);
         for (int kc = 0; kc < 8; ++kc) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -255,7 +268,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       mbar_wait(smem_u32(q_bar), 0);
       tc_fence_after();
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
+      for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++it) {
         const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
         mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1u);
         tc_fence_after();
@@ -281,7 +294,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     // histogram read off the epilogue warps.
     if (!DENSE) {
       const int c_lo = p.blk_class[qb], c_hi = p.blk_class[qb + 1];
-      const int n_ctas_qb = pairs_qb * kCtas, my_idx = pair_in_qb * kCtas + static_cast<int>(rank);
+      const int n_ctas_qb = qb_peers * kCtas, my_idx = qb_rank * kCtas + static_cast<int>(rank);
       volatile uint32_t* done = s_done;
       const uint64_t t_start = globaltimer_ns();
       for (;;) {
@@ -312,7 +325,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     uint32_t tnext = 0;
     if (my_col_live) tnext = ld_cg_u32(my_tau_src);
     uint32_t it = 0;
-    for (int64_t t = pair_in_qb; t < n_tiles; t += pairs_qb, ++it) {
+    for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
       if (my_col_live) {
         s_tau[etid] = fast_tau<RED>(f32_dec(tnext), my_cnt);

@@ -13,6 +13,8 @@ struct TcArgs {
   int32_t n_stages;       // bank-tile ring depth
   uint32_t smem_b_bytes;  // per-CTA bytes of the resident query block
   uint64_t bank_hint;     // L2 cache policy for bank tiles
+  int32_t unit_base;      // unit plan: first unit of this launch (unit = unit_base + pair)
+  int32_t n_ranges;       // unit plan: tile ranges R (0 = single launch, Q block = pair % n_qb)
   const int32_t* blk_class;  // [n_qb+1] first class of each Q block
   const int32_t* blk_split;  // [n_qb] grouped reduces: column (multiple of 32) where the second epilogue warp set starts
 };

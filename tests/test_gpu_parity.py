@@ -158,6 +158,36 @@ def test_topk_synonym_groups(lib, ctx, reduce):
     check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=reduce)
 
 
+@pytest.mark.parametrize("n_cls,syn", [(700, False), (230, True)])
+def test_unit_plan_many_query_blocks(lib, ctx, n_cls, syn):
+    """More queries than one resident block holds, block count not dividing the CTA pairs: the scan runs as
+    several launches of balanced (query block x tile range) units.  Must equal the oracle and, bit for bit,
+    the single-launch schedule."""
+    from swat_b200 import synth
+    sizes = [1 + (i * 5) % 7 for i in range(n_cls)] if syn else 1          # 230 classes -> ~900 queries
+    qc, queries, coq = synth.make_queries(n_cls, sizes, seed=21, dtype=torch.bfloat16)
+    cap, _, _ = synth.make_bank(360_000, qc, seed=21, dtype=torch.bfloat16, rho=0.3, tie_block=300, chunk=1 << 16, with_images=False)
+    capf, qf = cap.float().numpy(), queries.float().numpy()
+    red = "max" if syn else "none"
+    coq_np = coq.numpy()
+    qs = lib.Queries(ctx, queries.float(), coq, n_cls, red)
+    capd = cap.cuda()
+    l0 = ctx.launch_count
+    g = lib.topk(ctx, qs, capd, 100, 0.0)
+    n_launch = ctx.launch_count - l0
+    ctx.set_option("unit_plan", 0)
+    try:
+        l0 = ctx.launch_count
+        h = lib.topk(ctx, qs, capd, 100, 0.0)
+        assert ctx.launch_count - l0 < n_launch, "unit plan did not engage"
+    finally:
+        ctx.set_option("unit_plan", 1)
+    assert torch.equal(g[1], h[1]) and torch.equal(g[0], h[0]) and torch.equal(g[3], h[3])
+    S = so.score_matrix(capf, qf, coq_np, n_cls, red)
+    o = so.topk_walk(capf, qf, 100, 0.0, class_of_query=coq_np, n_classes=n_cls, reduce=red)
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what="unit plan")
+
+
 def test_exclusion_bitmap_and_threshold(lib, ctx2):
     bank = _rand_unit(5000, 11, torch.bfloat16)
     q = _rand_unit(12, 12, torch.bfloat16)

@@ -16,6 +16,10 @@ def timeit(fn, reps=4):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ts.sort(); return ts[len(ts) // 2]
 print(f"N={N} rows; roof = min(HBM {hbm/1e9:.0f} GB/s / 1KB, {tf/1e12:.0f} TF / (1024 Q))")
+md = [f"# Query-count sweep (BASELINE config 5 shape): {N:,} x 512 bf16 rows resident on 1 x B200, C = Q, top-500 selecting scan", "",
+      f"Roofline = slower of 1 KB/row at {hbm/1e9:.0f} GB/s (measured copy bandwidth; a read-only stream can exceed it) and "
+      f"Q x 1024 flop/row at {tf/1e12:.1f} TF/s (measured sustained bf16).  CUDA events, median of 4.", "",
+      "| Q | scan ms | G rows/s | roof G rows/s | frac | bound |", "|---:|---:|---:|---:|---:|---|"]
 for Q in (16, 64, 128, 200, 256, 400, 512, 1000, 1024, 2048, 4096, 8192):
     _, queries, _ = synth.make_queries(Q, 1, seed=1, dtype=torch.bfloat16)
     qs = _lib.Queries(ctx, queries.float())
@@ -23,6 +27,7 @@ for Q in (16, 64, 128, 200, 256, 400, 512, 1000, 1024, 2048, 4096, 8192):
     ms = timeit(lambda: (job.reset(), job.scan(cap)))
     roof = min(hbm / 1024, tf / (1024.0 * Q))
     print(f"Q={Q:5d}: scan {ms:8.3f} ms  {N/ms/1e6:7.3f} G rows/s  roof {roof/1e9:6.3f} G rows/s  frac {N/ms*1e3/roof:5.3f}  overflow={job.overflowed()}", flush=True)
+    md.append(f"| {Q} | {ms:.3f} | {N/ms/1e6:.3f} | {roof/1e9:.3f} | {N/ms*1e3/roof:.3f} | {'hbm' if hbm/1024 <= tf/(1024.0*Q) else 'tensor'} |")
     job.close(); qs.close()
 # imagenet-like synonym groups: C=1000 classes, 5191 queries, MAX reduce
 sizes = [1 + (i * 37) % 10 for i in range(1000)]
@@ -32,6 +37,9 @@ qs = _lib.Queries(ctx, queries.float(), coq, 1000, "max")
 job = _lib.Job(ctx, qs, 500, 0.0)
 ms = timeit(lambda: (job.reset(), job.scan(cap)), reps=3)
 Q = queries.shape[0]; roof = min(hbm / 1024, tf / (1024.0 * Q))
+md.append(f"| {Q} (C=1000, MAX over synonym groups) | {ms:.3f} | {N/ms/1e6:.3f} | {roof/1e9:.3f} | {N/ms*1e3/roof:.3f} | tensor |")
+__import__("os").makedirs("gpurun_out", exist_ok=True)
+open("gpurun_out/qsweep.md", "w").write("\n".join(md) + "\n")
 print(f"imagenet-like C=1000 Q={Q} MAX: scan {ms:.3f} ms {N/ms/1e6:.3f} G rows/s roof {roof/1e9:.3f} frac {N/ms*1e3/roof:.3f} overflow={job.overflowed()}")
 job.close(); qs.close()
 # config 1: 1M x 512 fp32, C=200, exact fp32 kernel
