@@ -35,7 +35,6 @@ struct SlowCtx {
   uint32_t* list_count;       // ATOMIC_LIST only: slot counter of that list
   uint32_t* hist;             // [C * kHistBins]
   uint32_t* flags;
-  const uint32_t* exclude;    // nullable
   uint32_t list_cap;
   uint32_t row_base;
   float hist_lo, hist_scale;
@@ -46,7 +45,6 @@ __device__ __forceinline__ SlowCtx make_slow_ctx(const ScanArgs& a, uint32_t lis
   s.list_count = a.st.list_count + list_id;
   s.hist = a.st.hist;
   s.flags = a.st.flags;
-  s.exclude = a.exclude;
   s.list_cap = a.st.list_cap;
   s.row_base = a.row_base;
   s.hist_lo = a.st.hist_lo;
@@ -94,36 +92,67 @@ static __device__ __noinline__ void refresh_tau(const JobState& st, int cls) {
   }
 }
 
-// Slow path: at least one lane of the warp passed the fast predicate for class `cls`.
+// Row-level part of the accept predicate (exclusion bitmap: near-duplicates, rows already taken by an earlier
+// sampler, sample_retrieval.py:452-462).  It does not depend on the column, so it is folded into row_valid once
+// per row instead of being tested per survivor.
+__device__ __forceinline__ bool row_excluded(const uint32_t* exclude, uint32_t row) {
+  return exclude != nullptr && ((exclude[row >> 5] >> (row & 31)) & 1u) != 0u;
+}
+
+// v[j] for a run-time j without spilling the register array: a jump table of 32 moves.
+template <int NC> __device__ __forceinline__ float pick_column(const float (&v)[NC], int j) {
+  static_assert(NC == 32, "chunks are 32 columns wide");
+  float r = 0.0f;
+  switch (j) {
+#define SWAT_PICK(k) case k: r = v[k]; break;
+    SWAT_PICK(0) SWAT_PICK(1) SWAT_PICK(2) SWAT_PICK(3) SWAT_PICK(4) SWAT_PICK(5) SWAT_PICK(6) SWAT_PICK(7)
+    SWAT_PICK(8) SWAT_PICK(9) SWAT_PICK(10) SWAT_PICK(11) SWAT_PICK(12) SWAT_PICK(13) SWAT_PICK(14) SWAT_PICK(15)
+    SWAT_PICK(16) SWAT_PICK(17) SWAT_PICK(18) SWAT_PICK(19) SWAT_PICK(20) SWAT_PICK(21) SWAT_PICK(22) SWAT_PICK(23)
+    SWAT_PICK(24) SWAT_PICK(25) SWAT_PICK(26) SWAT_PICK(27) SWAT_PICK(28) SWAT_PICK(29) SWAT_PICK(30) SWAT_PICK(31)
+#undef SWAT_PICK
+  }
+  return r;
+}
+
+// Slow path.  mask bit j: this lane's row passed the fast predicate at column col0 + j (v[j] holds the class value).
+// With ~k'(1 + ln(N/n0)) survivors per class a 32 x 32 chunk holds one with probability 0.3-0.5 at the benchmark
+// sizes, so this runs for every second or third chunk and has to be short: no per-column branches, no call.  Each
+// round appends the lowest remaining survivor of EVERY lane (lane-parallel; one round in the usual case): slots
+// from a ballot, a 16-byte store into the warp's list, a fire-and-forget histogram RED.
 // ATOMIC_LIST: lists are shared between warps (SIMT kernel) and slots are reserved with an atomic;
 // otherwise the list is private to this warp and the position lives in a register.
-// Returns the number of entries appended.
-template <bool ATOMIC_LIST>
-static __device__ __noinline__ uint32_t slow_append(const SlowCtx sc, uint32_t list_pos, int cls, float val, bool pass, uint32_t row) {
-  if (pass && sc.exclude != nullptr) pass = ((sc.exclude[row >> 5] >> (row & 31)) & 1u) == 0u;
-  const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-  if (ballot == 0) return 0;
-  const int lane = threadIdx.x & 31;
-  const uint32_t n = __popc(ballot);
-  if (ATOMIC_LIST) {
-    if (lane == 0) list_pos = atomicAdd(sc.list_count, n);
-    list_pos = __shfl_sync(0xffffffffu, list_pos, 0);
-  }
-  if (pass) {
-    const float s = val + 0.0f;  // -0.0 -> +0.0: Python compares them equal, the key must too
-    const uint32_t slot = list_pos + __popc(ballot & ((1u << lane) - 1u));
-    if (slot < sc.list_cap) {
-      const uint64_t key = make_key(s, sc.row_base + row);
-      sc.list_base[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(cls), 0u);
+template <int NC, int RED, bool ATOMIC_LIST>
+__device__ __forceinline__ void drain_survivors(const SlowCtx& sc, EpiCtx& cx, const float (&v)[NC], uint32_t mask, int col0) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t ballot = __ballot_sync(0xffffffffu, mask != 0u);
+  while (ballot != 0u) {
+    const uint32_t n = __popc(ballot);
+    uint32_t base = cx.list_pos;
+    if (ATOMIC_LIST) {
+      if (lane == 0) base = atomicAdd(sc.list_count, n);
+      base = __shfl_sync(0xffffffffu, base, 0);
     } else {
-      atomicOr(sc.flags, 2u);
+      cx.list_pos += n;
     }
-    int b = static_cast<int>((s - sc.hist_lo) * sc.hist_scale);
-    b = b < 0 ? 0 : (b > kHistBins - 1 ? kHistBins - 1 : b);
-    // fire-and-forget reduction (no return value, nothing waits on it)
-    asm volatile("red.global.add.u32 [%0], 1;" :: "l"(sc.hist + static_cast<size_t>(cls) * kHistBins + b) : "memory");
+    if (mask != 0u) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const int cls = cx.cls_col[col0 + j];
+      const float s = red_fin<RED>(pick_column<NC>(v, j), cx.cnt_col[col0 + j]) + 0.0f;   // -0.0 -> +0.0: Python compares them equal, the key must too
+      const uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
+      if (slot < sc.list_cap) {
+        const uint64_t key = make_key(s, sc.row_base + cx.row);
+        sc.list_base[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(cls), 0u);
+      } else {
+        atomicOr(sc.flags, 2u);
+      }
+      int b = static_cast<int>((s - sc.hist_lo) * sc.hist_scale);
+      b = b < 0 ? 0 : (b > kHistBins - 1 ? kHistBins - 1 : b);
+      // fire-and-forget reduction (no return value, nothing waits on it)
+      asm volatile("red.global.add.u32 [%0], 1;" :: "l"(sc.hist + static_cast<size_t>(cls) * kHistBins + b) : "memory");
+    }
+    ballot = __ballot_sync(0xffffffffu, mask != 0u);
   }
-  return n;
 }
 
 // Threshold the fast path compares the *accumulated* value of a class against.  For MEAN the
@@ -185,14 +214,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& 
       }
     }
     const uint32_t mask = cx.row_valid ? ~__brev(fail) : 0u;
-    if (__any_sync(0xffffffffu, mask != 0u)) {
-      const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        if ((any >> j) & 1u)   // warp-uniform
-          cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], red_fin<RED>(v[j], cnt[j]), (mask >> j) & 1u, cx.row);
-      }
-    }
+    drain_survivors<NC, RED, ATOMIC_LIST>(sc, cx, v, mask, col0);
     return;
   }
   uint32_t mask = 0;
@@ -214,14 +236,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& 
     if (PART) p = p && (cx.my_cls == cls[j]);
     mask |= static_cast<uint32_t>(p) << j;
   }
-  if (__any_sync(0xffffffffu, mask != 0u)) {
-    const uint32_t any = __reduce_or_sync(0xffffffffu, mask);
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      if ((any >> j) & 1u)   // warp-uniform
-        cx.list_pos += slow_append<ATOMIC_LIST>(sc, cx.list_pos, cls[j], red_fin<RED>(v[j], cnt[j]), (mask >> j) & 1u, cx.row);
-    }
-  }
+  drain_survivors<NC, RED, ATOMIC_LIST>(sc, cx, v, mask, col0);
 }
 
 }  // namespace swat

@@ -41,7 +41,7 @@ scan_simt_kernel(const ScanArgs a, const T* __restrict__ bank, const T* __restri
   cx.cls_col = s_cls;
   cx.cnt_col = s_cnt;
   cx.row = static_cast<uint32_t>(row);
-  cx.row_valid = row < a.n_rows;
+  cx.row_valid = row < a.n_rows && !row_excluded(a.exclude, static_cast<uint32_t>(row));
   cx.my_cls = -1;
   if (PART && cx.row_valid) cx.my_cls = a.row_class[row];
   cx.acc = red_init<RED>();

@@ -3,7 +3,7 @@
 // One persistent CTA (cta_group::1) or CTA pair (cta_group::2, 256 bank rows per MMA) per SM.
 //   warp 0   TMA producer : query block once (resident for the whole kernel), then the bank, each
 //                           byte exactly once per Q block, 128 rows x 64 k (16 KB, SWIZZLE_128B) per stage
-//   warp 1   MMA issuer   : one thread, tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM),
+//   warp 1   MMA issuer   : converged warp, one elected lane issues tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM),
 //                           M = 128*ctas, N = padded query columns (<=256), K = 16 per instruction
 //   warp 2   TMEM allocator (512 columns = two accumulator buffers of <=256 columns)
 //   warp 3   threshold refresher: class thresholds from the score histograms, off the critical path
@@ -27,6 +27,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0)); return r;
+}
+// one lane of the (converged) warp; always the same one, so tcgen05.commit tracks the MMAs it issued
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -242,49 +248,66 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
 
   if (warp == 0) {
     // ================================================================== TMA producer
-    if (lane == 0) {
+    // The whole warp walks the ring (converged, so addresses stay in uniform registers); one elected lane issues.
+    {
       const uint32_t q_bar_a = smem_u32(q_bar);
       const uint32_t q_bar_lead = (kCtas == 2) ? mapa_rank0(q_bar_a) : q_bar_a;
-      if (rank == 0) mbar_arrive_expect_tx(q_bar_a, 8u * b_chunk_bytes * kCtas);
-      for (int kc = 0; kc < 8; ++kc)
-        tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
-                           0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(q_bar_a, 8u * b_chunk_bytes * kCtas);
+        for (int kc = 0; kc < 8; ++kc)
+          tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
+                             0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
+      }
+      const uint32_t sA_a = smem_u32(sA), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+      const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
       uint32_t stage = 0, phase = 0;
       for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
         const int row0 = static_cast<int>(t * kTileRows + rank * 128);
+#pragma unroll 1
         for (int kc = 0; kc < 8; ++kc) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          if (rank == 0) mbar_arrive_expect_tx(fb, static_cast<uint32_t>(kStageBytes) * kCtas);
-          tma_load_2d<kCtas>(smem_u32(sA + stage * kStageBytes), &tm_bank, (kCtas == 2) ? mapa_rank0(fb) : fb, kc * 64, row0, p.bank_hint);
+          mbar_wait(empty_a + stage * 8u, phase ^ 1u);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(full_a + stage * 8u, static_cast<uint32_t>(kStageBytes) * kCtas);
+            tma_load_2d<kCtas>(sA_a + stage * kStageBytes, &tm_bank, full_lead + stage * 8u, kc * 64, row0, p.bank_hint);
+          }
           if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (leader CTA)
-    if (rank == 0 && lane == 0) {
+    // Converged warp, one elected lane issues: a loop run by a single divergent lane makes the compiler wrap every
+    // tcgen05 instruction in an elect/broadcast loop (~150 instructions per stage), and the issue thread, not the
+    // tensor pipe, then bounds the tile period.
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(128 * kCtas, NB);
       mbar_wait(smem_u32(q_bar), 0);
       tc_fence_after();
+      const uint64_t a_base = make_smem_desc(smem_u32(sA)), b_base = make_smem_desc(smem_u32(sB));
+      const uint32_t a_step = static_cast<uint32_t>(kStageBytes) >> 4, b_step = b_chunk_bytes >> 4;   // start-address field units
+      const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+      const uint32_t tfull_a = smem_u32(tfull_bar), tempty_a = smem_u32(tempty_bar);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++it) {
         const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
-        mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1u);
+        mbar_wait(tempty_a + buf * 8u, bphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256u;
+#pragma unroll 1
         for (int kc = 0; kc < 8; ++kc) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          mbar_wait(full_a + stage * 8u, phase);
           tc_fence_after();
-          const uint64_t a0 = make_smem_desc(smem_u32(sA + stage * kStageBytes));
-          const uint64_t b0 = make_smem_desc(smem_u32(sB + kc * b_chunk_bytes));
+          if (elect_one()) {
+            const uint64_t a0 = a_base + stage * a_step;
+            const uint64_t b0 = b_base + static_cast<uint32_t>(kc) * b_step;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 64-wide K chunk = 4 x UMMA_K(16); +32 B inside the swizzle atom
-            umma_bf16<kCtas>(d_tmem, a0 + 2u * k, b0 + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
-          umma_commit<kCtas>(smem_u32(&empty_bar[stage]));
+            for (int k = 0; k < 4; ++k)   // 64-wide K chunk = 4 x UMMA_K(16); +32 B inside the swizzle atom
+              umma_bf16<kCtas>(d_tmem, a0 + 2u * k, b0 + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_commit<kCtas>(empty_a + stage * 8u);
+          }
           if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
         }
-        umma_commit<kCtas>(smem_u32(&tfull_bar[buf]));
+        if (elect_one()) umma_commit<kCtas>(tfull_a + buf * 8u);
       }
     }
   } else if (warp == 3) {
@@ -333,7 +356,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       }
       const int64_t row = t * kTileRows + rank * 128 + quad * 32 + lane;
       cx.row = static_cast<uint32_t>(row);
-      cx.row_valid = row < p.s.n_rows;
+      cx.row_valid = row < p.s.n_rows && !row_excluded(p.s.exclude, static_cast<uint32_t>(row));
       cx.my_cls = -1;
       if (PART && cx.row_valid) cx.my_cls = p.s.row_class[row];
       cx.acc = red_init<RED>();
