@@ -8,6 +8,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_tc -s 8 -c 2 -f -o gpurun_out/r01_scan_tc \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
 # Q = 1000 (imagenet shape, 4 Q blocks): does the bank still stream from HBM once?
-timeout 900 ncu --set full --clock-control none -k regex:scan_tc -s 8 -c 2 -f -o gpurun_out/r01_scan_tc_q1000 \
+timeout 900 ncu --set full --clock-control none -k regex:scan_tc -s 6 -c 3 -f -o gpurun_out/r01_scan_tc_q1000 \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --classes 1000 --t2t-only > gpurun_out/ncu_q1000.log 2>&1; echo "ncu q1000 exit $?"
 tail -c 700 gpurun_out/bench_r01.json
