@@ -102,11 +102,14 @@ int32_t swat_job_set_class_depth(swat_job* job, const int32_t* h_depth, void* st
 int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base,
                       const void* d_t2i_bank, float t2i_threshold, const int32_t* d_row_class,
                       const uint32_t* d_exclude, int32_t engine, void* stream);
-/* Sorted top-k_fetch of every class: d_scores [C,k_fetch] f32, d_rows [C,k_fetch] i64 (shard-local
- * row ids as passed via row_base, -1 padded), d_counts [C] i32, d_truncated [C] i32 (nullable;
- * 1 = more than k_fetch rows were eligible, i.e. the list is a strict prefix of the walk). */
-int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t* d_counts,
+/* Sorted top-k_fetch of every class: d_scores [C,k_fetch] f32, d_rows [C,k_fetch] i64 (row_offset +
+ * the shard-local row id passed via row_base; -1 padded), d_counts [C] i32, d_truncated [C] i32
+ * (nullable; 1 = more than k_fetch rows were eligible, i.e. the list is a strict prefix of the walk). */
+int32_t swat_job_select(swat_job* job, int64_t row_offset, float* d_scores, int64_t* d_rows, int32_t* d_counts,
                         int32_t* d_truncated, void* stream);
+/* Asynchronously copies the job's overflow word (see swat_job_status) to *d_flags on `stream`, so a
+ * multi-GPU caller can ship it with the candidates instead of synchronising before the exchange. */
+int32_t swat_job_export_flags(swat_job* job, int32_t* d_flags, void* stream);
 /* Synchronises the stream the job last ran on; *overflowed != 0 means the results are invalid:
  * bit0 = a class candidate buffer overflowed (raise "cand_cap"), bit1 = a survivor list overflowed
  * (raise "list_entries").  swat_topk / swat_topk_host retry by themselves. */
@@ -128,13 +131,16 @@ int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_ba
 
 /* ---- multi-GPU: merge after the single NCCL gather ------------------------------ */
 /* d_scores/d_rows/d_aux: [G,C,k_in] gathered shard candidate lists (rows already global, < 2^32),
- * d_counts [G,C], d_truncated [G,C] (nullable).  Keeps, per class, the k_out best entries under
+ * d_counts [G,C], d_truncated [G,C] (nullable).  shard_stride_bytes == 0: the arrays are contiguous;
+ * otherwise shard g of EVERY array starts g * shard_stride_bytes after shard 0 (the arrays are slices
+ * of one packed per-rank buffer, as an all-gather delivers them).  Keeps, per class, the k_out best entries under
  * (score desc, row asc) among those with aux >= aux_threshold (d_aux == NULL: no predicate) -- the
  * reference's accept walk (:507-527) run over the union of the shards' candidates.
  * d_incomplete [C] (nullable): 1 = the result reaches below the last candidate of a truncated shard
  * (rows that shard never reported could belong in it): re-run the shards with a larger k_in. */
 int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux,
-                        const int32_t* d_counts, const int32_t* d_truncated, int32_t n_shards, int32_t n_classes,
+                        const int32_t* d_counts, const int32_t* d_truncated, int32_t n_shards,
+                        int64_t shard_stride_bytes, int32_t n_classes,
                         int32_t k_in, int32_t k_out, float aux_threshold, float* d_out_scores, int64_t* d_out_rows,
                         float* d_out_aux, int32_t* d_out_counts, int32_t* d_incomplete, void* stream);
 

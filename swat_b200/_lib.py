@@ -23,7 +23,7 @@ DIM = 512
 EXPORTS = [
     "swat_version", "swat_last_error", "swat_ctx_create", "swat_ctx_destroy", "swat_ctx_set_option",
     "swat_ctx_launch_count", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
-    "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
+    "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_export_flags", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
     "swat_scores_dense", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
 ]
 
@@ -62,11 +62,12 @@ def load() -> C.CDLL:
         "swat_job_reset": [vp, vp],
         "swat_job_set_class_depth": [vp, vp, vp],
         "swat_job_scan": [vp, vp, i32, i64, i64, vp, f32, vp, vp, i32, vp],
-        "swat_job_select": [vp, vp, vp, vp, vp, vp],
+        "swat_job_select": [vp, i64, vp, vp, vp, vp, vp],
+        "swat_job_export_flags": [vp, vp, vp],
         "swat_job_status": [vp, C.POINTER(i32)],
         "swat_job_destroy": [vp],
         "swat_t2i_walk": [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
-        "swat_merge_topk": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp],
+        "swat_merge_topk": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_scores_dense": [vp, vp, vp, i32, i64, vp, i32, vp],
         "swat_near_duplicates": [vp, vp, i32, i64, vp, vp, i32, i32, f32, vp, vp],
         "swat_topk": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
@@ -233,15 +234,28 @@ class Job:
                                     float(t2i_threshold), _ptr(row_class), _ptr(exclude), ENGINE[engine],
                                     _stream(self.ctx.device)))
 
-    def select(self):
+    def select(self, row_offset: int = 0, out=None):
+        """Sorted top-k_fetch per class; ``out = (scores, rows, counts, trunc)`` writes into caller tensors
+        (e.g. slices of a packed exchange buffer)."""
         dev = torch.device("cuda", self.ctx.device)
         Cn, kf = self.queries.n_classes, self.k_fetch
-        scores = torch.empty(Cn, kf, dtype=torch.float32, device=dev)
-        rows = torch.empty(Cn, kf, dtype=torch.int64, device=dev)
-        counts = torch.empty(Cn, dtype=torch.int32, device=dev)
-        trunc = torch.empty(Cn, dtype=torch.int32, device=dev)
-        _check(load().swat_job_select(self._h, _ptr(scores), _ptr(rows), _ptr(counts), _ptr(trunc), _stream(self.ctx.device)))
+        if out is None:
+            scores = torch.empty(Cn, kf, dtype=torch.float32, device=dev)
+            rows = torch.empty(Cn, kf, dtype=torch.int64, device=dev)
+            counts = torch.empty(Cn, dtype=torch.int32, device=dev)
+            trunc = torch.empty(Cn, dtype=torch.int32, device=dev)
+        else:
+            scores, rows, counts, trunc = out
+            _out_ok(scores, (Cn, kf), torch.float32); _out_ok(rows, (Cn, kf), torch.int64)
+            _out_ok(counts, (Cn,), torch.int32); _out_ok(trunc, (Cn,), torch.int32)
+        _check(load().swat_job_select(self._h, int(row_offset), _ptr(scores), _ptr(rows), _ptr(counts), _ptr(trunc),
+                                      _stream(self.ctx.device)))
         return scores, rows, counts, trunc
+
+    def export_flags(self, out: torch.Tensor):
+        """Stream-ordered copy of the overflow word into ``out`` (one int32 on the device): no host sync."""
+        _out_ok(out, (1,), torch.int32)
+        _check(load().swat_job_export_flags(self._h, _ptr(out), _stream(self.ctx.device)))
 
     def overflowed(self) -> int:
         """0 = fine; bit0 = class candidate buffers ("cand_cap"), bit1 = survivor lists ("list_entries")."""
@@ -332,15 +346,26 @@ def topk_host(ctx: Context, queries: Queries, t2t_bank: torch.Tensor, k: int, t2
     return scores, rows, t2i, counts
 
 
+def _out_ok(t: torch.Tensor, shape, dtype):
+    if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError(f"output tensor must be a contiguous CUDA {dtype} tensor of shape {tuple(shape)}")
+
+
 def t2i_walk(ctx: Context, queries: Queries, img_bank: torch.Tensor, cand_scores, cand_rows, cand_counts, truncated, k: int,
-             t2i_threshold: float = 0.25, img_row_base: int = 0):
+             t2i_threshold: float = 0.25, img_row_base: int = 0, out=None):
+    """T2I re-score of the candidates + accept walk.  ``out = (scores, rows, t2i, counts)`` writes into caller tensors."""
     _bank_ok(img_bank, "img_bank", True)
     dev = img_bank.device
     Cn, kf = cand_scores.shape
-    o_s = torch.empty(Cn, k, dtype=torch.float32, device=dev)
-    o_r = torch.empty(Cn, k, dtype=torch.int64, device=dev)
-    o_t = torch.empty(Cn, k, dtype=torch.float32, device=dev)
-    o_c = torch.empty(Cn, dtype=torch.int32, device=dev)
+    if out is None:
+        o_s = torch.empty(Cn, k, dtype=torch.float32, device=dev)
+        o_r = torch.empty(Cn, k, dtype=torch.int64, device=dev)
+        o_t = torch.empty(Cn, k, dtype=torch.float32, device=dev)
+        o_c = torch.empty(Cn, dtype=torch.int32, device=dev)
+    else:
+        o_s, o_r, o_t, o_c = out
+        _out_ok(o_s, (Cn, k), torch.float32); _out_ok(o_r, (Cn, k), torch.int64)
+        _out_ok(o_t, (Cn, k), torch.float32); _out_ok(o_c, (Cn,), torch.int32)
     o_i = torch.empty(Cn, dtype=torch.int32, device=dev)
     _check(load().swat_t2i_walk(ctx._h, queries._h, _ptr(img_bank), _dtype_code(img_bank), int(img_bank.shape[0]), int(img_row_base),
                                 None, _ptr(cand_scores), _ptr(cand_rows), _ptr(cand_counts), _ptr(truncated), int(kf), int(k),
@@ -349,23 +374,33 @@ def t2i_walk(ctx: Context, queries: Queries, img_bank: torch.Tensor, cand_scores
 
 
 def merge_topk(ctx: Context, scores: torch.Tensor, rows: torch.Tensor, counts: torch.Tensor, aux: Optional[torch.Tensor] = None,
-               truncated: Optional[torch.Tensor] = None, k_out: Optional[int] = None, aux_threshold: float = float("-inf")):
+               truncated: Optional[torch.Tensor] = None, k_out: Optional[int] = None, aux_threshold: float = float("-inf"),
+               n_shards: Optional[int] = None, shard_stride_bytes: int = 0):
     """Merge gathered shard candidate lists ``[G,C,k_in]`` (rows global) into ``[C,k_out]``: the best
     ``k_out`` entries with ``aux >= aux_threshold``.  Returns ``(scores, rows, aux | None, counts,
     incomplete)``; ``incomplete[c] == 1`` means a truncated shard may hold rows that belong in the
-    result (re-run the shards with a larger ``k_in``)."""
-    G, Cn, k_in = scores.shape
+    result (re-run the shards with a larger ``k_in``).
+
+    With ``shard_stride_bytes > 0`` the arguments are shard 0's ``[C,k_in]`` / ``[C]`` slices of an
+    all-gathered packed buffer and shard g of every array lies ``g * shard_stride_bytes`` further on
+    (``n_shards`` then gives G); nothing is copied."""
+    if shard_stride_bytes:
+        if n_shards is None:
+            raise ValueError("n_shards is required with shard_stride_bytes")
+        G, (Cn, k_in) = int(n_shards), scores.shape
+    else:
+        G, Cn, k_in = scores.shape
+        scores, rows, counts = scores.contiguous(), rows.contiguous(), counts.contiguous()
+        aux = None if aux is None else aux.contiguous()
+        truncated = None if truncated is None else truncated.contiguous()
     k_out = int(k_in if k_out is None else k_out)
     dev = scores.device
-    scores, rows, counts = scores.contiguous(), rows.contiguous(), counts.contiguous()
-    aux = None if aux is None else aux.contiguous()
-    truncated = None if truncated is None else truncated.contiguous()
     o_s = torch.empty(Cn, k_out, dtype=torch.float32, device=dev)
     o_r = torch.empty(Cn, k_out, dtype=torch.int64, device=dev)
     o_a = torch.empty(Cn, k_out, dtype=torch.float32, device=dev) if aux is not None else None
     o_c = torch.empty(Cn, dtype=torch.int32, device=dev)
     o_i = torch.empty(Cn, dtype=torch.int32, device=dev)
-    _check(load().swat_merge_topk(ctx._h, _ptr(scores), _ptr(rows), _ptr(aux), _ptr(counts), _ptr(truncated), int(G), int(Cn),
-                                  int(k_in), k_out, float(aux_threshold), _ptr(o_s), _ptr(o_r), _ptr(o_a), _ptr(o_c), _ptr(o_i),
-                                  _stream(ctx.device)))
+    _check(load().swat_merge_topk(ctx._h, _ptr(scores), _ptr(rows), _ptr(aux), _ptr(counts), _ptr(truncated), int(G),
+                                  int(shard_stride_bytes), int(Cn), int(k_in), k_out, float(aux_threshold), _ptr(o_s), _ptr(o_r),
+                                  _ptr(o_a), _ptr(o_c), _ptr(o_i), _stream(ctx.device)))
     return o_s, o_r, o_a, o_c, o_i

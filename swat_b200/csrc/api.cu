@@ -961,13 +961,23 @@ int32_t swat_job_scan(swat_job* job, const void* d_bank, int32_t dtype, int64_t 
                    static_cast<cudaStream_t>(stream));
 }
 
-int32_t swat_job_select(swat_job* job, float* d_scores, int64_t* d_rows, int32_t* d_counts, int32_t* d_truncated, void* stream) {
+int32_t swat_job_select(swat_job* job, int64_t row_offset, float* d_scores, int64_t* d_rows, int32_t* d_counts, int32_t* d_truncated,
+                        void* stream) {
   if (!job || !d_scores || !d_rows || !d_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  if (row_offset < 0) return fail(SWAT_ERR_INVALID, "row_offset must be >= 0");
   (void)cudaGetLastError();
   CU_OK(cudaSetDevice(job->ctx->device));
-  CU_OK(launch_select(job->st, job->q->C, 0, d_scores, d_rows, d_counts, d_truncated, static_cast<cudaStream_t>(stream)));
+  CU_OK(launch_select(job->st, job->q->C, row_offset, d_scores, d_rows, d_counts, d_truncated, static_cast<cudaStream_t>(stream)));
   job->last_stream = static_cast<cudaStream_t>(stream);
   job->ctx->launches += kSelectLaunches;
+  return SWAT_OK;
+}
+
+int32_t swat_job_export_flags(swat_job* job, int32_t* d_flags, void* stream) {
+  if (!job || !d_flags) return fail(SWAT_ERR_INVALID, "null argument");
+  (void)cudaGetLastError();
+  CU_OK(cudaSetDevice(job->ctx->device));
+  CU_OK(cudaMemcpyAsync(d_flags, job->st.flags, sizeof(int32_t), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return SWAT_OK;
 }
 
@@ -1016,16 +1026,17 @@ int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_ba
 }
 
 int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
-                        const int32_t* d_truncated, int32_t n_shards, int32_t n_classes, int32_t k_in, int32_t k_out,
-                        float aux_threshold, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux, int32_t* d_out_counts,
-                        int32_t* d_incomplete, void* stream) {
+                        const int32_t* d_truncated, int32_t n_shards, int64_t shard_stride_bytes, int32_t n_classes, int32_t k_in,
+                        int32_t k_out, float aux_threshold, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
+                        int32_t* d_out_counts, int32_t* d_incomplete, void* stream) {
   if (!ctx || !d_scores || !d_rows || !d_counts || !d_out_scores || !d_out_rows || !d_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
+  if (shard_stride_bytes < 0 || (shard_stride_bytes & 7) != 0) return fail(SWAT_ERR_INVALID, "shard_stride_bytes must be a non-negative multiple of 8");
   if (n_shards < 1 || n_classes < 1 || k_in < 1 || k_out < 1 || k_out > kMaxKFetch)
     return fail(SWAT_ERR_INVALID, "bad merge shape G=%d C=%d k_in=%d k_out=%d", n_shards, n_classes, k_in, k_out);
   (void)cudaGetLastError();
   CU_OK(cudaSetDevice(ctx->device));
   SW_OK(ctx->w_keys.ensure(static_cast<size_t>(n_shards) * n_classes * k_in * 8));
-  CU_OK(launch_merge(d_scores, d_rows, d_aux, aux_threshold, d_counts, d_truncated, n_shards, n_classes, k_in, k_out,
+  CU_OK(launch_merge(d_scores, d_rows, d_aux, aux_threshold, d_counts, d_truncated, n_shards, shard_stride_bytes, n_classes, k_in, k_out,
                      ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows, d_out_aux, d_out_counts, d_incomplete,
                      static_cast<cudaStream_t>(stream)));
   ctx->launches += 2;

@@ -353,19 +353,37 @@ __global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) 
 }
 
 // ---------------------------------------------------------------------------------- shard merge
+// The gathered arrays are either contiguous ([G,C,k] / [G,C]) or slices of per-rank packed buffers laid end to
+// end by the all-gather: shard g of every array then starts g * stride bytes after shard 0.
+struct ShardView {
+  int64_t big_f32, big_i64, small;   // byte strides between shards for [C,k] f32, [C,k] i64 and [C] i32 arrays
+};
+__host__ __device__ inline ShardView make_shard_view(int64_t stride_bytes, int C, int k) {
+  ShardView v;
+  v.big_f32 = stride_bytes ? stride_bytes : static_cast<int64_t>(C) * k * 4;
+  v.big_i64 = stride_bytes ? stride_bytes : static_cast<int64_t>(C) * k * 8;
+  v.small = stride_bytes ? stride_bytes : static_cast<int64_t>(C) * 4;
+  return v;
+}
+template <typename T> __device__ __forceinline__ const T* shard_ptr(const T* base, int g, int64_t stride) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + static_cast<int64_t>(g) * stride);
+}
+
 // keys laid out [C][G*k]; absent entries and entries failing the aux (T2I) predicate get key 0,
 // which sorts below every real key
 __global__ void merge_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows,
                                   const float* __restrict__ aux, float aux_thr, const int32_t* __restrict__ counts,
-                                  int G, int C, int k, uint64_t* __restrict__ keys) {
+                                  int G, ShardView sv, int C, int k, uint64_t* __restrict__ keys) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(G) * C * k;
   if (i >= total) return;
   const int j = static_cast<int>(i % k);
   const int c = static_cast<int>((i / k) % C);
   const int g = static_cast<int>(i / (static_cast<size_t>(k) * C));
+  const size_t e = static_cast<size_t>(c) * k + j;
   uint64_t key = 0;
-  if (j < counts[g * C + c] && (aux == nullptr || aux[i] >= aux_thr)) key = make_key(scores[i] + 0.0f, static_cast<uint32_t>(rows[i]));
+  if (j < shard_ptr(counts, g, sv.small)[c] && (aux == nullptr || shard_ptr(aux, g, sv.big_f32)[e] >= aux_thr))
+    key = make_key(shard_ptr(scores, g, sv.big_f32)[e] + 0.0f, static_cast<uint32_t>(shard_ptr(rows, g, sv.big_i64)[e]));
   keys[(static_cast<size_t>(c) * G + g) * k + j] = key;
 }
 
@@ -375,7 +393,7 @@ __global__ void merge_keys_kernel(const float* __restrict__ scores, const int64_
 __global__ void __launch_bounds__(kSelThreads)
 merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores, const int64_t* __restrict__ rows,
              const float* __restrict__ aux, const int32_t* __restrict__ counts, const int32_t* __restrict__ truncated,
-             int G, int C, int k, int k_out, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+             int G, ShardView sv, int C, int k, int k_out, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
              float* __restrict__ out_aux, int32_t* __restrict__ out_counts, int32_t* __restrict__ incomplete) {
   __shared__ uint64_t s_keys[kSortCap];
   __shared__ uint32_t s_hist[256];
@@ -406,10 +424,10 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
       uint64_t frontier = 0;
       if (truncated) {
         for (int g = 0; g < G; ++g) {
-          const int m = counts[g * C + c];
-          if (truncated[g * C + c] && m > 0) {
-            const size_t last = (static_cast<size_t>(g) * C + c) * k + (m - 1);
-            const uint64_t fk = make_key(scores[last] + 0.0f, static_cast<uint32_t>(rows[last]));
+          const int m = shard_ptr(counts, g, sv.small)[c];
+          if (shard_ptr(truncated, g, sv.small)[c] && m > 0) {
+            const size_t last = static_cast<size_t>(c) * k + (m - 1);
+            const uint64_t fk = make_key(shard_ptr(scores, g, sv.big_f32)[last] + 0.0f, static_cast<uint32_t>(shard_ptr(rows, g, sv.big_i64)[last]));
             frontier = fk > frontier ? fk : frontier;
           }
         }
@@ -430,7 +448,7 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
       }
       if (lo < cnt && s_keys[lo] == key) {
         const int g = static_cast<int>(i / k), j = static_cast<int>(i % k);
-        out_aux[static_cast<size_t>(c) * k_out + lo] = aux[(static_cast<size_t>(g) * C + c) * k + j];
+        out_aux[static_cast<size_t>(c) * k_out + lo] = shard_ptr(aux, g, sv.big_f32)[static_cast<size_t>(c) * k + j];
       }
     }
   }
@@ -521,16 +539,17 @@ cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream) {
 }
 
 cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, float aux_thr,
-                         const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int n_classes, int k, int k_out,
-                         uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
+                         const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int64_t shard_stride_bytes, int n_classes,
+                         int k, int k_out, uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
                          int32_t* d_out_counts, int32_t* d_incomplete, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(n_shards) * n_classes * k;
   if (total == 0) return cudaSuccess;
+  const ShardView sv = make_shard_view(shard_stride_bytes, n_classes, k);
   merge_keys_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(d_scores, d_rows, d_aux, aux_thr, d_counts,
-                                                                                  n_shards, n_classes, k, d_key_scratch);
+                                                                                  n_shards, sv, n_classes, k, d_key_scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_scores, d_rows, d_aux, d_counts, d_truncated, n_shards,
+  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_scores, d_rows, d_aux, d_counts, d_truncated, n_shards, sv,
                                                       n_classes, k, k_out, d_out_scores, d_out_rows, d_out_aux, d_out_counts,
                                                       d_incomplete);
   return cudaGetLastError();

@@ -26,31 +26,90 @@ def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def packed_layout(n_classes: int, k: int, with_t2i: bool) -> dict:
+    """int32 offsets of one rank's exchange buffer: ``rows`` (int64, first so it stays 8-byte aligned), ``scores``,
+    ``t2i`` (optional), ``counts``, ``trunc``, one ``flags`` word (the job's overflow bits) and padding to an even
+    length, so that rank r's slice of the all-gathered buffer starts on an 8-byte boundary too."""
+    n = int(n_classes) * int(k)
+    lay = {"rows": 0, "scores": 2 * n}
+    o = 3 * n
+    lay["t2i"] = o if with_t2i else None
+    o += n if with_t2i else 0
+    lay["counts"] = o; o += n_classes
+    lay["trunc"] = o; o += n_classes
+    lay["flags"] = o; o += 1
+    lay["len"] = o + (o & 1)
+    lay["n_classes"], lay["k"] = int(n_classes), int(k)
+    return lay
+
+
+class PackedCandidates:
+    """One rank's exchange buffer with typed views into it: kernels write their outputs straight into the
+    views, the buffer goes into the all-gather as it is, and the merge reads the gathered buffer through a
+    per-shard stride -- no pack or unpack copies."""
+
+    def __init__(self, n_classes: int, k: int, with_t2i: bool, device, buf: Optional[torch.Tensor] = None):
+        self.lay = lay = packed_layout(n_classes, k, with_t2i)
+        n = n_classes * k
+        self.buf = torch.zeros(lay["len"], dtype=torch.int32, device=device) if buf is None else buf
+        b = self.buf
+        self.rows = b[0:2 * n].view(torch.int64).view(n_classes, k)
+        self.scores = b[lay["scores"]:lay["scores"] + n].view(torch.float32).view(n_classes, k)
+        self.t2i = b[lay["t2i"]:lay["t2i"] + n].view(torch.float32).view(n_classes, k) if with_t2i else None
+        self.counts = b[lay["counts"]:lay["counts"] + n_classes]
+        self.trunc = b[lay["trunc"]:lay["trunc"] + n_classes]
+        self.flags = b[lay["flags"]:lay["flags"] + 1]
+
+
+def _get_job(ctx, queries, k_fetch, t2t_threshold, cap, lists):
+    cache = ctx.__dict__.setdefault("_job_cache", {})
+    key = (id(queries), int(k_fetch), float(t2t_threshold), cap, lists)
+    job = cache.get(key)
+    if job is None:                       # job buffers (survivor lists: ~100s of MB) are reused across calls
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache))).close()
+        job = cache[key] = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
+    else:
+        job.reset()
+    return job
+
+
 def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_threshold: float = 0.0,
                      t2i_bank: Optional[torch.Tensor] = None, row_offset: int = 0,
                      row_class: Optional[torch.Tensor] = None, exclude: Optional[torch.Tensor] = None,
-                     class_depth: Optional[torch.Tensor] = None):
+                     class_depth: Optional[torch.Tensor] = None, packed: Optional[PackedCandidates] = None,
+                     check: bool = True):
     """This shard's T2T top-``k_fetch`` per class (global row ids) with the T2I score of every
-    candidate.  Returns ``(scores, rows, t2i | None, counts, truncated)`` on the device."""
+    candidate.  Returns ``(scores, rows, t2i | None, counts, truncated)`` on the device.
+
+    ``packed``: write the results into that exchange buffer.  ``check=False`` (with ``packed``): do not
+    synchronise to test the job's overflow bits; they are copied into ``packed.flags`` on the stream and
+    travel with the candidates, so every rank sees every rank's bits after the exchange."""
     dbg = os.environ.get("SWAT_DEBUG")
     cap, lists = None, None
-    cache = ctx.__dict__.setdefault("_job_cache", {})
+    Cn = queries.n_classes
     for _ in range(8):
-        key = (id(queries), int(k_fetch), float(t2t_threshold), cap, lists)
-        job = cache.get(key)
-        if job is None:                       # job buffers (survivor lists: ~100s of MB) are reused across calls
-            if len(cache) >= 4:
-                cache.pop(next(iter(cache))).close()
-            job = cache[key] = _lib.Job(ctx, queries, k_fetch, t2t_threshold)
-        else:
-            job.reset()
+        job = _get_job(ctx, queries, k_fetch, t2t_threshold, cap, lists)
         job.set_class_depth(class_depth)
         job.scan(t2t_bank, row_base=0, row_class=row_class, exclude=exclude)
-        scores, rows, counts, trunc = job.select()
+        if packed is None:
+            scores, rows, counts, trunc = job.select(row_offset)
+        elif t2i_bank is None:
+            scores, rows, counts, trunc = job.select(row_offset, out=(packed.scores, packed.rows, packed.counts, packed.trunc))
+        else:                             # the T2I stage writes scores/rows/counts; select only fills the truncated flags in place
+            dev = packed.buf.device
+            scores, rows, counts, trunc = job.select(row_offset, out=(
+                torch.empty(Cn, k_fetch, dtype=torch.float32, device=dev), torch.empty(Cn, k_fetch, dtype=torch.int64, device=dev),
+                torch.empty(Cn, dtype=torch.int32, device=dev), packed.trunc))
+        if packed is not None and not check:
+            job.export_flags(packed.flags)
+            break
         over = job.overflowed()
         if dbg:
             print(f"[swat dist] scan+select k_fetch={k_fetch} overflow={over}", flush=True)
         if not over:
+            if packed is not None:
+                packed.flags.zero_()
             break
         if over & 1:
             cap = (cap or (2 * k_fetch + 4096)) * 4
@@ -67,60 +126,76 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
     t2i = None
     if t2i_bank is not None:
         # threshold -inf and k == k_fetch: every candidate is kept in order, we only want its T2I score
+        out = None if packed is None else (packed.scores, packed.rows, packed.t2i, packed.counts)
         scores, rows, t2i, counts, _ = _lib.t2i_walk(ctx, queries, t2i_bank, scores, rows, counts, None, k_fetch,
-                                                     float("-inf"), img_row_base=0)
-    rows = torch.where(rows >= 0, rows + int(row_offset), rows)
+                                                     float("-inf"), img_row_base=row_offset, out=out)
     if dbg:
         torch.cuda.synchronize()
         print("[swat dist] local candidates ready", flush=True)
     return scores, rows, t2i, counts, trunc
 
 
-def pack(scores, rows, t2i, counts, trunc) -> torch.Tensor:
-    """One int32 buffer per rank so the exchange is a single collective."""
-    parts = [rows.contiguous().view(torch.int32).flatten(), scores.contiguous().view(torch.int32).flatten()]
+def pack(scores, rows, t2i, counts, trunc, flags: int = 0) -> torch.Tensor:
+    """One int32 buffer per rank (layout: ``packed_layout``) so the exchange is a single collective."""
+    Cn, k = scores.shape
+    p = PackedCandidates(Cn, k, t2i is not None, scores.device)
+    p.rows.copy_(rows); p.scores.copy_(scores)
     if t2i is not None:
-        parts.append(t2i.contiguous().view(torch.int32).flatten())
-    parts += [counts.to(torch.int32).flatten(), trunc.to(torch.int32).flatten()]
-    return torch.cat(parts)
+        p.t2i.copy_(t2i)
+    p.counts.copy_(counts.to(torch.int32)); p.trunc.copy_(trunc.to(torch.int32))
+    p.flags.fill_(int(flags))
+    return p.buf
 
 
 def unpack(buf: torch.Tensor, world: int, n_classes: int, k_fetch: int, with_t2i: bool):
+    """Dense ``[world, ...]`` copies of the gathered arrays (CPU tests, generic merge functions)."""
     buf = buf.view(world, -1)
-    n = n_classes * k_fetch
-    o = 0
-    rows = buf[:, o:o + 2 * n].contiguous().view(torch.int64).view(world, n_classes, k_fetch); o += 2 * n
-    scores = buf[:, o:o + n].contiguous().view(torch.float32).view(world, n_classes, k_fetch); o += n
-    t2i = None
-    if with_t2i:
-        t2i = buf[:, o:o + n].contiguous().view(torch.float32).view(world, n_classes, k_fetch); o += n
-    counts = buf[:, o:o + n_classes].contiguous(); o += n_classes
-    trunc = buf[:, o:o + n_classes].contiguous()
-    return scores, rows, t2i, counts, trunc
+    parts = [PackedCandidates(n_classes, k_fetch, with_t2i, buf.device, buf=buf[w].contiguous()) for w in range(world)]
+    st = lambda name: torch.stack([getattr(p, name) for p in parts])
+    return st("scores"), st("rows"), (st("t2i") if with_t2i else None), st("counts"), st("trunc")
+
+
+def unpack_flags(buf: torch.Tensor, world: int, n_classes: int, k_fetch: int, with_t2i: bool) -> torch.Tensor:
+    lay = packed_layout(n_classes, k_fetch, with_t2i)
+    return buf.view(world, -1)[:, lay["flags"]]
+
+
+def gather_packed(mine: torch.Tensor, world: int, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Single all-gather of the packed candidate lists (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    if world <= 1:
+        return mine
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty(world * mine.numel(), dtype=torch.int32, device=mine.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    if os.environ.get("SWAT_DEBUG"):
+        torch.cuda.synchronize()
+        print("[swat dist] all_gather done", flush=True)
+    return out
+
+
+def merge_packed(gathered: torch.Tensor, lay: dict, world: int, k: int, t2i_threshold: float, ctx=None,
+                 merge_fn: Optional[Callable] = None):
+    """Merge walk over an all-gathered packed buffer.  On the GPU the merge kernel reads the buffer in place
+    (per-shard stride = one rank's buffer); ``merge_fn`` (CPU tests) gets dense copies."""
+    Cn, kf, with_t2i = lay["n_classes"], lay["k"], lay["t2i"] is not None
+    thr = t2i_threshold if with_t2i else float("-inf")
+    if merge_fn is not None:
+        return merge_fn(*unpack(gathered, world, Cn, kf, with_t2i), k, thr)
+    first = PackedCandidates(Cn, kf, with_t2i, gathered.device, buf=gathered[:lay["len"]])
+    return _lib.merge_topk(ctx, first.scores, first.rows, first.counts, aux=first.t2i, truncated=first.trunc, k_out=k,
+                           aux_threshold=thr, n_shards=world, shard_stride_bytes=lay["len"] * 4)
 
 
 def gather_merge(local, k: int, t2i_threshold: float, world: int, ctx=None, group=None,
                  merge_fn: Optional[Callable] = None):
-    """Single all-gather of the packed candidate lists (NCCL over NVLink on GPUs, gloo in the CPU
-    tests), then the merge walk.  ``merge_fn(scores, rows, t2i, counts, trunc, k, thr)`` replaces the
-    CUDA merge in the CPU tests.  Returns ``(scores, rows, t2i | None, counts, incomplete)``."""
-    import torch.distributed as dist
+    """Exchange + merge for candidate tuples ``(scores, rows, t2i | None, counts, trunc)``.
+    ``merge_fn(scores, rows, t2i, counts, trunc, k, thr)`` replaces the CUDA merge in the CPU tests.
+    Returns ``(scores, rows, t2i | None, counts, incomplete)``."""
     scores, rows, t2i, counts, trunc = local
     n_classes, k_fetch = scores.shape
-    mine = pack(scores, rows, t2i, counts, trunc)
-    if world > 1:
-        out = torch.empty(world * mine.numel(), dtype=torch.int32, device=mine.device)
-        dist.all_gather_into_tensor(out, mine, group=group)
-        if os.environ.get("SWAT_DEBUG"):
-            torch.cuda.synchronize()
-            print("[swat dist] all_gather done", flush=True)
-    else:
-        out = mine
-    g_scores, g_rows, g_t2i, g_counts, g_trunc = unpack(out, world, n_classes, k_fetch, t2i is not None)
-    thr = t2i_threshold if t2i is not None else float("-inf")
-    if merge_fn is not None:
-        return merge_fn(g_scores, g_rows, g_t2i, g_counts, g_trunc, k, thr)
-    return _lib.merge_topk(ctx, g_scores, g_rows, g_counts, aux=g_t2i, truncated=g_trunc, k_out=k, aux_threshold=thr)
+    out = gather_packed(pack(scores, rows, t2i, counts, trunc), world, group)
+    return merge_packed(out, packed_layout(n_classes, k_fetch, t2i is not None), world, k, t2i_threshold, ctx, merge_fn)
 
 
 def topk_sharded(ctx, queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: float = 0.0,
@@ -142,9 +217,28 @@ def topk_sharded(ctx, queries, t2t_bank: torch.Tensor, k: int, t2t_threshold: fl
     else:
         depth = None
     k_fetch = max(1, min(int(k_fetch), max_k_fetch))
-    local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset, class_depth=depth)
-    res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
-    bad = res[4].nonzero().flatten().tolist()          # identical on every rank: the merge input is the all-gather
+    # Optimistic pass: nothing synchronises before the exchange.  Kernels write into the packed buffer, the overflow
+    # bits travel with it, and ONE read-back at the end fetches every rank's bits and the merge's `incomplete` flags.
+    Cn, with_t2i = queries.n_classes, t2i_bank is not None
+    bufs = ctx.__dict__.setdefault("_packed_cache", {})
+    key = (Cn, k_fetch, with_t2i, world)
+    if key not in bufs:
+        if len(bufs) >= 4:
+            bufs.pop(next(iter(bufs)))
+        p = PackedCandidates(Cn, k_fetch, with_t2i, t2t_bank.device)
+        bufs[key] = (p, torch.empty(world * p.lay["len"], dtype=torch.int32, device=t2t_bank.device) if world > 1 else None)
+    packed, gbuf = bufs[key]
+    local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset, class_depth=depth, packed=packed, check=False)
+    gathered = gather_packed(packed.buf, world, group, out=gbuf)
+    res = merge_packed(gathered, packed.lay, world, k, t2i_threshold, ctx=ctx)
+    status = torch.cat([unpack_flags(gathered, world, Cn, k_fetch, with_t2i), res[4]]).tolist()   # the step's only host sync
+    if any(status[:world]):
+        # some rank's candidate buffers overflowed (identical view on every rank): redo with the checked local stage,
+        # which grows that rank's buffers and rescans before anything is exchanged
+        local = local_candidates(ctx, queries, t2t_bank, k_fetch, t2t_threshold, t2i_bank, row_offset, class_depth=depth)
+        res = gather_merge(local, k, t2i_threshold, world, ctx=ctx, group=group)
+        status = [0] * world + res[4].tolist()
+    bad = [c for c, v in enumerate(status[world:]) if v]          # identical on every rank: the merge input is the all-gather
     if not bad:
         return res
     out_s, out_r, out_t, out_c, _ = res

@@ -42,6 +42,21 @@ def test_pack_unpack_roundtrip():
     assert t is None and torch.equal(r[2], parts[2][1])
 
 
+def test_packed_layout_alignment():
+    """int64 rows must stay 8-byte aligned in every rank's slice of the gathered buffer; views alias the buffer."""
+    from swat_b200.dist import PackedCandidates, packed_layout
+    for C, k, t in ((5, 7, True), (5, 7, False), (3, 1, False), (200, 1024, True), (1, 1, True)):
+        lay = packed_layout(C, k, t)
+        assert lay["len"] % 2 == 0 and lay["rows"] == 0 and lay["flags"] < lay["len"]
+        p = PackedCandidates(C, k, t, "cpu")
+        p.rows.fill_(2 ** 40 + 3); p.scores.fill_(1.5); p.counts.fill_(k); p.trunc.fill_(1); p.flags.fill_(3)
+        if t:
+            p.t2i.fill_(0.25)
+        q = PackedCandidates(C, k, t, "cpu", buf=p.buf.clone())
+        assert int(q.rows[C - 1, k - 1]) == 2 ** 40 + 3 and float(q.scores[0, 0]) == 1.5 and int(q.flags[0]) == 3
+        assert int(q.counts[C - 1]) == k and int(q.trunc[0]) == 1 and (not t or float(q.t2i[C - 1, 0]) == 0.25)
+
+
 def _oracle_merge(scores, rows, t2i, counts, trunc, k, thr):
     """CPU stand-in for swat_merge_topk with the same contract (predicate walk + frontier check)."""
     G, C, kf = scores.shape
@@ -94,6 +109,13 @@ def _worker(rank, world, port, ret):
                               k, 0.25, world, merge_fn=_oracle_merge)
     full2 = so.topk_walk(capf, qf, k, 0.0)
     ok = ok and all(res2[1][c, :int(res2[3][c])].tolist() == full2[0][c, :full2[3][c]].tolist() for c in range(C))
+    # packed exchange buffer written in place (what the GPU path does): same result, and every rank sees every rank's flags
+    pk = sdist.PackedCandidates(C, kf, True, "cpu")
+    pk.scores.copy_(sc); pk.rows.copy_(rows); pk.t2i.copy_(ti); pk.counts.copy_(cnt); pk.trunc.copy_(tr); pk.flags.fill_(rank * 2)
+    gathered = sdist.gather_packed(pk.buf, world)
+    res3 = sdist.merge_packed(gathered, pk.lay, world, k, 0.25, merge_fn=_oracle_merge)
+    ok = ok and torch.equal(res3[1], res[1]) and torch.equal(res3[3], res[3]) and torch.equal(res3[0], res[0])
+    ok = ok and sdist.unpack_flags(gathered, world, C, kf, True).tolist() == [2 * r for r in range(world)]
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

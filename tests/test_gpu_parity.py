@@ -271,6 +271,17 @@ def test_merge_and_shard_invariance(lib, ctx2):
         assert int(inc.sum()) == 0, f"G={G}"
         assert torch.equal(mr, full[1]) and torch.equal(mc, full[3]), f"T2I G={G}"
         assert torch.equal(ms, full[0]) and torch.equal(mt, full[2])
+        # the exchange path proper: kernels write into packed buffers (no overflow check before the exchange), the
+        # merge reads the gathered buffer in place through the per-shard stride
+        pks = []
+        for a, b in bounds:
+            pk = dist.PackedCandidates(30, 1024, True, d_cap.device)
+            dist.local_candidates(ctx2, qs, d_cap[a:b], 1024, 0.0, d_img[a:b], row_offset=a, packed=pk, check=False)
+            pks.append(pk)
+        gathered = torch.cat([pk.buf for pk in pks])
+        ps, pr, pt, pc, pinc = dist.merge_packed(gathered, pks[0].lay, G, 250, 0.25, ctx=ctx2)
+        assert torch.equal(pr, full[1]) and torch.equal(pc, full[3]) and torch.equal(ps, full[0]) and torch.equal(pt, full[2])
+        assert int(pinc.sum()) == 0 and dist.unpack_flags(gathered, G, 30, 1024, True).tolist() == [0] * G
     # a frontier violation must be reported: k_fetch too small to find 250 passing rows
     parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 64, 0.0, d_img[a:b], row_offset=a) for a, b in bounds]
     s, r, t, c, tr = dist.unpack(torch.cat([dist.pack(*p) for p in parts]), 8, 30, 64, True)
