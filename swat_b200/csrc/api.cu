@@ -97,6 +97,8 @@ struct swat_ctx {
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_used[3] = {nullptr, nullptr, nullptr};
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
+  int32_t* h_status = nullptr;      // pinned: [0] job overflow word, [1..C] incomplete flags (one read-back per step)
+  size_t h_status_cap = 0;
   swat_job* cached_job = nullptr;   // job buffers are reused across whole-pipeline calls
   // last sub-query set built for a targeted escalation (repeated calls hit the same classes)
   swat_queries* esc_q = nullptr;
@@ -437,6 +439,14 @@ int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, bool dual, floa
   return SWAT_OK;
 }
 
+int32_t ensure_status(swat_ctx* ctx, size_t n_ints) {
+  if (n_ints <= ctx->h_status_cap) return SWAT_OK;
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  ctx->h_status = nullptr; ctx->h_status_cap = 0;
+  CU_OK(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), n_ints * sizeof(int32_t)));
+  ctx->h_status_cap = n_ints;
+  return SWAT_OK;
+}
 int32_t ensure_pinned(swat_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->h_pinned_cap) return SWAT_OK;
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -563,21 +573,28 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     job->last_stream = stream;
     ctx->launches += kSelectLaunches;
     CU_OK(cudaEventRecord(ctx->ev[2], stream));
+    // Resident banks with a T2I stage run it optimistically and read the overflow word together with the walk's
+    // `incomplete` flags: one host sync per step instead of two.  (Overflowed lists hold valid rows, just not all.)
+    const bool late_check = !direct && !b.host;
     uint32_t flags = 0;
-    SW_OK(job_flags(job, &flags));
-    {
+    auto account_scan = [&]() {
       float ms = 0;
       cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing[0] += ms;
       cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timing[1] += ms;
       ctx->timing[4] += 1;
-    }
-    if (flags & 3u) {
+    };
+    auto grow_buffers = [&]() -> int32_t {
       const int64_t limit = std::max<int64_t>(b.n_rows, 1 << 16);
       if ((flags & 1u) && cap >= limit) return fail(SWAT_ERR_OVERFLOW, "class candidate overflow with cap >= n_rows");
       if (flags & 1u) cap = std::min<int64_t>(cap * 4, limit);
       if (flags & 2u) list_entries *= 4;
       ctx->timing[7] += 1;
-      continue;
+      return SWAT_OK;
+    };
+    if (!late_check) {
+      SW_OK(job_flags(job, &flags));
+      account_scan();
+      if (flags & 3u) { SW_OK(grow_buffers()); continue; }
     }
     if (direct && !(dual && d_out_t2i)) break;
     // ---- T2I stage on the candidates
@@ -662,13 +679,21 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       CU_OK(cudaMemcpyAsync(d_out_counts, t.out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, stream));
     }
     CU_OK(cudaEventRecord(ctx->ev[4], stream));
-    std::vector<int32_t> inc(C, 0);
-    CU_OK(cudaMemcpyAsync(inc.data(), t.incomplete, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+    SW_OK(ensure_status(ctx, static_cast<size_t>(C) + 1));
+    ctx->h_status[0] = 0;
+    if (late_check) CU_OK(cudaMemcpyAsync(ctx->h_status, job->st.flags, 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaMemcpyAsync(ctx->h_status + 1, t.incomplete, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
     CU_OK(cudaStreamSynchronize(stream));
+    const int32_t* inc = ctx->h_status + 1;
     {
       float ms = 0;
       cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
       ctx->timing[2] += ms;
+    }
+    if (late_check) {
+      flags = static_cast<uint32_t>(ctx->h_status[0]);
+      account_scan();
+      if (flags & 3u) { SW_OK(grow_buffers()); continue; }
     }
     if (direct) break;
     std::vector<int> bad;
@@ -766,6 +791,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   if (ctx->esc_q) swat_queries_destroy(ctx->esc_q);
   for (auto& lvl : ctx->e_bufs) for (auto& bf : lvl) bf.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->work_stream) cudaStreamDestroy(ctx->work_stream);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
