@@ -239,6 +239,7 @@ def run_ours(a, rank, world, local_rank):
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, scan_launches = [], 0
+    scan_events = ctx.__dict__["_time_scans"] = []      # swat_b200.dist records (start, end) events around each scan
     barrier()
     ev0.record()
     for _ in range(a.steps):
@@ -249,6 +250,7 @@ def run_ours(a, rank, world, local_rank):
             scan_launches += int(tm["scan_launches"])
     ev1.record()
     barrier()
+    ctx.__dict__["_time_scans"] = None
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
     escalations = ctx.last_timing()["escalations"] if world == 1 else 0.0
@@ -262,13 +264,9 @@ def run_ours(a, rank, world, local_rank):
 
     # ---- scan-kernel roofline (rank 0's kernel; CUDA events on the launching stream)
     hbm, tf, src = peaks()
-    if not scan_ms:                                     # multi-GPU path: time the scan alone, same stream
-        for _ in range(3):
-            job = _lib.Job(ctx, qs, 1024 if img is not None else k, 0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); job.scan(cap); e1.record(); torch.cuda.synchronize(dev)
-            scan_ms.append(e0.elapsed_time(e1)); job.close()
-        scan_launches = a.steps
+    if not scan_ms:                                     # multi-GPU path: events recorded around every scan of the timed steps
+        scan_ms = [e0.elapsed_time(e1) for e0, e1 in scan_events]
+        scan_launches = len(scan_ms)
     scan_ms.sort()
     scan = scan_ms[len(scan_ms) // 2]
     q_cols = a.classes

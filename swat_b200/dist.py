@@ -91,7 +91,14 @@ def local_candidates(ctx, queries, t2t_bank: torch.Tensor, k_fetch: int, t2t_thr
     for _ in range(8):
         job = _get_job(ctx, queries, k_fetch, t2t_threshold, cap, lists)
         job.set_class_depth(class_depth)
+        timed = ctx.__dict__.get("_time_scans")       # bench.py: CUDA events around the scan, on the launching stream
+        if timed is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         job.scan(t2t_bank, row_base=0, row_class=row_class, exclude=exclude)
+        if timed is not None:
+            e1.record()
+            timed.append((e0, e1))
         if packed is None:
             scores, rows, counts, trunc = job.select(row_offset)
         elif t2i_bank is None:
