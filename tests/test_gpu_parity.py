@@ -308,6 +308,35 @@ def test_streaming_job_matches_single_view(lib, ctx2):
     job.close()
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_ragged_and_tiny_banks(lib, ctx, dtype):
+    """Banks smaller than, equal to and just past a tile (128 / 256 rows), a single row, a single query, k larger than
+    the bank, everything excluded, a threshold nothing reaches -- resident and host pipelines, both engines."""
+    for n_rows, n_cls in ((1, 1), (1, 17), (127, 3), (128, 3), (129, 17), (255, 1), (256, 5), (257, 17), (1000, 200)):
+        bank = _rand_unit(n_rows, 100 + n_rows, dtype)
+        img = _rand_unit(n_rows, 200 + n_rows, dtype)
+        q = _rand_unit(n_cls, 300 + n_cls, torch.bfloat16).float()
+        bf, imf, qf = bank.float().numpy(), img.float().numpy(), q.numpy()
+        S = so.score_matrix(bf, qf)
+        qs = lib.Queries(ctx, q)
+        for k in (1, 40, 300):
+            o = so.topk_walk(bf, qf, k, 0.0)
+            g = lib.topk(ctx, qs, bank.cuda(), k, 0.0)
+            check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=f"N={n_rows} C={n_cls} k={k}")
+            o = so.topk_walk(bf, qf, k, 0.0, t2i_bank=imf, t2i_threshold=0.0)
+            g = lib.topk(ctx, qs, bank.cuda(), k, 0.0, t2i_bank=img.cuda(), t2i_threshold=0.0)
+            check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=f"T2I N={n_rows} C={n_cls} k={k}")
+            h = lib.topk_host(ctx, qs, bank, k, 0.0, t2i_bank=img, t2i_threshold=0.0)
+            assert torch.equal(h[1], g[1].cpu()) and torch.equal(h[3], g[3].cpu())
+        # nothing can be accepted: threshold above every score, or every row excluded
+        g = lib.topk(ctx, qs, bank.cuda(), 10, 2.0)
+        assert int(g[3].sum()) == 0 and bool((g[1] == -1).all())
+        bits = torch.full(((n_rows + 31) // 32,), -1, dtype=torch.int32)
+        g = lib.topk(ctx, qs, bank.cuda(), 10, 0.0, exclude=bits.cuda())
+        assert int(g[3].sum()) == 0 and bool((g[1] == -1).all())
+        qs.close()
+
+
 def test_bad_arguments_raise(lib, ctx2):
     q = _rand_unit(4, 1)
     with pytest.raises(lib.SwatError):
