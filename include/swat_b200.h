@@ -150,6 +150,14 @@ int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_r
 int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype,
                           int64_t n_rows, float* d_out, int32_t engine, void* stream);
 
+/* ---- exclusion-set producer: zeroshot_clip_img_filter (:278-329) --------------------------------- */
+/* d_pred [n_rows] i32: argmax over the class scores of every row (lowest class on ties) -- the prediction of the
+ * zero-shot head `MyLinear(weights = stacked class prompts, bias = False)` (:1489-1492, :299-301).  Rows whose
+ * prediction differs from their own class go into filtered_images_dict.  The scores are produced in row chunks
+ * by the same scan kernels (dense mode) and never leave the device. */
+int32_t swat_zeroshot_predict(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype,
+                              int64_t n_rows, int32_t* d_pred, int32_t engine, void* stream);
+
 /* ---- exclusion-set producer: remove_near_duplicates2 (:237-275) --------------------------------- */
 /* d_order [n]: bank row ids grouped by class (file order kept inside a class), d_class_start [C+1]:
  * first position of each class in d_order.  d_dup [n] (by position in d_order) is set to 1 for every

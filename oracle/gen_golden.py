@@ -15,6 +15,7 @@ Test infrastructure, not product code.
 from __future__ import annotations
 
 import hashlib
+from collections import defaultdict
 import json
 import logging
 import os
@@ -101,6 +102,32 @@ def case_bank(sr, name, n_rows, C, k, seed, dtype, partitioned, rho, tie_block):
     # near-duplicate removal (remove_near_duplicates2 :237-275) on the regrouped dict
     dd, frac, avg = sr.remove_near_duplicates2(feats)
     dup_fixture = {"dict": {kk: sorted(path_to_row_tmp[p] for p in v) for kk, v in dd.items() if v}, "fractions": frac, "avg": avg}
+    # zero-shot filter (zeroshot_clip_img_filter :278-329): head = class prompts at the rows of their class ids (:1489-1490)
+    W = torch.zeros(max(class_ids) + 1, 512)
+    for c in range(C):
+        W[class_ids[c]] = qc[c].float()
+    head = torch.nn.Linear(512, W.shape[0], bias=False)
+    with torch.no_grad():
+        head.weight.copy_(W)
+    root = tempfile.mkdtemp()
+    for kk in feats.keys():
+        os.makedirs(os.path.join(root, kk))
+    open(os.path.join(root, "not_a_class.txt"), "w").close()
+    with torch.no_grad():
+        zs = sr.zeroshot_clip_img_filter(None, None, root, pre_extracted_feats=feats, head=head)
+    zs_fixture = {kk: sorted(path_to_row_tmp[p] for p in v) for kk, v in zs.items() if v}
+    # random sampler (random_sampler :592-661), seeded like the CLI does (:1710)
+    import random as _random
+    rnd = {}
+    for tag, thr, th, use_dups in (("plain", 0.0, False, False), ("t2i", 0.2, False, True), ("tailhead", 0.2, True, False)):
+        _random.seed(1234)
+        rargs = Namespace(dataset=name, output_folder=tmp, prefix="RND")
+        ms, nd = sr.random_sampler(rargs, logging.getLogger("golden"), prompts, k, thr, feats,
+                                   duplicates_dict=dd if use_dups else defaultdict(set), tail_head=th)
+        rnd[tag] = dict(rows=[path_to_row_tmp[p] for fl in ms["file_list"] for p in fl], counts=nd,
+                        featsum=[float(x) for x in torch.cat(ms["feature_list"]).double().sum(dim=1).tolist()],
+                        sampled_sha=hashlib.sha256(open(f"{tmp}/RND_sampled_list.txt", "rb").read()).hexdigest(),
+                        filtered_sha=hashlib.sha256(open(f"{tmp}/RND_filtered_list.txt", "rb").read()).hexdigest())
     # regroup fixture: key order + per-class original rows
     path_to_row = {p: i for i, p in enumerate(paths)}
     regroup_keys = list(feats.keys())
@@ -123,7 +150,7 @@ def case_bank(sr, name, n_rows, C, k, seed, dtype, partitioned, rho, tie_block):
         arrays[f"regroup_rows_{i}"] = regroup_rows[i]
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
     meta = dict(name=name, n_rows=n_rows, C=C, k=k, seed=seed, dtype=str(dtype), partitioned=partitioned,
-                regroup_keys=regroup_keys, near_dup=dup_fixture,
+                regroup_keys=regroup_keys, near_dup=dup_fixture, zeroshot=zs_fixture, random=rnd,
                 counts={tag: {m: res[m]["counts"] for m in res} for tag, res in (("part", res_p), ("unpart", res_u))},
                 diag={tag: {m: {x: res[m][x] for x in ("filtered_sha", "sampled_sha", "sampled_head", "n_filtered")}
                             for m in res} for tag, res in (("part", res_p), ("unpart", res_u))})

@@ -141,6 +141,68 @@ def remove_near_duplicates2(pre_extracted_feats: dict, threshold: float = 0.9, p
     return dup, fractions, sum(fractions) / len(fractions)
 
 
+def zeroshot_clip_img_filter(pre_extracted_feats: dict, head_weight: np.ndarray, classes=None, positional: bool = False):
+    """``zeroshot_clip_img_filter`` (:278-329): rows whose zero-shot prediction ``argmax(feats @ W^T)`` (:299-300) is not
+    their own class id; same file-id-vs-position comparison as the dedup (:315-318)."""
+    if classes is None:
+        classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))
+    W = np.asarray(head_weight, dtype=np.float32)
+    out = defaultdict(set)
+    fractions = []
+    for cls in classes:
+        files = pre_extracted_feats[cls]["file_paths"]
+        logits = np.asarray(pre_extracted_feats[cls]["feats"], dtype=np.float32) @ W.T
+        preds = np.argmax(logits, axis=1)
+        to_remove = set(np.nonzero(preds != int(cls))[0].tolist())
+        for pos, f in enumerate(files):
+            key = pos if positional else int(f.split("/")[-1].split(".")[0])
+            if key in to_remove:
+                out[cls].add(f)
+        fractions.append((len(files) - len(to_remove)) / len(files))
+    return out, fractions
+
+
+def verbatim_random_sampler(prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict=None,
+                            filtered_images_dict=None, tail_head=False, rng=None):
+    """``random_sampler`` (:592-661): per class shuffle (Python ``random``), then the accept walk of ``add_to_split``
+    (:439-482) with ``similarity`` = 1.0, or the T2I score when ``threshold != 0`` (:622-627).  Returns
+    ``(file_list per class, counts, sampled strings, filtered strings)`` -- strings without captions."""
+    import random as _random
+    rng = rng or _random
+    dups = duplicates_dict or defaultdict(set)
+    filt = filtered_images_dict or defaultdict(set)
+    classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))
+    files_out, counts, sampled, filtered = [], {}, [], []
+    for cls in classes:
+        file_list = pre_extracted_feats[cls]["file_paths"]
+        if file_list is None:
+            counts[cls] = 0
+            continue
+        sim = [1.0] * len(file_list)
+        if threshold != 0:
+            sim = similarity(np.asarray(prompt_tensors[cls]["mean"], dtype=np.float32)[None, :],
+                             np.asarray(pre_extracted_feats[cls]["feats"], dtype=np.float32))
+            sim = [sim] if isinstance(sim, float) else list(sim)
+        zipped = list(zip(file_list, sim))
+        rng.shuffle(zipped)
+        if tail_head:
+            if len(zipped) >= num_samples:
+                threshold = 0                      # :638-639 -- sticks for every later class
+        ct, acc = 0, []
+        for fp, s_ in zipped:
+            if ct == num_samples:
+                break
+            if s_ >= threshold and fp not in dups[str(cls)] and fp not in filt[str(cls)]:
+                acc.append(fp); ct += 1
+                sampled.append(f"{round(s_, 4)}/{threshold}, {fp}")
+            else:
+                filtered.append(f"{round(s_, 4)}/{threshold}, {fp}")
+        if acc:
+            files_out.append(acc)
+        counts[cls] = ct
+    return files_out, counts, sampled, filtered
+
+
 # --------------------------------------------------------------------------------------
 # accept / walk
 # --------------------------------------------------------------------------------------

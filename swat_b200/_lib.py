@@ -24,7 +24,7 @@ EXPORTS = [
     "swat_version", "swat_last_error", "swat_ctx_create", "swat_ctx_destroy", "swat_ctx_set_option",
     "swat_ctx_launch_count", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
     "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_export_flags", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
-    "swat_scores_dense", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
+    "swat_scores_dense", "swat_zeroshot_predict", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
 ]
 
 
@@ -69,6 +69,7 @@ def load() -> C.CDLL:
         "swat_t2i_walk": [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_merge_topk": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_scores_dense": [vp, vp, vp, i32, i64, vp, i32, vp],
+        "swat_zeroshot_predict": [vp, vp, vp, i32, i64, vp, i32, vp],
         "swat_near_duplicates": [vp, vp, i32, i64, vp, vp, i32, i32, f32, vp, vp],
         "swat_topk": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
         "swat_topk_host": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp],
@@ -281,6 +282,15 @@ def scores_dense(ctx: Context, queries: Queries, bank: torch.Tensor, engine="aut
     out = torch.empty(bank.shape[0], queries.n_classes, dtype=torch.float32, device=bank.device)
     _check(load().swat_scores_dense(ctx._h, queries._h, _ptr(bank), _dtype_code(bank), int(bank.shape[0]), _ptr(out),
                                     ENGINE[engine], _stream(ctx.device)))
+    return out
+
+
+def zeroshot_predict(ctx: Context, queries: Queries, bank: torch.Tensor, engine="auto") -> torch.Tensor:
+    """``[N]`` int32: argmax over the class scores of every row (the zero-shot head's prediction)."""
+    _bank_ok(bank, "bank", True)
+    out = torch.empty(bank.shape[0], dtype=torch.int32, device=bank.device)
+    _check(load().swat_zeroshot_predict(ctx._h, queries._h, _ptr(bank), _dtype_code(bank), int(bank.shape[0]), _ptr(out),
+                                        ENGINE[engine], _stream(ctx.device)))
     return out
 
 

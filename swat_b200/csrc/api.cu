@@ -1093,6 +1093,30 @@ int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_ba
   return scan_view(&tmp, d_bank, dtype, n_rows, 0, nullptr, 0.0f, nullptr, nullptr, engine, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int32_t swat_zeroshot_predict(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows, int32_t* d_pred,
+                              int32_t engine, void* stream) {
+  if (!ctx || !q || (!d_bank && n_rows > 0) || (!d_pred && n_rows > 0)) return fail(SWAT_ERR_INVALID, "null argument");
+  if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
+  if (n_rows < 0) return fail(SWAT_ERR_INVALID, "n_rows must be >= 0");
+  (void)cudaGetLastError();
+  CU_OK(cudaSetDevice(ctx->device));
+  const int64_t C = q->C;
+  const int64_t chunk = std::max<int64_t>(256, ((256ll << 20) / (4 * C)) / 256 * 256);    // <= 256 MB of scores at a time
+  swat_job tmp;   // dense mode never touches job state
+  tmp.ctx = ctx; tmp.q = q;
+  memset(&tmp.st, 0, sizeof(tmp.st));
+  const size_t row_bytes = static_cast<size_t>(kDim) * elem_size(dtype);
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+    const int64_t n = std::min(chunk, n_rows - r0);
+    SW_OK(ctx->w_boot.ensure(static_cast<size_t>(n) * C * 4));
+    SW_OK(scan_view(&tmp, static_cast<const char*>(d_bank) + static_cast<size_t>(r0) * row_bytes, dtype, n, 0, nullptr, 0.0f, nullptr, nullptr,
+                    engine, ctx->w_boot.as<float>(), static_cast<cudaStream_t>(stream)));
+    CU_OK(launch_argmax_rows(ctx->w_boot.as<float>(), n, static_cast<int>(C), d_pred + r0, static_cast<cudaStream_t>(stream)));
+    ctx->launches += 1;
+  }
+  return SWAT_OK;
+}
+
 int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, const void* d_t2i_bank, int32_t dtype, int64_t n_rows,
                   int64_t row_offset, int32_t k, float t2t_threshold, float t2i_threshold, const int32_t* d_row_class,
                   const uint32_t* d_exclude, float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts,

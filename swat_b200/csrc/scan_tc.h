@@ -48,6 +48,7 @@ struct T2iArgs {
 };
 cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream);
 
+cudaError_t launch_argmax_rows(const float* d_scores, int64_t n_rows, int n_classes, int32_t* d_pred, cudaStream_t stream);
 cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, float aux_thr,
                          const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int64_t shard_stride_bytes, int n_classes,
                          int k, int k_out, uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,

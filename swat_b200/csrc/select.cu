@@ -538,6 +538,35 @@ cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------- zero-shot prediction
+// argmax over the class scores of a row, lowest class index on ties (torch.argmax on the logits of the zero-shot head,
+// zeroshot_clip_img_filter sample_retrieval.py:299-301).  One warp per row.
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ scores, int64_t n_rows, int C, int32_t* __restrict__ pred) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const float* s = scores + r * C;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float v = s[c];
+    if (v > best || (v == best && c < arg)) { best = v; arg = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (lane == 0) pred[r] = arg == 0x7fffffff ? 0 : arg;
+}
+
+cudaError_t launch_argmax_rows(const float* d_scores, int64_t n_rows, int n_classes, int32_t* d_pred, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  argmax_rows_kernel<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, stream>>>(d_scores, n_rows, n_classes, d_pred);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, float aux_thr,
                          const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int64_t shard_stride_bytes, int n_classes,
                          int k, int k_out, uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,

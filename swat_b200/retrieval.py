@@ -177,6 +177,58 @@ def remove_near_duplicates2(pre_extracted_feats, threshold: float = 0.9, positio
 # ---------------------------------------------------------------------------------------------
 # samplers
 # ---------------------------------------------------------------------------------------------
+def _head_weight(head) -> torch.Tensor:
+    """``[C,512]`` weights of the zero-shot head: ``MyLinear`` (``.linear.weight``, utils/models.py:47-68), an
+    ``nn.Linear`` or a plain tensor.  The reference builds it with ``bias=False`` (:1490)."""
+    if torch.is_tensor(head):
+        return head.detach().float().cpu()
+    lin = getattr(head, "linear", head)
+    bias = getattr(lin, "bias", None)
+    if bias is not None and bool((bias.detach() != 0).any()):
+        raise NotImplementedError("zero-shot head with a non-zero bias")
+    return lin.weight.detach().float().cpu()
+
+
+def zeroshot_clip_img_filter(model=None, preprocess=None, root_folder=None, pre_extracted_feats=None, head=None,
+                             positional: bool = False, device: int = 0):
+    """``zeroshot_clip_img_filter`` (:278-329): classify every mined image with the zero-shot head and collect the
+    ones not predicted as their own class into ``filtered_images_dict``.  The logits ``feats @ W^T`` (:299) and the
+    argmax (:300) run on the GPU for all classes at once (``swat_zeroshot_predict``).
+
+    Like ``remove_near_duplicates2`` the reference compares the integer *file id* of every file with the set of
+    mispredicted *positions* (:315-318); that is reproduced unless ``positional=True``.  ``model`` and ``preprocess``
+    are unused (as in the reference, which requires pre-extracted features, :293-297)."""
+    if pre_extracted_feats is None:
+        raise ValueError("Pre-extracted features are required for zeroshot filtering.")        # :297
+    if root_folder is not None and os.path.isdir(root_folder):
+        classes = [c for c in os.listdir(root_folder) if os.path.isdir(os.path.join(root_folder, c))]   # :282-284
+    else:
+        classes = list(pre_extracted_feats.keys())
+    classes = sorted(classes, key=lambda x: int(x))                                              # :285
+    W = _head_weight(head)
+    _, img, paths, row_class = _flatten(pre_extracted_feats, classes)
+    ctx = get_context(device)
+    qs = _lib.Queries(ctx, W)
+    if img.dtype not in (torch.float32, torch.bfloat16):
+        img = img.float()
+    pred = _lib.zeroshot_predict(ctx, qs, img.contiguous().cuda(device)).cpu()
+    qs.close()
+    filtered_images_dict = defaultdict(set)
+    fractions = []
+    for ci, cls in enumerate(classes):
+        files = pre_extracted_feats[cls]["file_paths"]
+        n = len(files)
+        p = pred if row_class is None else pred[row_class == ci]      # file order inside the class is kept
+        to_remove = set((p != int(cls)).nonzero().flatten().tolist())                            # :303-309
+        for pos, f in enumerate(files):
+            key = pos if positional else int(f.split("/")[-1].split(".")[0])                     # :315-318
+            if key in to_remove:
+                filtered_images_dict[cls].add(f)
+        fractions.append((n - len(to_remove)) / n)
+    print(f"Average unique images: {round(sum(fractions) / len(fractions), 4)}")                 # :326
+    return filtered_images_dict
+
+
 def _flatten(pre_extracted_feats, classes: List[str]):
     """Return (caption [N,512], image [N,512], paths, row_class int32 [N] or None)."""
     if isinstance(pre_extracted_feats, RegroupedFeats):
@@ -384,6 +436,81 @@ def t2i_ranked_sampler(args, logger, prompt_tensors, num_samples, threshold, pre
                         filtered_images_dict, with_t2i=False, rank_on_images=True)
 
 
+def random_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats,
+                   duplicates_dict=None, filtered_images_dict=None, tail_head=False):
+    """``random_sampler`` (:592-661): per class, shuffle the rows with Python's ``random`` (seeded by the caller,
+    :1710) and accept the first ``num_samples`` that pass ``similarity >= threshold`` and the exclusion sets
+    (``add_to_split`` :439-482).  ``similarity`` is 1.0, or the T2I score of the class prompt when ``threshold != 0``
+    (:622-627; computed on the GPU).  No ranking is involved, so the walk itself stays on the host, as in the
+    reference; the RNG is consumed exactly as ``random.shuffle(path_sim_zip)`` does."""
+    import random
+    dups = duplicates_dict if duplicates_dict is not None else defaultdict(set)
+    filt = filtered_images_dict if filtered_images_dict is not None else defaultdict(set)
+    caption_map = None
+    cmap_path = getattr(args, "caption_map_path", None)
+    if cmap_path is None:
+        try:
+            from .config import CAPTION_MAP_DICT
+            cmap_path = CAPTION_MAP_DICT.get(args.dataset)
+        except Exception:
+            cmap_path = None
+    if cmap_path and os.path.exists(cmap_path):
+        with open(cmap_path, "rb") as f:                                                         # :599-601
+            caption_map = pickle.load(f)
+    classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))                     # :603-604
+    mined_split = {"feature_list": [], "label_list": [], "file_list": []}
+    num_imgs_sampled_dict = {}
+    filtered_list: List[str] = []
+    sampled_list: List[str] = []
+    tail_ct = 0
+    for cls in classes:
+        file_list = pre_extracted_feats[cls]["file_paths"]
+        if file_list is None:
+            num_imgs_sampled_dict[cls] = 0                                                       # :614-617
+            continue
+        img_embeddings = pre_extracted_feats[cls]["feats"]
+        similarity = [1.0 for _ in range(len(file_list))]
+        if threshold != 0:
+            class_prompt = torch.as_tensor(prompt_tensors[cls]["mean"]).unsqueeze(0)             # :623-626
+            similarity = cal_t2i_similarity(class_prompt, img_embeddings)
+        order = list(range(len(file_list)))
+        random.shuffle(order)                                                                    # :633 (same draws as shuffling the zip)
+        if tail_head:
+            if len(order) < num_samples:
+                tail_ct += 1
+            else:
+                threshold = 0                                                                    # :636-641 -- sticks for later classes
+        ct, acc = 0, []
+        for i in order:                                                                          # add_to_split :450-469
+            if ct == num_samples:
+                break
+            fp, sim = file_list[i], similarity[i]
+            caption = check_caption(caption_map, fp) if caption_map is not None else ""
+            info = f"{round(sim, 4)}/{threshold}, {fp}, {caption}"
+            if sim >= threshold and fp not in dups[str(cls)] and fp not in filt[str(cls)]:
+                acc.append(i)
+                ct += 1
+                sampled_list.append(info)
+            else:
+                filtered_list.append(info)
+        if acc:
+            idx = torch.tensor(acc, dtype=torch.int64)
+            mined_split["feature_list"].append(torch.as_tensor(img_embeddings)[idx].float())
+            mined_split["label_list"].append(torch.full((len(acc),), int(cls), dtype=torch.int64))
+            mined_split["file_list"].append([file_list[i] for i in acc])
+        num_imgs_sampled_dict[cls] = ct
+    if tail_head:
+        print(f"Number of tail classes: {tail_ct}")
+    os.makedirs(args.output_folder, exist_ok=True)
+    logger.info(f"len(filtered_list): {len(filtered_list)}")
+    with open(f"{args.output_folder}/{args.prefix}_filtered_list.txt", "w") as f:                # :649-651
+        f.write("\n".join(filtered_list))
+    logger.info(f"len(sampled_list): {len(sampled_list)}")
+    with open(f"{args.output_folder}/{args.prefix}_sampled_list.txt", "w") as f:                 # :654-656
+        f.write("\n".join(sampled_list))
+    return mined_split, num_imgs_sampled_dict
+
+
 def _load_fewshot(args):
     fs = getattr(args, "fewshot_features", None)
     if fs is not None:
@@ -464,7 +591,9 @@ def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=Non
     feats = transform_extracted_fea(pre_extracted_feats) if "labels" in pre_extracted_feats else pre_extracted_feats
     logger.info(f"Sampling method: {args.sampling_method}, sampling number: {args.num_samples}, "
                 f"sampling threshold: {args.sampling_threshold}")
-    if args.sampling_method == "T2T-rank":
+    if args.sampling_method == "Random":                                             # :1517-1526
+        mined_split, num_imgs_sampled_dict = random_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    elif args.sampling_method == "T2T-rank":
         mined_split, num_imgs_sampled_dict = t2t_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
     elif args.sampling_method == "T2T-rank-T2I-tshd":
         mined_split, num_imgs_sampled_dict = t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)

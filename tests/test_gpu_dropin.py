@@ -170,3 +170,43 @@ def test_near_duplicate_removal_matches_reference(name):
                                                   so.transform_extracted_fea({k: (v.numpy() if torch.is_tensor(v) else v) for k, v in raw.items()}),
                                                   duplicates_dict={k: set(v) for k, v in o_dd.items()})
     assert nd == o_nd
+
+
+@pytest.mark.parametrize("name", ["bank_bf16", "bank_f32"])
+def test_zeroshot_filter_and_random_sampler(name):
+    """zeroshot_clip_img_filter (GPU logits + argmax) and random_sampler (host shuffle, GPU T2I predicate) against the
+    reference's outputs, including the bytes of the two diagnostic files of the random sampler."""
+    import hashlib, logging, random, tempfile
+    from argparse import Namespace
+    from swat_b200 import retrieval
+    z, meta, cap, img, q, raw, prompts, paths, cmap = _case(name)
+    feats = retrieval.transform_extracted_fea(raw)
+    class_ids = z["class_ids"]
+    row = {p: i for i, p in enumerate(paths)}
+    W = torch.zeros(int(class_ids.max()) + 1, 512)
+    W[torch.from_numpy(class_ids)] = torch.as_tensor(q).float()
+    head = torch.nn.Linear(512, W.shape[0], bias=False)
+    with torch.no_grad():
+        head.weight.copy_(W)
+    root = tempfile.mkdtemp()
+    for kk in feats.keys():
+        os.makedirs(os.path.join(root, kk))
+    zs = retrieval.zeroshot_clip_img_filter(None, None, root, pre_extracted_feats=feats, head=head)
+    assert {k: sorted(row[p] for p in v) for k, v in zs.items() if v} == meta["zeroshot"]
+    dd, _, _ = retrieval.remove_near_duplicates2(feats)
+    tmp = tempfile.mkdtemp()
+    cm = tmp + "/cap.map"
+    with open(cm, "wb") as f:
+        pickle.dump(cmap, f)
+    for tag, thr, th, use_dups in (("plain", 0.0, False, False), ("t2i", 0.2, False, True), ("tailhead", 0.2, True, False)):
+        random.seed(1234)
+        args = Namespace(dataset="synthetic", output_folder=tmp, prefix="RND", caption_map_path=cm)
+        ms, nd = retrieval.random_sampler(args, logging.getLogger("t"), prompts, int(z["k"]), thr, feats,
+                                          duplicates_dict=dd if use_dups else None, tail_head=th)
+        ref = meta["random"][tag]
+        assert [row[p] for fl in ms["file_list"] for p in fl] == ref["rows"], tag
+        assert nd == ref["counts"], tag
+        np.testing.assert_allclose(torch.cat(ms["feature_list"]).double().sum(dim=1).numpy(), ref["featsum"], atol=1e-9)
+        if name == "bank_bf16" or thr == 0.0:      # fp32 T2I scores print with 4 decimals; bf16-valued inputs make them exact
+            assert hashlib.sha256(open(f"{tmp}/RND_sampled_list.txt", "rb").read()).hexdigest() == ref["sampled_sha"], tag
+            assert hashlib.sha256(open(f"{tmp}/RND_filtered_list.txt", "rb").read()).hexdigest() == ref["filtered_sha"], tag

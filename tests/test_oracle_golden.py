@@ -185,3 +185,29 @@ def test_near_duplicates_match_reference(name):
     assert abs(avg - ref["avg"]) < 1e-12 and max(frac) > 0
     row = {p: i for i, p in enumerate(paths)}
     assert {k: sorted(row[p] for p in v) for k, v in dd.items() if v} == ref["dict"]
+
+
+@pytest.mark.parametrize("name", ["bank_bf16", "bank_f32"])
+def test_zeroshot_filter_and_random_sampler_match_reference(name):
+    """zeroshot_clip_img_filter (:278-329) and random_sampler (:592-661): the oracle's ports against the reference's
+    outputs (the random sampler consumes Python's RNG exactly like the reference, so the seed pins the result)."""
+    import random
+    z, meta, cap, img, q = load_bank_case(name)
+    class_ids, labels = z["class_ids"], z["labels"]
+    paths, _ = make_paths(labels, class_ids)
+    raw = {"caption_features": cap, "image_features": img, "labels": class_ids[labels], "filepath": paths}
+    feats = so.transform_extracted_fea(raw)
+    row = {p: i for i, p in enumerate(paths)}
+    W = np.zeros((int(class_ids.max()) + 1, 512), np.float32)
+    W[class_ids] = q
+    zs, _ = so.zeroshot_clip_img_filter(feats, W)
+    assert {k: sorted(row[p] for p in v) for k, v in zs.items() if v} == meta["zeroshot"]
+    prompts = {str(int(class_ids[c])): {"mean": q[c]} for c in range(len(class_ids))}
+    dd, _, _ = so.remove_near_duplicates2(feats)
+    for tag, thr, th, use_dups in (("plain", 0.0, False, False), ("t2i", 0.2, False, True), ("tailhead", 0.2, True, False)):
+        random.seed(1234)
+        files, counts, sampled, filtered = so.verbatim_random_sampler(prompts, int(z["k"]), thr, feats,
+                                                                      duplicates_dict=dd if use_dups else None, tail_head=th)
+        ref = meta["random"][tag]
+        assert [row[p] for fl in files for p in fl] == ref["rows"], tag
+        assert counts == ref["counts"], tag
