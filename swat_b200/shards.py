@@ -112,18 +112,31 @@ class FlatShard:
                 "filepath": self.paths()}
 
     def to_device(self, device, rows: Optional[slice] = None, pinned_chunk_rows: int = 1 << 18):
-        """Rows -> HBM through a pinned staging buffer (page-locked copies run at full PCIe rate)."""
+        """Rows -> HBM (a rank of a sharded run passes its own row range).  Two pinned staging buffers: the host copy
+        of chunk i+1 out of the page cache overlaps the asynchronous H2D copy of chunk i, which runs at full PCIe rate
+        because the source is page-locked."""
         rows = rows or slice(0, self.n_rows)
         n = rows.stop - rows.start
         tdt = _TORCH[self.dtype]
         out_c = torch.empty(n, DIM, dtype=tdt, device=device)
         out_i = torch.empty(n, DIM, dtype=tdt, device=device) if self._img is not None else None
-        stage = torch.empty(min(pinned_chunk_rows, max(n, 1)), DIM, dtype=tdt, pin_memory=True)
-        for src, dst in ((self._cap, out_c), (self._img, out_i)):
-            if src is None:
-                continue
-            for s0 in range(0, n, stage.shape[0]):
-                m = min(stage.shape[0], n - s0)
-                stage[:m].copy_(self._tensor(src, slice(rows.start + s0, rows.start + s0 + m)))
-                dst[s0:s0 + m].copy_(stage[:m], non_blocking=False)
+        chunk = min(pinned_chunk_rows, max(n, 1))
+        stages = [torch.empty(chunk, DIM, dtype=tdt, pin_memory=True) for _ in range(2)]
+        busy = [None, None]
+        i = 0
+        with torch.cuda.device(device):
+            for src, dst in ((self._cap, out_c), (self._img, out_i)):
+                if src is None:
+                    continue
+                for s0 in range(0, n, chunk):
+                    m = min(chunk, n - s0)
+                    b = i & 1
+                    if busy[b] is not None:
+                        busy[b].synchronize()                  # the H2D copy that last read this buffer is done
+                    stages[b][:m].copy_(self._tensor(src, slice(rows.start + s0, rows.start + s0 + m)))
+                    dst[s0:s0 + m].copy_(stages[b][:m], non_blocking=True)
+                    busy[b] = torch.cuda.Event()
+                    busy[b].record()
+                    i += 1
+            torch.cuda.synchronize()
         return out_c, out_i

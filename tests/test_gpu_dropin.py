@@ -210,3 +210,34 @@ def test_zeroshot_filter_and_random_sampler(name):
         if name == "bank_bf16" or thr == 0.0:      # fp32 T2I scores print with 4 decimals; bf16-valued inputs make them exact
             assert hashlib.sha256(open(f"{tmp}/RND_sampled_list.txt", "rb").read()).hexdigest() == ref["sampled_sha"], tag
             assert hashlib.sha256(open(f"{tmp}/RND_filtered_list.txt", "rb").read()).hexdigest() == ref["filtered_sha"], tag
+
+
+@pytest.mark.parametrize("name,dt", [("bank_bf16", "bf16"), ("bank_f32", "f32")])
+def test_flat_shard_to_hbm_and_sampler(tmp_path, name, dt):
+    """Loader row of SURVEY 8f: mined .pth -> flat shard -> HBM (whole shard and a rank's row range, small staging
+    chunks so both pinned buffers cycle) -> same bytes, and the sampler on the loaded dict gives the reference rows."""
+    from swat_b200 import retrieval, shards
+    z, meta, cap, img, q, raw, prompts, paths, cmap = _case(name)
+    pth = str(tmp_path / "mined.pth")
+    shards.save_mined_pth(pth, raw["caption_features"], raw["image_features"], raw["labels"], paths)
+    shards.convert_pth_to_flat(pth, str(tmp_path / "flat"), dt)
+    fs = shards.FlatShard(str(tmp_path / "flat"))
+    want_c = raw["caption_features"].to(torch.bfloat16 if dt == "bf16" else torch.float32)
+    want_i = raw["image_features"].to(torch.bfloat16 if dt == "bf16" else torch.float32)
+    c, i = fs.to_device("cuda:0", pinned_chunk_rows=100)
+    assert torch.equal(c.cpu(), want_c) and torch.equal(i.cpu(), want_i)
+    c, i = fs.to_device("cuda:0", rows=slice(37, 411), pinned_chunk_rows=64)
+    assert torch.equal(c.cpu(), want_c[37:411]) and torch.equal(i.cpu(), want_i[37:411])
+    feats = retrieval.transform_extracted_fea(fs.as_mined_dict())
+    args = Namespace(dataset="synthetic", output_folder=str(tmp_path / "out"), prefix="T2T", bank_dtype=dt, caption_map_path="/nonexistent")
+    ms, nd = retrieval.t2t_ranked_t2i_tshd_sampler(args, logging.getLogger("t"), prompts, int(z["k"]), 0.0, feats)
+    assert nd == meta["counts"]["part"]["t2t_t2i"]
+    row = {p: r for r, p in enumerate(paths)}
+    S = so.score_matrix(cap, q)
+    ref_rows, pos = z["part_t2t_t2i_rows"], 0
+    for files, labs in zip(ms["file_list"], ms["label_list"]):
+        n = len(files)
+        c = int(np.nonzero(z["class_ids"] == int(labs[0]))[0][0])
+        assert_walk_equal([row[p] for p in files], ref_rows[pos:pos + n], lambda r, c=c: S[r, c], TIE_TOL, boundary_tol=1e-3,
+                          what=f"{name} flat shard class {c}")
+        pos += n
