@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import json
 import os
+import warnings
 from typing import Optional
 
 import numpy as np
@@ -89,7 +90,9 @@ class FlatShard:
 
     def _tensor(self, m, rows: Optional[slice] = None):
         a = m if rows is None else m[rows]
-        t = torch.from_numpy(np.ascontiguousarray(a) if rows is not None else np.asarray(a))
+        with warnings.catch_warnings():       # the mapping is read-only by design; the tensors are only ever read
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(np.ascontiguousarray(a) if rows is not None else np.asarray(a))
         return t.view(torch.bfloat16) if self.dtype == "bf16" else t
 
     def caption(self, rows: Optional[slice] = None) -> torch.Tensor:
