@@ -131,6 +131,7 @@ struct swat_job {
   int n_classes_alloc = 0;
   bool fresh = true;                  // no rows folded in since the last reset
   uint32_t* d_k_class = nullptr;      // [n_classes_alloc] per-class k_fetch, used when the depths differ
+  std::vector<uint32_t> h_k_class;    // what swat_job_set_class_depth last uploaded there (empty = unknown)
   cudaStream_t last_stream = nullptr;
 };
 
@@ -553,6 +554,7 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     SW_OK(acquire_job(ctx, q, kf, thr, cap, list_entries, &job));
     if (!dual && !k_class.empty()) {
       CU_OK(cudaMemcpyAsync(job->d_k_class, k_class.data(), static_cast<size_t>(C) * 4, cudaMemcpyHostToDevice, stream));
+      job->h_k_class.clear();
       job->st.k_class = job->d_k_class;
     }
     SW_OK(swat_job_reset(job, stream));
@@ -972,8 +974,11 @@ int32_t swat_job_set_class_depth(swat_job* job, const int32_t* h_depth, void* st
       return fail(SWAT_ERR_INVALID, "class depth %d of class %d outside [1, k_fetch=%u]", h_depth[c], c, job->st.k_fetch);
     d[c] = static_cast<uint32_t>(h_depth[c]);
   }
-  CU_OK(cudaMemcpyAsync(job->d_k_class, d.data(), static_cast<size_t>(C) * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
-  CU_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));     // d is pageable and dies here
+  if (d != job->h_k_class) {          // steady state: the same depths every step, nothing to upload and no sync
+    CU_OK(cudaMemcpyAsync(job->d_k_class, d.data(), static_cast<size_t>(C) * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    CU_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));     // d is pageable and dies here
+    job->h_k_class = d;
+  }
   job->st.k_class = job->d_k_class;
   return SWAT_OK;
 }
