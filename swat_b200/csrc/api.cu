@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -60,10 +62,13 @@ struct DevBuf {   // grow-only device workspace
   size_t cap = 0;
   int32_t ensure(size_t bytes) {
     if (bytes <= cap) return SWAT_OK;
+    const auto t0 = std::chrono::steady_clock::now();
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     CU_OK(cudaMalloc(&p, bytes));
     cap = bytes;
+    if (getenv("SWAT_DEBUG")) fprintf(stderr, "[swat] workspace grows to %zu bytes (%.2f ms)\n", bytes,
+                                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return SWAT_OK;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -92,6 +97,8 @@ struct swat_ctx {
   // workspaces for the whole-pipeline calls
   DevBuf w_scores, w_rows, w_counts, w_trunc, w_t2i, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
   DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
+  DevBuf w_swap[10];                // bank-swap escalation pass: two re-score stages
+  bool swap_pass = true;            // classes with fewer than k rows passing T2I: enumerate the passers from the image bank
   cudaStream_t copy_stream = nullptr, work_stream = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_used[3] = {nullptr, nullptr, nullptr};
@@ -333,6 +340,8 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
   if (e == cudaSuccess) e = cudaMalloc(&st.list_count, static_cast<size_t>(st.n_lists) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&st.flags, 16);
   if (e == cudaSuccess) e = cudaMalloc(&j->d_k_class, C * 4);
+  if (getenv("SWAT_DEBUG")) fprintf(stderr, "[swat] job allocated: C=%zu k_fetch=%d cap=%u lists=%u x %u entries (%.1f MB)\n", C, k_fetch, st.cap,
+                                    st.n_lists, st.list_cap, static_cast<double>(st.n_lists) * st.list_cap * 16 / 1e6);
   if (e != cudaSuccess) {
     swat_job_destroy(j);
     return fail(SWAT_ERR_CUDA, "job allocation failed (C=%zu, cap=%lld, list entries=%lld): %s", C, (long long)cap,
@@ -345,6 +354,13 @@ int32_t job_create_cap(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, fl
 // whole-pipeline calls reuse one job allocation per ctx as long as the sizes fit
 int32_t acquire_job(swat_ctx* ctx, const swat_queries* q, int32_t k_fetch, float thr, int64_t cap, int64_t list_entries, swat_job** out) {
   swat_job* j = ctx->cached_job;
+  struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~Timer() {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > 1.0 && getenv("SWAT_DEBUG")) fprintf(stderr, "[swat] acquire_job took %.2f ms\n", ms);
+    }
+  } timer;
   const int64_t private_lists = std::max(1, ctx->sm_count) * static_cast<int64_t>(kTcEpiWarps);
   if (j && j->n_classes_alloc >= q->C && j->st.cap >= cap && static_cast<int64_t>(j->st.list_cap) * private_lists >= list_entries) {
     if (k_fetch < 1 || k_fetch > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k_fetch must be in [1, %d], got %d", kMaxKFetch, k_fetch);
@@ -461,6 +477,97 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
                      float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream,
                      int32_t k_fetch_init, int depth);
 
+constexpr int32_t kSwapPass = kMaxKFetch + 1;    // k_fetch_init beyond the widest over-fetch: try the bank-swap pass, then the in-pass predicate
+constexpr int32_t kForceDual = kMaxKFetch + 2;   // ... go straight to the exact in-pass predicate
+
+// Bank-swap escalation pass.  A class whose T2T-ordered walk ran out of candidates has FEW rows passing the T2I
+// predicate (that is why k were not found among the best 4096 by T2T).  So enumerate the passers instead: scan the
+// IMAGE bank with the T2I threshold (minus a margin for tensor-core vs exact summation order) as the row threshold;
+// if fewer than 4096 rows of the class survive, that list holds every row that can pass the predicate.  Re-score
+// them exactly against both banks (T2I, then T2T with the T2T threshold) and sort by T2T: exactly the walk of
+// add_t2t_ranked_t2i_tshd_to_split (:507-527), at the cost of one tensor-core pass instead of the fp32 two-bank scan.
+// unresolved: classes with 4096 or more such rows (plenty of passers, all with a low T2T score) -- left to the caller.
+int32_t swap_pass(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
+                  float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream,
+                  std::vector<int>* unresolved) {
+  const int C = q->C;
+  const int32_t kf = kMaxKFetch;
+  const float margin = 1.0e-4f;
+  BankSrc sb = b;
+  sb.t2t = b.t2i;              // rows are ranked by their image score here
+  sb.t2i = nullptr;
+  int64_t cap = auto_cap(ctx, kf), list_entries = auto_list_entries(ctx, C, kf);
+  const size_t n = static_cast<size_t>(C) * kf;
+  SW_OK(ctx->w_scores.ensure(n * 4)); SW_OK(ctx->w_rows.ensure(n * 8)); SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
+  SW_OK(ctx->w_trunc.ensure(static_cast<size_t>(C) * 4));
+  for (int rounds = 0;; ++rounds) {
+    if (rounds > 8) return fail(SWAT_ERR_OVERFLOW, "bank-swap pass: retry budget exhausted");
+    swat_job* job = nullptr;
+    SW_OK(acquire_job(ctx, q, kf, t2i_thr - margin, cap, list_entries, &job));
+    SW_OK(swat_job_reset(job, stream));
+    CU_OK(cudaEventRecord(ctx->ev[0], stream));
+    SW_OK(scan_all(ctx, job, sb, false, 0.0f, stream));
+    CU_OK(cudaEventRecord(ctx->ev[1], stream));
+    CU_OK(launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(),
+                        ctx->w_trunc.as<int32_t>(), stream));
+    job->last_stream = stream;
+    ctx->launches += kSelectLaunches;
+    uint32_t flags = 0;
+    SW_OK(job_flags(job, &flags));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing[0] += ms;
+    ctx->timing[4] += 1;
+    if (!(flags & 3u)) break;
+    const int64_t limit = std::max<int64_t>(b.n_rows, 1 << 16);
+    if ((flags & 1u) && cap >= limit) return fail(SWAT_ERR_OVERFLOW, "class candidate overflow with cap >= n_rows");
+    if (flags & 1u) cap = std::min<int64_t>(cap * 4, limit);
+    if (flags & 2u) list_entries *= 4;
+  }
+  DevBuf* w = ctx->w_swap;
+  for (int i = 0; i < 2; ++i) {                 // two re-score stages: [0..4] exact T2I, [5..9] exact T2T
+    SW_OK(w[5 * i + 0].ensure(n * 4)); SW_OK(w[5 * i + 1].ensure(n * 8)); SW_OK(w[5 * i + 2].ensure(n * 4));
+    SW_OK(w[5 * i + 3].ensure(static_cast<size_t>(C) * 4)); SW_OK(w[5 * i + 4].ensure(static_cast<size_t>(C) * 4));
+  }
+  SW_OK(ctx->w_t2i.ensure(n * 4));
+  T2iArgs t;
+  memset(&t, 0, sizeof(t));
+  t.dtype = b.dtype;
+  t.queries = (b.dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
+  t.class_begin = q->d_class_begin;
+  t.reduce = q->reduce;
+  t.n_classes = C;
+  t.k = kf; t.k_fetch = kf;
+  t.img_rows = b.n_rows; t.img_row_base = row_offset; t.img_index = nullptr;
+  t.t2i_scratch = ctx->w_t2i.as<float>();
+  // stage A: exact image score of every candidate, keep those at or above the T2I threshold
+  t.img_bank = b.t2i; t.t2i_thr = t2i_thr;
+  t.cand_scores = ctx->w_scores.as<float>(); t.cand_rows = ctx->w_rows.as<int64_t>(); t.cand_counts = ctx->w_counts.as<int32_t>();
+  t.truncated = nullptr;
+  t.out_scores = w[0].as<float>(); t.out_rows = w[1].as<int64_t>(); t.out_t2i = w[2].as<float>(); t.out_counts = w[3].as<int32_t>();
+  t.incomplete = w[4].as<int32_t>();
+  CU_OK(launch_t2i_walk(t, stream));
+  // stage B: exact caption score of the survivors, keep those at or above the T2T threshold; their T2I score rides along
+  t.img_bank = b.t2t; t.t2i_thr = thr;
+  t.cand_scores = w[2].as<float>(); t.cand_rows = w[1].as<int64_t>(); t.cand_counts = w[3].as<int32_t>();
+  t.out_scores = w[5].as<float>(); t.out_rows = w[6].as<int64_t>(); t.out_t2i = w[7].as<float>(); t.out_counts = w[8].as<int32_t>();
+  t.incomplete = w[9].as<int32_t>();
+  CU_OK(launch_t2i_walk(t, stream));
+  // order by (T2T desc, row asc), keep k: the merge walk over one "shard" with the caption score as the key
+  SW_OK(ctx->w_keys.ensure(n * 8));
+  SW_OK(ctx->w_out_t2i.ensure(static_cast<size_t>(C) * k * 4));
+  CU_OK(launch_merge(w[7].as<float>(), w[6].as<int64_t>(), w[5].as<float>(), -INFINITY, w[8].as<int32_t>(), nullptr, 1, 0, C, kf, k,
+                     ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows, d_out_t2i ? d_out_t2i : ctx->w_out_t2i.as<float>(), d_out_counts,
+                     nullptr, stream));
+  ctx->launches += 6;
+  SW_OK(ensure_status(ctx, static_cast<size_t>(C) + 1));
+  CU_OK(cudaMemcpyAsync(ctx->h_status + 1, ctx->w_trunc.as<int32_t>(), static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+  CU_OK(cudaStreamSynchronize(stream));
+  unresolved->clear();
+  for (int c = 0; c < C; ++c) if (ctx->h_status[1 + c] != 0) unresolved->push_back(c);
+  return SWAT_OK;
+}
+
 // Targeted escalation: re-run only the classes whose T2I walk could not be proven exact, with a
 // wider over-fetch (and finally the exact in-pass predicate), then splice their rows into the result.
 int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
@@ -519,8 +626,19 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
   if (depth == 0) for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
   int32_t k_fetch = k;
   bool dual = false;          // exact in-pass predicate fallback
+  if (want_t2i && k_fetch_init == kSwapPass && ctx->swap_pass && !b.host) {
+    // escalation beyond the widest over-fetch: enumerate the T2I passers from the image bank (one tensor-core pass);
+    // classes with too many of them for that fall through to the exact in-pass predicate
+    std::vector<int> unresolved;
+    SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, &unresolved));
+    if (!unresolved.empty())
+      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
+                             d_out_counts, stream, depth));
+    q->last_k_fetch = kMaxKFetch;
+    return SWAT_OK;
+  }
   if (want_t2i) {
-    if (k_fetch_init > kMaxKFetch) dual = true;   // escalation beyond the widest over-fetch
+    if (k_fetch_init > kMaxKFetch) dual = true;   // exact in-pass predicate
     else if (k_fetch_init > 0) k_fetch = k_fetch_init;
     // Host banks stream over PCIe (~20x slower than the scan): a second pass costs far more than a
     // wider first one, so over-fetch 4k there; HBM-resident banks start at 2k.
@@ -719,6 +837,15 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       break;
     }
     k_class.clear();
+    if (next > kMaxKFetch && ctx->swap_pass && !b.host && depth < 3) {
+      std::vector<int> unresolved;
+      SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, &unresolved));
+      if (!unresolved.empty())
+        SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
+                               d_out_counts, stream, depth));
+      k_fetch = kMaxKFetch;
+      break;
+    }
     if (next > kMaxKFetch) dual = true;
     else {
       k_fetch = next;
@@ -787,7 +914,9 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_t2i, &ctx->w_incomplete, &ctx->w_keys,
                     &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
-                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot};
+                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot,
+                    &ctx->w_swap[0], &ctx->w_swap[1], &ctx->w_swap[2], &ctx->w_swap[3], &ctx->w_swap[4], &ctx->w_swap[5], &ctx->w_swap[6],
+                    &ctx->w_swap[7], &ctx->w_swap[8], &ctx->w_swap[9]};
   for (DevBuf* b : bufs) b->release();
   if (ctx->cached_job) swat_job_destroy(ctx->cached_job);
   if (ctx->esc_q) swat_queries_destroy(ctx->esc_q);
@@ -812,6 +941,7 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   else if (n == "overfetch") ctx->overfetch = static_cast<int>(value);
   else if (n == "host_chunk_rows") ctx->host_chunk_rows = value;
   else if (n == "unit_plan") ctx->unit_plan = value != 0;
+  else if (n == "swap_pass") ctx->swap_pass = value != 0;
   else if (n == "bootstrap_rows") ctx->bootstrap_rows = std::max<int64_t>(0, value);
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
   return SWAT_OK;

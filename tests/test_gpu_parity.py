@@ -225,19 +225,60 @@ def test_overflow_retry_and_t2i_escalation(lib):
     ctx.close()
 
 
+def test_bank_swap_escalation(lib):
+    """Classes with fewer than k rows passing T2I: after the over-fetch ladder the pipeline enumerates the passers
+    from the IMAGE bank (one tensor-core pass + exact re-scores) instead of the fp32 two-bank scan.  Class 3 has ~60
+    passers (resolved by the swap pass), class 5 has 5000 passers with noise captions (more than the swap pass can
+    enumerate: falls through to the in-pass predicate), every other class has none."""
+    bank = _rand_unit(60_000, 71, torch.bfloat16)
+    img = _rand_unit(60_000, 72, torch.bfloat16)
+    q = _rand_unit(24, 73, torch.bfloat16)
+    img[1000:60_000:997] = q[3]
+    img[7:60_000:12] = q[5]
+    bf, imf, qf = bank.float().numpy(), img.float().numpy(), q.float().numpy()
+    S = so.score_matrix(bf, qf)
+    o = so.topk_walk(bf, qf, 400, 0.0, t2i_bank=imf, t2i_threshold=0.25)
+    assert 0 < int(o[3][3]) < 400 and int(o[3][5]) == 400 and int(o[3].sum()) == int(o[3][3]) + 400
+    scans = {}
+    for swap in (1, 0):
+        ctx = lib.Context(0, swap_pass=swap)
+        qs = lib.Queries(ctx, q.float())
+        for rep in range(2):          # second call: the remembered per-class depths send the short classes straight to the swap pass
+            g = lib.topk(ctx, qs, bank.cuda(), 400, 0.0, t2i_bank=img.cuda(), t2i_threshold=0.25)
+            check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=f"swap={swap} rep={rep}")
+            I = so.score_matrix(imf, qf)
+            for c in (3, 5):
+                n = int(g[3][c]); r = g[1][c, :n].cpu().numpy()
+                np.testing.assert_allclose(g[2][c, :n].cpu().numpy(), I[r, c], atol=SCORE_TOL)
+                assert np.all(I[r, c] >= 0.25 - 1e-6)
+        scans[swap] = ctx.last_timing()["scan_launches"]
+        qs.close(); ctx.close()
+    assert scans[1] >= 2 and scans[0] >= 2
+
+
 def test_host_pipeline_equals_resident(lib, ctx2):
     from swat_b200 import synth
     qc, queries, _ = synth.make_queries(40, 1, seed=31, dtype=torch.bfloat16)
     cap, img, labels = synth.make_bank(70_000, qc, seed=31, dtype=torch.bfloat16, rho=0.2, tie_block=200, chunk=1 << 16)
     qs = lib.Queries(ctx2, queries.float())
     ctx2.set_option("host_chunk_rows", 8192)
+    capf, imgf, qf = cap.float().numpy(), img.float().numpy(), queries.float().numpy()
+    S = so.score_matrix(capf, qf)
     for t2i_dev, t2i_host in ((None, None), (img.cuda(), img.pin_memory())):
         r = lib.topk(ctx2, qs, cap.cuda(), 300, 0.0, t2i_bank=t2i_dev, row_offset=1000)
         h = lib.topk_host(ctx2, qs, cap.pin_memory(), 300, 0.0, t2i_bank=t2i_host, row_offset=1000)
-        assert torch.equal(r[1].cpu(), h[1]) and torch.equal(r[3].cpu(), h[3])
-        assert torch.equal(r[0].cpu(), h[0])
-        if t2i_dev is not None:
-            assert torch.equal(r[2].cpu(), h[2])
+        assert torch.equal(r[3].cpu(), h[3])
+        if t2i_dev is None:
+            assert torch.equal(r[1].cpu(), h[1]) and torch.equal(r[0].cpu(), h[0])
+        else:
+            # fewer than k rows pass T2I in every class here: the resident pipeline ends in the bank-swap pass (exact
+            # re-scores), the host pipeline in the in-pass predicate (fp32 FMA) -- same rows up to near-ties, scores to 1e-6
+            o = so.topk_walk(capf, qf, 300, 0.0, t2i_bank=imgf, t2i_threshold=0.25)
+            for g in (r, h):
+                rows = torch.where(g[1] >= 0, g[1] - 1000, g[1])
+                check_result(g[0], rows, g[3], o[0], o[1], o[3], S, TIE_TOL, what="host vs resident")
+            np.testing.assert_allclose(r[0].cpu().numpy(), h[0].numpy(), atol=2e-6)
+            np.testing.assert_allclose(r[2].cpu().numpy(), h[2].numpy(), atol=2e-6)
     ctx2.set_option("host_chunk_rows", 1 << 18)
 
 
