@@ -254,6 +254,19 @@ def test_bank_swap_escalation(lib):
         scans[swap] = ctx.last_timing()["scan_launches"]
         qs.close(); ctx.close()
     assert scans[1] >= 2 and scans[0] >= 2
+    # partitioned data (a row is eligible for its own class only): 3 classes x 20 000 rows, class 1 has 50 passers
+    lab = np.repeat(np.arange(3), 20_000).astype(np.int32)
+    img2 = _rand_unit(60_000, 74, torch.bfloat16)
+    q2 = q[:3].clone()
+    img2[20_000:40_000:400] = q2[1]
+    bf2, imf2, qf2 = bank.float().numpy(), img2.float().numpy(), q2.float().numpy()
+    o = so.topk_walk(bf2, qf2, 100, 0.0, t2i_bank=imf2, t2i_threshold=0.25, row_labels=lab)
+    assert int(o[3][0]) == 0 and int(o[3][2]) == 0 and 0 < int(o[3][1]) < 100
+    ctx = lib.Context(0)
+    qs = lib.Queries(ctx, q2.float())
+    g = lib.topk(ctx, qs, bank.cuda(), 100, 0.0, t2i_bank=img2.cuda(), t2i_threshold=0.25, row_class=torch.from_numpy(lab).cuda())
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], so.score_matrix(bf2, qf2), TIE_TOL, what="partitioned swap")
+    qs.close(); ctx.close()
 
 
 def test_host_pipeline_equals_resident(lib, ctx2):
