@@ -171,7 +171,11 @@ int32_t swat_near_duplicates(swat_ctx* ctx, const void* d_bank, int32_t dtype, i
 /* t2t_ranked_sampler (:724-771) when d_t2i_bank == NULL, t2t_ranked_t2i_tshd_sampler (:774-825)
  * otherwise, for all classes at once.  Outputs [C,k] (d_out_t2i nullable), rows are
  * row_offset + local row.  Handles candidate-buffer overflow and T2I over-fetch escalation
- * internally (falls back to the exact in-pass predicate).  Synchronises. */
+ * internally: deeper over-fetch for the classes that need it, then a pass over the image bank that
+ * enumerates the rows able to pass T2I (classes with few of them), finally the exact in-pass
+ * predicate.  Bank rows and queries are cosine features, L2-normalised as extract_mined_feature.py:121,181
+ * and utils/features.py:30-31 produce them (the image-bank pass allows 1e-4 between tensor-core and exact
+ * scores).  Synchronises. */
 int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, const void* d_t2i_bank,
                   int32_t dtype, int64_t n_rows, int64_t row_offset, int32_t k, float t2t_threshold,
                   float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude,
