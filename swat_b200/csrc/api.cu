@@ -108,9 +108,11 @@ struct swat_ctx {
   size_t h_status_cap = 0;
   swat_job* cached_job = nullptr;   // job buffers are reused across whole-pipeline calls
   // last sub-query set built for a targeted escalation (repeated calls hit the same classes)
-  swat_queries* esc_q = nullptr;
-  const swat_queries* esc_parent = nullptr;
-  std::vector<int> esc_classes;
+  // sub-query sets of the classes being escalated, kept across calls (two slots: deeper over-fetch / bank-swap pass)
+  swat_queries* esc_q[2] = {nullptr, nullptr};
+  const swat_queries* esc_parent[2] = {nullptr, nullptr};
+  std::vector<int> esc_classes[2];
+  int esc_next = 0;
   DevBuf e_bufs[4][4];   // per escalation depth: scores, rows, t2i, counts of the sub-run
 };
 
@@ -586,12 +588,13 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
   if (depth > 3) return fail(SWAT_ERR_INCOMPLETE, "escalation nested too deep");
   swat_queries* sub = nullptr;
   const bool cached = depth == 0;   // nested levels own their sub-query set: the cache entry is in use above them
-  if (cached && ctx->esc_q && ctx->esc_parent == q && ctx->esc_classes == classes) {
-    sub = ctx->esc_q;
-  } else {
-    if (cached && ctx->esc_q) { swat_queries_destroy(ctx->esc_q); ctx->esc_q = nullptr; }
+  for (int i = 0; cached && i < 2 && !sub; ++i)
+    if (ctx->esc_q[i] && ctx->esc_parent[i] == q && ctx->esc_classes[i] == classes) sub = ctx->esc_q[i];
+  if (!sub) {
+    const int slot = ctx->esc_next;
+    if (cached && ctx->esc_q[slot]) { swat_queries_destroy(ctx->esc_q[slot]); ctx->esc_q[slot] = nullptr; }
     SW_OK(swat_queries_create(ctx, hq.data(), static_cast<int32_t>(coq.size()), coq.data(), n, q->reduce, &sub));
-    if (cached) { ctx->esc_q = sub; ctx->esc_parent = q; ctx->esc_classes = classes; }
+    if (cached) { ctx->esc_q[slot] = sub; ctx->esc_parent[slot] = q; ctx->esc_classes[slot] = classes; ctx->esc_next = slot ^ 1; }
   }
   DevBuf &o_s = ctx->e_bufs[depth][0], &o_r = ctx->e_bufs[depth][1], &o_t = ctx->e_bufs[depth][2], &o_c = ctx->e_bufs[depth][3];
   int32_t rc = o_s.ensure(static_cast<size_t>(n) * k * 4);
@@ -799,10 +802,11 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       CU_OK(cudaMemcpyAsync(d_out_counts, t.out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, stream));
     }
     CU_OK(cudaEventRecord(ctx->ev[4], stream));
-    SW_OK(ensure_status(ctx, static_cast<size_t>(C) + 1));
+    SW_OK(ensure_status(ctx, 2 * static_cast<size_t>(C) + 1));
     ctx->h_status[0] = 0;
     if (late_check) CU_OK(cudaMemcpyAsync(ctx->h_status, job->st.flags, 4, cudaMemcpyDeviceToHost, stream));
     CU_OK(cudaMemcpyAsync(ctx->h_status + 1, t.incomplete, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaMemcpyAsync(ctx->h_status + 1 + C, t.out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
     CU_OK(cudaStreamSynchronize(stream));
     const int32_t* inc = ctx->h_status + 1;
     {
@@ -827,13 +831,28 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     if (b.row_class == nullptr && static_cast<int>(bad.size()) < C) {
       int32_t from = k_fetch;                           // the escalated classes were walked to this depth
       if (!k_class.empty()) { from = kMaxKFetch; for (int c : bad) from = std::min<int32_t>(from, static_cast<int32_t>(k_class[c])); }
-      const int32_t nxt = (from < kMaxKFetch) ? std::min(kMaxKFetch, from * 2) : kMaxKFetch + 1;
-      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, bad, nxt, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
-                             stream, depth));
-      if (depth == 0 && ctx->overfetch == 0 && q->last_k_fetch > 0) {      // remember the depth that worked, per class
-        if (static_cast<int>(q->kclass_hint.size()) != C) q->kclass_hint.assign(C, 0);
-        for (int c : bad) q->kclass_hint[c] = std::max(q->kclass_hint[c], q->last_k_fetch);
+      const int32_t nxt = (from < kMaxKFetch) ? std::min(kMaxKFetch, from * 2) : kSwapPass;
+      // A class that accepted p of the d candidates walked so far needs about d*k/p of them.  Where that is beyond the
+      // widest over-fetch the ladder would only waste passes: those classes go straight to the bank-swap pass.
+      std::vector<int> deeper, few;
+      const int32_t* accepted = ctx->h_status + 1 + C;           // copied out before any nested call reuses the buffer
+      for (int c : bad) {
+        const int64_t d = k_class.empty() ? k_fetch : static_cast<int64_t>(k_class[c]);
+        const int64_t p = accepted[c];
+        const bool hopeless = p <= 0 || d * k / p > 2 * kMaxKFetch;   // factor 2: borderline classes still try the ladder
+        (hopeless && nxt != kSwapPass && ctx->swap_pass && !b.host ? few : deeper).push_back(c);
       }
+      if (!deeper.empty()) {
+        SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, deeper, nxt, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
+                               stream, depth));
+        if (depth == 0 && ctx->overfetch == 0 && q->last_k_fetch > 0) {      // remember the depth that worked, per class
+          if (static_cast<int>(q->kclass_hint.size()) != C) q->kclass_hint.assign(C, 0);
+          for (int c : deeper) q->kclass_hint[c] = std::max(q->kclass_hint[c], q->last_k_fetch);
+        }
+      }
+      if (!few.empty())      // no depth hint for these: walking them deeper in the main pass would not help
+        SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, few, kSwapPass, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
+                               stream, depth));
       break;
     }
     k_class.clear();
@@ -919,7 +938,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
                     &ctx->w_swap[7], &ctx->w_swap[8], &ctx->w_swap[9]};
   for (DevBuf* b : bufs) b->release();
   if (ctx->cached_job) swat_job_destroy(ctx->cached_job);
-  if (ctx->esc_q) swat_queries_destroy(ctx->esc_q);
+  for (int i = 0; i < 2; ++i) if (ctx->esc_q[i]) { swat_queries* e = ctx->esc_q[i]; ctx->esc_q[i] = nullptr; swat_queries_destroy(e); }
   for (auto& lvl : ctx->e_bufs) for (auto& bf : lvl) bf.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -1068,7 +1087,7 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
 
 int32_t swat_queries_destroy(swat_queries* q) {
   if (!q) return SWAT_OK;
-  if (q->ctx->esc_parent == q) q->ctx->esc_parent = nullptr;
+  for (int i = 0; i < 2; ++i) if (q->ctx->esc_parent[i] == q) q->ctx->esc_parent[i] = nullptr;
   cudaSetDevice(q->ctx->device);
   cudaFree(q->d_arena);
   delete q;

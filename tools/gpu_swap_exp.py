@@ -11,10 +11,10 @@ q = queries.float().clone()
 for c in (7, 99):                                  # two classes whose prompt matches nothing in the bank
     q[c] = torch.nn.functional.normalize(torch.randn(512, generator=g), dim=0)
 q = q.to(torch.bfloat16).float()
-for swap in (1,):
+for swap in (1, 0):
     ctx = _lib.Context(0, swap_pass=swap)
     qs = _lib.Queries(ctx, q)
-    for rep in range(5):
+    for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         s, r, t, c = _lib.topk(ctx, qs, cap, 500, 0.0, t2i_bank=img)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
