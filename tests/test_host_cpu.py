@@ -130,3 +130,32 @@ def test_bench_reference_arm_line_shape():
     line = json.loads(out.stdout.strip().split("\n")[-1])
     assert line["impl"] == "reference" and line["unit"] == "rows/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_random_sampler_threshold0_is_host_only(tmp_path):
+    """random_sampler with threshold 0 (the way sampling() calls it, :1517-1526) involves no scores at all: the mirror
+    must reproduce the reference's shuffle + walk and the bytes of its two diagnostic files without touching a GPU."""
+    import hashlib, logging, pickle, random
+    from argparse import Namespace
+    import torch
+    from swat_b200 import retrieval
+    from tests.golden_util import load_bank_case, make_paths
+    for name in ("bank_bf16", "bank_f32"):
+        z, meta, cap, img, q = load_bank_case(name)
+        class_ids, labels = z["class_ids"], z["labels"]
+        paths, cmap = make_paths(labels, class_ids)
+        raw = {"caption_features": torch.from_numpy(cap), "image_features": torch.from_numpy(img),
+               "labels": torch.from_numpy(class_ids[labels]), "filepath": paths}
+        feats = retrieval.transform_extracted_fea(raw)
+        prompts = {str(class_ids[c]): {"mean": torch.from_numpy(q[c])} for c in range(len(class_ids))}
+        cm = str(tmp_path / f"{name}.map")
+        with open(cm, "wb") as f:
+            pickle.dump(cmap, f)
+        random.seed(1234)
+        args = Namespace(dataset="synthetic", output_folder=str(tmp_path / name), prefix="RND", caption_map_path=cm)
+        ms, nd = retrieval.random_sampler(args, logging.getLogger("t"), prompts, int(z["k"]), 0.0, feats)
+        ref = meta["random"]["plain"]
+        row = {p: i for i, p in enumerate(paths)}
+        assert [row[p] for fl in ms["file_list"] for p in fl] == ref["rows"] and nd == ref["counts"]
+        assert hashlib.sha256(open(f"{args.output_folder}/RND_sampled_list.txt", "rb").read()).hexdigest() == ref["sampled_sha"]
+        assert hashlib.sha256(open(f"{args.output_folder}/RND_filtered_list.txt", "rb").read()).hexdigest() == ref["filtered_sha"]
