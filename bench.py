@@ -312,8 +312,9 @@ def run_ours(a, rank, world, local_rank):
             # walk), then one all-gather of the [C,k] results and an associative merge
             s, r, t, c = _lib.topk_host(ctx, qs, h_cap, k, 0.0, t2i_bank=h_img, t2i_threshold=0.25, row_offset=row_offset)
             tm = ctx.last_timing()
-            local = (s.cuda(dev), r.cuda(dev), None if t is None else t.cuda(dev), c.cuda(dev), torch.zeros_like(c).cuda(dev))
-            res_m = sdist.gather_merge(local, k, float("-inf"), world, ctx=ctx)
+            local = (s.cuda(dev), r.cuda(dev), None if t is None else t.cuda(dev), c.cuda(dev),
+                     torch.full((c.numel(),), float("-inf"), dtype=torch.float32, device=dev))      # exact local walks: no limit
+            res_m = sdist.gather_merge(local, k, world, ctx=ctx)
             out = [x.cpu() for x in res_m[:4] if x is not None]
             return res_m, tm["h2d_bytes"] + sum(x.numel() * x.element_size() for x in local if x is not None), \
                 tm["d2h_bytes"] + sum(x.numel() * x.element_size() for x in out)

@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define SWAT_DIM 512
-#define SWAT_VERSION 100 /* 0.1.0 */
+#define SWAT_VERSION 200 /* 0.2.0 */
 
 typedef enum {
   SWAT_OK = 0,
@@ -51,7 +51,9 @@ typedef enum { SWAT_BF16 = 0, SWAT_F32 = 1 } swat_dtype;
  * MAX / MIN: i2i_similarity_p2p modes (:377-385); MAX is the north star's "max over synonyms". */
 typedef enum { SWAT_REDUCE_NONE = 0, SWAT_REDUCE_MEAN = 1, SWAT_REDUCE_MAX = 2, SWAT_REDUCE_MIN = 3 } swat_reduce;
 
-/* which scan kernel: AUTO = tcgen05 kernel for bf16 banks, SIMT fp32-FMA kernel for fp32 banks. */
+/* which scan kernel: AUTO = the tcgen05 kernel (bf16 banks natively; fp32 banks are converted to bf16 on the fly by
+ * converter warps and every candidate is re-scored exactly in fp32 afterwards); SIMT = the fp32-FMA kernel (any
+ * dtype, the in-pass T2I predicate, and the on-device checker). */
 typedef enum { SWAT_ENGINE_AUTO = 0, SWAT_ENGINE_TC = 1, SWAT_ENGINE_SIMT = 2 } swat_engine;
 
 typedef struct swat_ctx swat_ctx;
@@ -66,7 +68,8 @@ int32_t swat_ctx_create(int32_t device, swat_ctx** out);
 int32_t swat_ctx_destroy(swat_ctx* ctx);
 /* tuning knobs (all optional): "cta_group" (1|2, before swat_queries_create), "max_ctas", "cand_cap"
  * (per-class candidates kept after the final threshold), "list_entries" (total survivor-list entries),
- * "overfetch" (first k_fetch of the T2I walk), "host_chunk_rows"; 0 = automatic */
+ * "overfetch" (first k_fetch of the T2I walk), "host_chunk_rows"; 0 = automatic.  Switches (default 1): "unit_plan",
+ * "swap_pass", "zero_copy" (host pipeline reads candidates' rows from pinned banks in place), "bootstrap_rows" */
 int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value);
 /* counters since ctx creation: kernels launched by this library (bench.py's gpu_launches claim) */
 int64_t swat_ctx_launch_count(const swat_ctx* ctx);
@@ -116,30 +119,40 @@ int32_t swat_job_export_flags(swat_job* job, int32_t* d_flags, void* stream);
 int32_t swat_job_status(swat_job* job, int32_t* overflowed);
 int32_t swat_job_destroy(swat_job* job);
 
-/* ---- T2I stage: cal_t2i_similarity (:335-353) + add_t2t_ranked_t2i_tshd_to_split (:492-540) ---- */
-/* For the candidates of each class (walk order), score the image row against the class queries,
- * keep rows with t2i >= t2i_threshold and stop at k.  d_img_bank row r is shard row
- * img_row_base + r; with d_img_index != NULL the bank is a compact gather and candidate j of class c
- * reads bank row d_img_index[c*k_fetch + j].  d_incomplete [C]: 1 = fewer than k accepted although
- * the candidate list was truncated (caller must escalate k_fetch). */
-int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_bank, int32_t dtype,
-                      int64_t img_rows, int64_t img_row_base, const int64_t* d_img_index,
-                      const float* d_cand_scores, const int64_t* d_cand_rows, const int32_t* d_cand_counts,
-                      const int32_t* d_truncated, int32_t k_fetch, int32_t k, float t2i_threshold,
-                      float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts,
-                      int32_t* d_incomplete, void* stream);
+/* ---- exact re-score + accept walk: add_to_split (:439-482), cal_t2i_similarity (:335-353) +
+ *      add_t2t_ranked_t2i_tshd_to_split (:492-540) ------------------------------------------------------------- */
+/* The scan kernels rank rows by an APPROXIMATE score: tensor-core accumulation order for bf16 banks, bf16-rounded rows
+ * and queries for fp32 banks.  *eps bounds |approximate - canonical| for the given bank dtype and engine
+ * (SWAT_ENGINE_AUTO = what swat_job_scan would pick). */
+int32_t swat_scan_eps(const swat_queries* q, int32_t dtype, int32_t engine, float* eps);
+/* Candidates of each class ([C,k_fetch] as swat_job_select writes them): re-score every candidate with the canonical
+ * fixed-order fp32 dot against d_t2t_bank (and d_aux_bank when given: the predicate bank, e.g. the image rows), re-sort
+ * on (exact score desc, row asc) -- the reference's stable sorted(..., reverse=True) (:754, :807) -- and walk:
+ * accept rows with exact >= t2t_threshold and aux >= aux_threshold, stop at k.  Bank row r is the row whose id in
+ * d_cand_rows is bank_row_base + r.  A truncated list vouches only for rows scoring above (approximate score of its
+ * last candidate + eps).  d_out_limit [C] (nullable): -inf = the class is proven exact, else rows scoring <= limit
+ * may be missing; d_incomplete [C] (nullable): 1 = fewer than k accepted and not proven (escalate k_fetch).
+ * q_aux (nullable = q): the predicate's own query set over the same classes -- the few-shot image prompts of
+ * t2t_rank_i2t_tshd_sampler / t2t_rank_i2i_tshd_sampler (:869, :929). */
+int32_t swat_rescore_walk(swat_ctx* ctx, const swat_queries* q, const swat_queries* q_aux,
+                          const void* d_t2t_bank, const void* d_aux_bank,
+                          int32_t dtype, int64_t bank_rows, int64_t bank_row_base,
+                          const float* d_cand_scores, const int64_t* d_cand_rows, const int32_t* d_cand_counts,
+                          const int32_t* d_truncated, int32_t k_fetch, int32_t k, float t2t_threshold,
+                          float aux_threshold, float eps, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
+                          int32_t* d_out_counts, float* d_out_limit, int32_t* d_incomplete, void* stream);
 
 /* ---- multi-GPU: merge after the single NCCL gather ------------------------------ */
-/* d_scores/d_rows/d_aux: [G,C,k_in] gathered shard candidate lists (rows already global, < 2^32),
- * d_counts [G,C], d_truncated [G,C] (nullable).  shard_stride_bytes == 0: the arrays are contiguous;
+/* d_scores/d_rows/d_aux: [G,C,k_in] gathered per-shard walk results (canonical scores; rows global, < 2^32),
+ * d_counts [G,C], d_limit [G,C] (nullable): shard g vouches only for rows scoring above d_limit[g][c] (-inf = its
+ * list is complete; what swat_rescore_walk wrote).  shard_stride_bytes == 0: the arrays are contiguous;
  * otherwise shard g of EVERY array starts g * shard_stride_bytes after shard 0 (the arrays are slices
  * of one packed per-rank buffer, as an all-gather delivers them).  Keeps, per class, the k_out best entries under
- * (score desc, row asc) among those with aux >= aux_threshold (d_aux == NULL: no predicate) -- the
- * reference's accept walk (:507-527) run over the union of the shards' candidates.
- * d_incomplete [C] (nullable): 1 = the result reaches below the last candidate of a truncated shard
- * (rows that shard never reported could belong in it): re-run the shards with a larger k_in. */
+ * (score desc, row asc) among those with aux >= aux_threshold (d_aux == NULL: no predicate).
+ * d_incomplete [C] (nullable): 1 = the result reaches down to some shard's limit (rows that shard never reported
+ * could belong in it): re-run the shards with a larger k_fetch. */
 int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux,
-                        const int32_t* d_counts, const int32_t* d_truncated, int32_t n_shards,
+                        const int32_t* d_counts, const float* d_limit, int32_t n_shards,
                         int64_t shard_stride_bytes, int32_t n_classes,
                         int32_t k_in, int32_t k_out, float aux_threshold, float* d_out_scores, int64_t* d_out_rows,
                         float* d_out_aux, int32_t* d_out_counts, int32_t* d_incomplete, void* stream);
@@ -149,6 +162,12 @@ int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_r
  * fast path never materialises this matrix. */
 int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype,
                           int64_t n_rows, float* d_out, int32_t engine, void* stream);
+
+/* Partitioned data (one class per row, transform_extracted_fea :1387-1415): d_out[i] = canonical score of row i against
+ * the queries of ITS OWN class d_row_class[i] (-inf where that is < 0) -- t2t_similarity / cal_t2i_similarity of every
+ * class over its own rows in one pass (:752, :804-806).  Feeds the walk diagnostics (filtered_list.txt :463-469). */
+int32_t swat_score_rows(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows,
+                        const int32_t* d_row_class, float* d_out, void* stream);
 
 /* ---- exclusion-set producer: zeroshot_clip_img_filter (:278-329) --------------------------------- */
 /* d_pred [n_rows] i32: argmax over the class scores of every row (lowest class on ties) -- the prediction of the
@@ -170,7 +189,8 @@ int32_t swat_near_duplicates(swat_ctx* ctx, const void* d_bank, int32_t dtype, i
 /* ---- whole pipeline on HBM-resident banks ------------------------------------------------------ */
 /* t2t_ranked_sampler (:724-771) when d_t2i_bank == NULL, t2t_ranked_t2i_tshd_sampler (:774-825)
  * otherwise, for all classes at once.  Outputs [C,k] (d_out_t2i nullable), rows are
- * row_offset + local row.  Handles candidate-buffer overflow and T2I over-fetch escalation
+ * row_offset + local row (row_offset + n_rows < 2^32 - 1).  Scores are canonical (see swat_rescore_walk): identical
+ * whichever engine, shard count or escalation path produced them.  Handles candidate-buffer overflow and over-fetch escalation
  * internally: deeper over-fetch for the classes that need it, then a pass over the image bank that
  * enumerates the rows able to pass T2I (classes with few of them), finally the exact in-pass
  * predicate.  Bank rows and queries are cosine features, L2-normalised as extract_mined_feature.py:121,181

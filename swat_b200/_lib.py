@@ -23,8 +23,8 @@ DIM = 512
 EXPORTS = [
     "swat_version", "swat_last_error", "swat_ctx_create", "swat_ctx_destroy", "swat_ctx_set_option",
     "swat_ctx_launch_count", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
-    "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_export_flags", "swat_job_status", "swat_job_destroy", "swat_t2i_walk", "swat_merge_topk",
-    "swat_scores_dense", "swat_zeroshot_predict", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
+    "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_export_flags", "swat_job_status", "swat_job_destroy", "swat_scan_eps", "swat_rescore_walk", "swat_merge_topk",
+    "swat_scores_dense", "swat_score_rows", "swat_zeroshot_predict", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
 ]
 
 
@@ -66,9 +66,11 @@ def load() -> C.CDLL:
         "swat_job_export_flags": [vp, vp, vp],
         "swat_job_status": [vp, C.POINTER(i32)],
         "swat_job_destroy": [vp],
-        "swat_t2i_walk": [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
+        "swat_scan_eps": [vp, i32, i32, C.POINTER(f32)],
+        "swat_rescore_walk": [vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
         "swat_merge_topk": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp],
         "swat_scores_dense": [vp, vp, vp, i32, i64, vp, i32, vp],
+        "swat_score_rows": [vp, vp, vp, i32, i64, vp, vp, vp],
         "swat_zeroshot_predict": [vp, vp, vp, i32, i64, vp, i32, vp],
         "swat_near_duplicates": [vp, vp, i32, i64, vp, vp, i32, i32, f32, vp, vp],
         "swat_topk": [vp, vp, vp, vp, i32, i64, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
@@ -192,6 +194,9 @@ class Queries:
         for sub in self.__dict__.get("_subsets", {}).values():
             sub.close()
         self.__dict__["_subsets"] = {}
+        for job in self.__dict__.get("_job_cache", {}).values():      # swat_b200.dist keeps its streaming jobs here
+            job.close()
+        self.__dict__["_job_cache"] = {}
         if self._h:
             load().swat_queries_destroy(self._h)
             self._h = C.c_void_p()
@@ -285,6 +290,17 @@ def scores_dense(ctx: Context, queries: Queries, bank: torch.Tensor, engine="aut
     return out
 
 
+def score_rows(ctx: Context, queries: Queries, bank: torch.Tensor, row_class: torch.Tensor) -> torch.Tensor:
+    """``[N]`` canonical score of every row against the queries of its own class (``row_class`` int32, -1 = none)."""
+    _bank_ok(bank, "bank", True)
+    if row_class.dtype != torch.int32 or row_class.numel() != bank.shape[0] or not row_class.is_cuda:
+        raise ValueError("row_class must be a CUDA int32 tensor with one entry per row")
+    out = torch.empty(bank.shape[0], dtype=torch.float32, device=bank.device)
+    _check(load().swat_score_rows(ctx._h, queries._h, _ptr(bank), _dtype_code(bank), int(bank.shape[0]), _ptr(row_class), _ptr(out),
+                                  _stream(ctx.device)))
+    return out
+
+
 def zeroshot_predict(ctx: Context, queries: Queries, bank: torch.Tensor, engine="auto") -> torch.Tensor:
     """``[N]`` int32: argmax over the class scores of every row (the zero-shot head's prediction)."""
     _bank_ok(bank, "bank", True)
@@ -361,35 +377,54 @@ def _out_ok(t: torch.Tensor, shape, dtype):
         raise ValueError(f"output tensor must be a contiguous CUDA {dtype} tensor of shape {tuple(shape)}")
 
 
-def t2i_walk(ctx: Context, queries: Queries, img_bank: torch.Tensor, cand_scores, cand_rows, cand_counts, truncated, k: int,
-             t2i_threshold: float = 0.25, img_row_base: int = 0, out=None):
-    """T2I re-score of the candidates + accept walk.  ``out = (scores, rows, t2i, counts)`` writes into caller tensors."""
-    _bank_ok(img_bank, "img_bank", True)
-    dev = img_bank.device
+def scan_eps(queries: Queries, dtype, engine="auto") -> float:
+    """Bound on |score a scan ranks a row by - canonical score| for banks of ``dtype`` (torch dtype or code)."""
+    code = dtype if isinstance(dtype, int) else (BF16 if dtype == torch.bfloat16 else F32)
+    e = C.c_float(0.0)
+    _check(load().swat_scan_eps(queries._h, code, ENGINE[engine], C.byref(e)))
+    return float(e.value)
+
+
+def rescore_walk(ctx: Context, queries: Queries, t2t_bank: torch.Tensor, cand_scores, cand_rows, cand_counts, truncated, k: int,
+                 t2t_threshold: float = 0.0, aux_bank: Optional[torch.Tensor] = None, aux_threshold: float = 0.25,
+                 bank_row_base: int = 0, eps: Optional[float] = None, out=None, aux_queries: Optional[Queries] = None):
+    """Exact re-score of the candidates (canonical fp32 dot against ``t2t_bank`` and, when given, ``aux_bank``) +
+    accept walk.  Returns ``(scores, rows, aux, counts, limit, incomplete)``; ``out = (scores, rows, aux, counts,
+    limit)`` writes into caller tensors (e.g. views of a packed exchange buffer)."""
+    _bank_ok(t2t_bank, "t2t_bank", True)
+    if aux_bank is not None:
+        _bank_ok(aux_bank, "aux_bank", True)
+        if aux_bank.shape != t2t_bank.shape or aux_bank.dtype != t2t_bank.dtype:
+            raise ValueError("aux_bank must match t2t_bank in shape and dtype")
+    dev = t2t_bank.device
     Cn, kf = cand_scores.shape
+    if eps is None:
+        eps = scan_eps(queries, t2t_bank.dtype)
     if out is None:
         o_s = torch.empty(Cn, k, dtype=torch.float32, device=dev)
         o_r = torch.empty(Cn, k, dtype=torch.int64, device=dev)
         o_t = torch.empty(Cn, k, dtype=torch.float32, device=dev)
         o_c = torch.empty(Cn, dtype=torch.int32, device=dev)
+        o_l = torch.empty(Cn, dtype=torch.float32, device=dev)
     else:
-        o_s, o_r, o_t, o_c = out
+        o_s, o_r, o_t, o_c, o_l = out
         _out_ok(o_s, (Cn, k), torch.float32); _out_ok(o_r, (Cn, k), torch.int64)
-        _out_ok(o_t, (Cn, k), torch.float32); _out_ok(o_c, (Cn,), torch.int32)
+        _out_ok(o_t, (Cn, k), torch.float32); _out_ok(o_c, (Cn,), torch.int32); _out_ok(o_l, (Cn,), torch.float32)
     o_i = torch.empty(Cn, dtype=torch.int32, device=dev)
-    _check(load().swat_t2i_walk(ctx._h, queries._h, _ptr(img_bank), _dtype_code(img_bank), int(img_bank.shape[0]), int(img_row_base),
-                                None, _ptr(cand_scores), _ptr(cand_rows), _ptr(cand_counts), _ptr(truncated), int(kf), int(k),
-                                float(t2i_threshold), _ptr(o_s), _ptr(o_r), _ptr(o_t), _ptr(o_c), _ptr(o_i), _stream(ctx.device)))
-    return o_s, o_r, o_t, o_c, o_i
+    _check(load().swat_rescore_walk(ctx._h, queries._h, None if aux_queries is None else aux_queries._h, _ptr(t2t_bank), _ptr(aux_bank), _dtype_code(t2t_bank), int(t2t_bank.shape[0]),
+                                    int(bank_row_base), _ptr(cand_scores), _ptr(cand_rows), _ptr(cand_counts), _ptr(truncated), int(kf),
+                                    int(k), float(t2t_threshold), float(aux_threshold), float(eps), _ptr(o_s), _ptr(o_r), _ptr(o_t),
+                                    _ptr(o_c), _ptr(o_l), _ptr(o_i), _stream(ctx.device)))
+    return o_s, o_r, o_t, o_c, o_l, o_i
 
 
 def merge_topk(ctx: Context, scores: torch.Tensor, rows: torch.Tensor, counts: torch.Tensor, aux: Optional[torch.Tensor] = None,
-               truncated: Optional[torch.Tensor] = None, k_out: Optional[int] = None, aux_threshold: float = float("-inf"),
+               limit: Optional[torch.Tensor] = None, k_out: Optional[int] = None, aux_threshold: float = float("-inf"),
                n_shards: Optional[int] = None, shard_stride_bytes: int = 0):
-    """Merge gathered shard candidate lists ``[G,C,k_in]`` (rows global) into ``[C,k_out]``: the best
-    ``k_out`` entries with ``aux >= aux_threshold``.  Returns ``(scores, rows, aux | None, counts,
-    incomplete)``; ``incomplete[c] == 1`` means a truncated shard may hold rows that belong in the
-    result (re-run the shards with a larger ``k_in``).
+    """Merge gathered per-shard walk results ``[G,C,k_in]`` (canonical scores, rows global) into ``[C,k_out]``: the
+    best ``k_out`` entries with ``aux >= aux_threshold``.  ``limit [G,C]`` float32: shard g vouches only for rows
+    scoring above ``limit[g,c]`` (``-inf`` = complete).  Returns ``(scores, rows, aux | None, counts, incomplete)``;
+    ``incomplete[c] == 1`` means the result reaches down to some shard's limit (re-run the shards deeper).
 
     With ``shard_stride_bytes > 0`` the arguments are shard 0's ``[C,k_in]`` / ``[C]`` slices of an
     all-gathered packed buffer and shard g of every array lies ``g * shard_stride_bytes`` further on
@@ -402,7 +437,7 @@ def merge_topk(ctx: Context, scores: torch.Tensor, rows: torch.Tensor, counts: t
         G, Cn, k_in = scores.shape
         scores, rows, counts = scores.contiguous(), rows.contiguous(), counts.contiguous()
         aux = None if aux is None else aux.contiguous()
-        truncated = None if truncated is None else truncated.contiguous()
+        limit = None if limit is None else limit.to(torch.float32).contiguous()
     k_out = int(k_in if k_out is None else k_out)
     dev = scores.device
     o_s = torch.empty(Cn, k_out, dtype=torch.float32, device=dev)
@@ -410,7 +445,7 @@ def merge_topk(ctx: Context, scores: torch.Tensor, rows: torch.Tensor, counts: t
     o_a = torch.empty(Cn, k_out, dtype=torch.float32, device=dev) if aux is not None else None
     o_c = torch.empty(Cn, dtype=torch.int32, device=dev)
     o_i = torch.empty(Cn, dtype=torch.int32, device=dev)
-    _check(load().swat_merge_topk(ctx._h, _ptr(scores), _ptr(rows), _ptr(aux), _ptr(counts), _ptr(truncated), int(G),
+    _check(load().swat_merge_topk(ctx._h, _ptr(scores), _ptr(rows), _ptr(aux), _ptr(counts), _ptr(limit), int(G),
                                   int(shard_stride_bytes), int(Cn), int(k_in), k_out, float(aux_threshold), _ptr(o_s), _ptr(o_r),
                                   _ptr(o_a), _ptr(o_c), _ptr(o_i), _stream(ctx.device)))
     return o_s, o_r, o_a, o_c, o_i

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
@@ -95,9 +96,10 @@ struct swat_ctx {
   int64_t launches = 0;
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // workspaces for the whole-pipeline calls
-  DevBuf w_scores, w_rows, w_counts, w_trunc, w_t2i, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
+  DevBuf w_scores, w_rows, w_counts, w_trunc, w_exact, w_aux, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
   DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
   DevBuf w_swap[10];                // bank-swap escalation pass: two re-score stages
+  bool zero_copy = true;            // host pipeline: read candidates' rows from pinned host banks in place
   bool swap_pass = true;            // classes with fewer than k rows passing T2I: enumerate the passers from the image bank
   cudaStream_t copy_stream = nullptr, work_stream = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -114,6 +116,7 @@ struct swat_ctx {
   std::vector<int> esc_classes[2];
   int esc_next = 0;
   DevBuf e_bufs[4][4];   // per escalation depth: scores, rows, t2i, counts of the sub-run
+  DevBuf e_remap[4][2];  // per escalation depth, partitioned data: class map and the renumbered row_class of the sub-run
 };
 
 struct swat_queries {
@@ -130,6 +133,9 @@ struct swat_queries {
   mutable std::vector<int32_t> kclass_hint;   // per class: deepest over-fetch its T2I walk has needed so far (0 = default)
   mutable int32_t last_k_fetch = 0;   // over-fetch at which the last pipeline run completed
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
+  int n_fstages = 0, n_opstages_f32 = 0;   // fp32 banks on the tcgen05 engine: staged fp32 boxes / bf16 operand stages
+  // |score of bf16-rounded row and bf16-rounded queries - fp32 score| <= eps_conv for every L2-normalised row (see swat_queries_create)
+  float eps_conv = 0.0f;
   CUtensorMap tm_q;
 };
 
@@ -146,17 +152,22 @@ struct swat_job {
 
 namespace {
 
-int32_t encode_2d_bf16(swat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint32_t box_rows) {
+// 2-D map of a row-major [rows, 512] array: 128-byte boxes (64 bf16 or 32 fp32 along k) x box_rows, SWIZZLE_128B
+int32_t encode_2d(swat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint32_t box_rows, int dtype) {
+  const bool f32 = dtype == SWAT_F32;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim) * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(SWAT_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d, rows %llu, box %u)", (int)r,
-                                     (unsigned long long)rows, box_rows);
+  CUresult r = ctx->encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SWAT_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d, rows %llu, box %u, dtype %d)", (int)r,
+                                     (unsigned long long)rows, box_rows, dtype);
   return SWAT_OK;
+}
+int32_t encode_2d_bf16(swat_ctx* ctx, CUtensorMap* tm, const void* ptr, uint64_t rows, uint32_t box_rows) {
+  return encode_2d(ctx, tm, ptr, rows, box_rows, SWAT_BF16);
 }
 
 // Split the Q query columns into n_qb blocks at class boundaries, every block padded to the same
@@ -188,6 +199,20 @@ bool plan_blocks(const std::vector<int32_t>& class_begin, int max_cols, int& n_q
   return false;
 }
 
+// Bound on |score a scan kernel ranks a row by - the canonical fp32 score of select.cu|.  Full-precision engines
+// (bf16 banks on the tensor cores: exact products, fp32 accumulation; the fp32-FMA kernel) differ from the canonical
+// summation order only: 512 terms x 2^-23 x sum|x_i q_i| <= 6.1e-5 for unit vectors, observed ~2e-6.
+constexpr float kEpsAccum = 1.0e-4f;
+
+int32_t resolve_engine(const swat_queries* q, int32_t dtype, bool dual) {
+  if (dual) return SWAT_ENGINE_SIMT;                 // in-pass T2I predicate
+  if (dtype == SWAT_BF16) return SWAT_ENGINE_TC;
+  return q->n_fstages > 0 ? SWAT_ENGINE_TC : SWAT_ENGINE_SIMT;
+}
+float scan_eps(const swat_queries* q, int32_t dtype, int32_t engine) {
+  return (engine == SWAT_ENGINE_TC && dtype == SWAT_F32) ? q->eps_conv : kEpsAccum;
+}
+
 int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
                   float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, float* dense_out,
                   cudaStream_t stream) {
@@ -199,9 +224,10 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
                 (long long)n_rows, (long long)row_base);
   if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
   if ((reinterpret_cast<uintptr_t>(d_bank) & 15) != 0) return fail(SWAT_ERR_INVALID, "bank pointer must be 16-byte aligned");
-  if (engine == SWAT_ENGINE_AUTO) engine = (dtype == SWAT_BF16 && d_t2i_bank == nullptr) ? SWAT_ENGINE_TC : SWAT_ENGINE_SIMT;
-  if (engine == SWAT_ENGINE_TC && (dtype != SWAT_BF16 || d_t2i_bank != nullptr))
-    return fail(SWAT_ERR_UNSUPPORTED, "the tcgen05 engine serves bf16 banks without the in-pass T2I predicate");
+  const bool f32 = dtype == SWAT_F32;
+  if (engine == SWAT_ENGINE_AUTO) engine = resolve_engine(q, dtype, d_t2i_bank != nullptr);
+  if (engine == SWAT_ENGINE_TC && d_t2i_bank != nullptr)
+    return fail(SWAT_ERR_UNSUPPORTED, "the tcgen05 engine does not evaluate the in-pass T2I predicate");
   ScanArgs a;
   a.st = job->st;
   a.col_class = q->d_col_class;
@@ -218,11 +244,15 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
   a.n_classes = q->C;
   job->last_stream = stream;
   if (engine == SWAT_ENGINE_TC) {
-    if (q->n_stages <= 0) return fail(SWAT_ERR_UNSUPPORTED, "query block does not fit in shared memory for the tcgen05 engine");
+    if ((f32 ? q->n_fstages : q->n_stages) <= 0)
+      return fail(SWAT_ERR_UNSUPPORTED, "query block does not fit in shared memory for the tcgen05 engine");
     TcArgs p{};
     p.n_qb = q->n_qb;
     p.n_blk = q->n_blk;
-    p.n_stages = q->n_stages;
+    p.n_stages = f32 ? q->n_opstages_f32 : q->n_stages;
+    p.n_fstages = f32 ? q->n_fstages : 0;
+    p.qb_base = 0;
+    p.qb_count = q->n_qb;
     p.smem_b_bytes = static_cast<uint32_t>(8) * (q->n_blk / q->ctas) * 128;
     p.bank_hint = (q->n_qb == 1) ? 0x12F0000000000000ull /* evict_first: streamed once */ : 0x1000000000000000ull;
     p.blk_class = q->d_blk_class;
@@ -244,7 +274,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     if (B > 0) {
       SW_OK(ctx->w_boot.ensure(static_cast<size_t>(q->C) * B * 4));
       CUtensorMap tm_pre;
-      SW_OK(encode_2d_bf16(ctx, &tm_pre, bank, static_cast<uint64_t>(B), 128));
+      SW_OK(encode_2d(ctx, &tm_pre, bank, static_cast<uint64_t>(B), 128, dtype));
       TcArgs pd = p;
       pd.s = a;
       pd.s.n_rows = B;
@@ -252,16 +282,20 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
       pd.s.dense_ld = B;
       pd.s.dense_transposed = 1;
       pd.bank_hint = 0x1000000000000000ull;
-      CU_OK(launch_scan_tc(&tm_pre, &q->tm_q, pd, q->ctas, q->reduce, false, true, grid, stream));
+      for (int b0 = 0; b0 < q->n_qb; b0 += grid / q->ctas) {
+        pd.qb_base = b0;
+        pd.qb_count = std::min(grid / q->ctas, q->n_qb - b0);
+        CU_OK(launch_scan_tc(&tm_pre, &q->tm_q, pd, q->ctas, q->reduce, false, true, f32, grid, stream));
+      }
       CU_OK(launch_bootstrap(job->st, q->C, ctx->w_boot.as<float>(), static_cast<uint32_t>(B), a.row_base,
                              static_cast<uint32_t>(grid) * kTcEpiWarps, stream));
       ctx->launches += 2;
-      bank += static_cast<size_t>(B) * kDim * 2;
+      bank += static_cast<size_t>(B) * kDim * (f32 ? 4 : 2);
       a.n_rows = n_rows - B;
       a.row_base += static_cast<uint32_t>(B);
     }
     CUtensorMap tm_bank;
-    SW_OK(encode_2d_bf16(ctx, &tm_bank, bank, static_cast<uint64_t>(a.n_rows), 128));
+    SW_OK(encode_2d(ctx, &tm_bank, bank, static_cast<uint64_t>(a.n_rows), 128, dtype));
     p.s = a;
     // Several Q blocks rarely divide the CTA pairs evenly (74 pairs: 4 blocks leave 2 idle, 16 leave 10, 21 leave 11) and
     // blocks served by different numbers of pairs drift apart, so the bank is re-read from HBM per block.  The unit
@@ -277,9 +311,15 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
         p.n_ranges = ranges;
       }
     }
+    if (p.n_ranges == 0 && q->n_qb > pairs) launches = (q->n_qb + pairs - 1) / pairs;   // legacy plan: `pairs` Q blocks per launch
     for (int i = 0; i < launches; ++i) {
-      p.unit_base = i * pairs;
-      CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, grid, stream));
+      if (p.n_ranges > 0) {
+        p.unit_base = i * pairs;
+      } else {
+        p.qb_base = i * pairs;
+        p.qb_count = std::min(pairs, q->n_qb - p.qb_base);
+      }
+      CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, f32, grid, stream));
     }
     ctx->launches += launches - 1;
   } else {
@@ -396,9 +436,20 @@ struct BankSrc {
   const void* t2t = nullptr; const void* t2i = nullptr;
   int dtype = 0; int64_t n_rows = 0;
   const int32_t* row_class = nullptr; const uint32_t* exclude = nullptr;
+  // host banks in pinned (page-locked) memory: device-visible aliases, the re-score kernel reads candidate rows
+  // straight over PCIe instead of a host-side gather
+  const void* t2t_mapped = nullptr; const void* t2i_mapped = nullptr;
 };
 
 size_t elem_size(int dtype) { return dtype == SWAT_BF16 ? 2 : 4; }
+
+// device-visible alias of a page-locked host allocation (cudaHostAlloc / cudaHostRegister), nullptr for pageable memory
+const void* mapped_alias(const void* h) {
+  if (!h) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
 
 // one pass over the whole bank, folding every view into `job`
 int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, bool dual, float t2i_thr, cudaStream_t stream) {
@@ -480,24 +531,116 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
                      int32_t k_fetch_init, int depth);
 
 constexpr int32_t kSwapPass = kMaxKFetch + 1;    // k_fetch_init beyond the widest over-fetch: try the bank-swap pass, then the in-pass predicate
-constexpr int32_t kForceDual = kMaxKFetch + 2;   // ... go straight to the exact in-pass predicate
+constexpr int32_t kForceDual = kMaxKFetch + 2;   // ... go straight to the in-pass predicate
+
+// per-class candidate lists as swat_job_select leaves them (ranked on the scan's approximate score)
+struct CandLists {
+  const float* scores; const int64_t* rows; const int32_t* counts; const int32_t* trunc; int stride;
+};
+
+// Exact re-score + accept walk of candidate lists against the banks of `b` (select.cu): canonical fp32 scores for the
+// ranking bank and, with use_aux, the predicate bank; results in walk order.  Host banks: pinned memory is read in
+// place by the kernel (zero-copy over PCIe, only the candidates' rows move); pageable memory is gathered on the host.
+int32_t walk_candidates(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, bool use_aux, int64_t row_offset, const CandLists& cl,
+                        int32_t k, float thr, float aux_thr, float eps, bool all_or_nothing, float* o_scores, int64_t* o_rows,
+                        float* o_aux, int32_t* o_counts, float* o_limit, int32_t* o_incomplete, cudaStream_t stream,
+                        const swat_queries* q_aux = nullptr) {
+  const int C = q->C;
+  const size_t n_slots = static_cast<size_t>(C) * cl.stride;
+  SW_OK(ctx->w_exact.ensure(n_slots * 4));
+  SW_OK(ctx->w_aux.ensure(n_slots * 4));
+  WalkArgs w;
+  memset(&w, 0, sizeof(w));
+  w.dtype = b.dtype;
+  w.queries = (b.dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
+  w.class_begin = q->d_class_begin;
+  w.reduce = q->reduce;
+  const swat_queries* qa = q_aux ? q_aux : q;
+  w.aux_queries = (b.dtype == SWAT_BF16) ? static_cast<const void*>(qa->d_q_bf16) : static_cast<const void*>(qa->d_q_f32);
+  w.aux_class_begin = qa->d_class_begin;
+  w.aux_reduce = qa->reduce;
+  w.cand_scores = cl.scores; w.cand_rows = cl.rows; w.cand_counts = cl.counts; w.truncated = cl.trunc;
+  w.stride = cl.stride; w.k = k; w.n_classes = C;
+  w.thr = thr; w.aux_thr = aux_thr; w.eps = eps; w.all_or_nothing = all_or_nothing ? 1 : 0;
+  w.exact_scratch = ctx->w_exact.as<float>(); w.aux_scratch = ctx->w_aux.as<float>();
+  w.out_scores = o_scores; w.out_rows = o_rows; w.out_aux = o_aux; w.out_counts = o_counts; w.out_limit = o_limit; w.incomplete = o_incomplete;
+  w.key_row_base = row_offset;
+  const bool mapped = b.host && b.t2t_mapped && (!use_aux || b.t2i_mapped);
+  if (!b.host || mapped) {
+    w.t2t_bank = b.host ? b.t2t_mapped : b.t2t;
+    w.aux_bank = use_aux ? (b.host ? b.t2i_mapped : b.t2i) : nullptr;
+    w.bank_rows = b.n_rows;
+    w.bank_row_base = row_offset;
+    w.gather_index = nullptr;
+    if (b.host) ctx->timing[5] += static_cast<double>(n_slots) * kDim * elem_size(b.dtype) * (use_aux ? 2 : 1);   // upper bound: every slot filled
+  } else {
+    // pageable host banks: gather the candidates' rows on the host, ship the compact blocks
+    const size_t row_bytes = static_cast<size_t>(kDim) * elem_size(b.dtype);
+    std::vector<int64_t> h_rows(n_slots);
+    std::vector<int32_t> h_counts(C);
+    CU_OK(cudaMemcpyAsync(h_rows.data(), cl.rows, n_slots * 8, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaMemcpyAsync(h_counts.data(), cl.counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaStreamSynchronize(stream));
+    ctx->timing[6] += static_cast<double>(n_slots * 8 + C * 4);
+    std::vector<int64_t> h_index(n_slots, -1);
+    std::vector<int64_t> src;
+    src.reserve(n_slots);
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < std::min(h_counts[c], cl.stride); ++j) {
+        h_index[static_cast<size_t>(c) * cl.stride + j] = static_cast<int64_t>(src.size());
+        src.push_back(h_rows[static_cast<size_t>(c) * cl.stride + j] - row_offset);
+      }
+    const size_t n_src = src.size();
+    const int n_banks = use_aux ? 2 : 1;
+    SW_OK(ensure_pinned(ctx, std::max<size_t>(n_src, 1) * row_bytes * n_banks));
+    char* stage = static_cast<char*>(ctx->h_pinned);
+    const char* banks[2] = {static_cast<const char*>(b.t2t), static_cast<const char*>(b.t2i)};
+    const unsigned nt = n_src * n_banks < 4096 ? 1u : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    auto work = [&](unsigned wi) {
+      for (int bk = 0; bk < n_banks; ++bk)
+        for (size_t i = wi; i < n_src; i += nt)
+          memcpy(stage + (static_cast<size_t>(bk) * n_src + i) * row_bytes, banks[bk] + static_cast<size_t>(src[i]) * row_bytes, row_bytes);
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned wi = 0; wi < nt; ++wi) th.emplace_back(work, wi);
+      for (auto& x : th) x.join();
+    }
+    SW_OK(ctx->w_img.ensure(std::max<size_t>(n_src, 1) * row_bytes * n_banks));
+    SW_OK(ctx->w_idx.ensure(n_slots * 8));
+    CU_OK(cudaMemcpyAsync(ctx->w_img.p, stage, n_src * row_bytes * n_banks, cudaMemcpyHostToDevice, stream));
+    CU_OK(cudaMemcpyAsync(ctx->w_idx.p, h_index.data(), n_slots * 8, cudaMemcpyHostToDevice, stream));
+    CU_OK(cudaStreamSynchronize(stream));   // h_index is pageable and dies at scope end
+    ctx->timing[5] += static_cast<double>(n_src * row_bytes * n_banks + n_slots * 8);
+    w.t2t_bank = ctx->w_img.p;
+    w.aux_bank = use_aux ? ctx->w_img.as<char>() + n_src * row_bytes : nullptr;
+    w.bank_rows = static_cast<int64_t>(n_src);
+    w.bank_row_base = 0;
+    w.gather_index = ctx->w_idx.as<int64_t>();
+  }
+  CU_OK(launch_rescore_walk(w, stream));
+  ctx->launches += kWalkLaunches;
+  return SWAT_OK;
+}
 
 // Bank-swap escalation pass.  A class whose T2T-ordered walk ran out of candidates has FEW rows passing the T2I
 // predicate (that is why k were not found among the best 4096 by T2T).  So enumerate the passers instead: scan the
-// IMAGE bank with the T2I threshold (minus a margin for tensor-core vs exact summation order) as the row threshold;
-// if fewer than 4096 rows of the class survive, that list holds every row that can pass the predicate.  Re-score
-// them exactly against both banks (T2I, then T2T with the T2T threshold) and sort by T2T: exactly the walk of
-// add_t2t_ranked_t2i_tshd_to_split (:507-527), at the cost of one tensor-core pass instead of the fp32 two-bank scan.
+// IMAGE bank with the T2I threshold (minus the scan's error bound) as the row threshold; if fewer than 4096 rows of the
+// class survive, that list holds every row that can pass the predicate.  The walk then re-scores them exactly against
+// both banks and orders them by T2T: exactly the walk of add_t2t_ranked_t2i_tshd_to_split (:507-527), at the cost of
+// one tensor-core pass instead of the fp32 two-bank scan.
 // unresolved: classes with 4096 or more such rows (plenty of passers, all with a low T2T score) -- left to the caller.
+// only: nullable [C] mask -- results are written for these classes only (the others keep what the ladder proved).
 int32_t swap_pass(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
                   float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream,
-                  std::vector<int>* unresolved) {
+                  const std::vector<int>* only, std::vector<int>* unresolved) {
   const int C = q->C;
   const int32_t kf = kMaxKFetch;
-  const float margin = 1.0e-4f;
   BankSrc sb = b;
   sb.t2t = b.t2i;              // rows are ranked by their image score here
   sb.t2i = nullptr;
+  const float eps = scan_eps(q, b.dtype, resolve_engine(q, b.dtype, false));
   int64_t cap = auto_cap(ctx, kf), list_entries = auto_list_entries(ctx, C, kf);
   const size_t n = static_cast<size_t>(C) * kf;
   SW_OK(ctx->w_scores.ensure(n * 4)); SW_OK(ctx->w_rows.ensure(n * 8)); SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
@@ -505,7 +648,7 @@ int32_t swap_pass(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_
   for (int rounds = 0;; ++rounds) {
     if (rounds > 8) return fail(SWAT_ERR_OVERFLOW, "bank-swap pass: retry budget exhausted");
     swat_job* job = nullptr;
-    SW_OK(acquire_job(ctx, q, kf, t2i_thr - margin, cap, list_entries, &job));
+    SW_OK(acquire_job(ctx, q, kf, t2i_thr - eps, cap, list_entries, &job));
     SW_OK(swat_job_reset(job, stream));
     CU_OK(cudaEventRecord(ctx->ev[0], stream));
     SW_OK(scan_all(ctx, job, sb, false, 0.0f, stream));
@@ -526,56 +669,40 @@ int32_t swap_pass(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_
     if (flags & 1u) cap = std::min<int64_t>(cap * 4, limit);
     if (flags & 2u) list_entries *= 4;
   }
+  // walk into scratch outputs, then copy the wanted classes
   DevBuf* w = ctx->w_swap;
-  for (int i = 0; i < 2; ++i) {                 // two re-score stages: [0..4] exact T2I, [5..9] exact T2T
-    SW_OK(w[5 * i + 0].ensure(n * 4)); SW_OK(w[5 * i + 1].ensure(n * 8)); SW_OK(w[5 * i + 2].ensure(n * 4));
-    SW_OK(w[5 * i + 3].ensure(static_cast<size_t>(C) * 4)); SW_OK(w[5 * i + 4].ensure(static_cast<size_t>(C) * 4));
-  }
-  SW_OK(ctx->w_t2i.ensure(n * 4));
-  T2iArgs t;
-  memset(&t, 0, sizeof(t));
-  t.dtype = b.dtype;
-  t.queries = (b.dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
-  t.class_begin = q->d_class_begin;
-  t.reduce = q->reduce;
-  t.n_classes = C;
-  t.k = kf; t.k_fetch = kf;
-  t.img_rows = b.n_rows; t.img_row_base = row_offset; t.img_index = nullptr;
-  t.t2i_scratch = ctx->w_t2i.as<float>();
-  // stage A: exact image score of every candidate, keep those at or above the T2I threshold
-  t.img_bank = b.t2i; t.t2i_thr = t2i_thr;
-  t.cand_scores = ctx->w_scores.as<float>(); t.cand_rows = ctx->w_rows.as<int64_t>(); t.cand_counts = ctx->w_counts.as<int32_t>();
-  t.truncated = nullptr;
-  t.out_scores = w[0].as<float>(); t.out_rows = w[1].as<int64_t>(); t.out_t2i = w[2].as<float>(); t.out_counts = w[3].as<int32_t>();
-  t.incomplete = w[4].as<int32_t>();
-  CU_OK(launch_t2i_walk(t, stream));
-  // stage B: exact caption score of the survivors, keep those at or above the T2T threshold; their T2I score rides along
-  t.img_bank = b.t2t; t.t2i_thr = thr;
-  t.cand_scores = w[2].as<float>(); t.cand_rows = w[1].as<int64_t>(); t.cand_counts = w[3].as<int32_t>();
-  t.out_scores = w[5].as<float>(); t.out_rows = w[6].as<int64_t>(); t.out_t2i = w[7].as<float>(); t.out_counts = w[8].as<int32_t>();
-  t.incomplete = w[9].as<int32_t>();
-  CU_OK(launch_t2i_walk(t, stream));
-  // order by (T2T desc, row asc), keep k: the merge walk over one "shard" with the caption score as the key
-  SW_OK(ctx->w_keys.ensure(n * 8));
-  SW_OK(ctx->w_out_t2i.ensure(static_cast<size_t>(C) * k * 4));
-  CU_OK(launch_merge(w[7].as<float>(), w[6].as<int64_t>(), w[5].as<float>(), -INFINITY, w[8].as<int32_t>(), nullptr, 1, 0, C, kf, k,
-                     ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows, d_out_t2i ? d_out_t2i : ctx->w_out_t2i.as<float>(), d_out_counts,
-                     nullptr, stream));
-  ctx->launches += 6;
+  SW_OK(w[0].ensure(static_cast<size_t>(C) * k * 4)); SW_OK(w[1].ensure(static_cast<size_t>(C) * k * 8));
+  SW_OK(w[2].ensure(static_cast<size_t>(C) * k * 4)); SW_OK(w[3].ensure(static_cast<size_t>(C) * 4)); SW_OK(w[4].ensure(static_cast<size_t>(C) * 4));
+  CandLists cl{ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(), ctx->w_trunc.as<int32_t>(), kf};
+  SW_OK(walk_candidates(ctx, q, b, true, row_offset, cl, k, thr, t2i_thr, eps, true, w[0].as<float>(), w[1].as<int64_t>(), w[2].as<float>(),
+                        w[3].as<int32_t>(), nullptr, w[4].as<int32_t>(), stream));
   SW_OK(ensure_status(ctx, static_cast<size_t>(C) + 1));
-  CU_OK(cudaMemcpyAsync(ctx->h_status + 1, ctx->w_trunc.as<int32_t>(), static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+  CU_OK(cudaMemcpyAsync(ctx->h_status + 1, w[4].as<int32_t>(), static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
   CU_OK(cudaStreamSynchronize(stream));
+  std::vector<char> want(C, only ? 0 : 1);
+  if (only) for (int c : *only) want[c] = 1;
   unresolved->clear();
-  for (int c = 0; c < C; ++c) if (ctx->h_status[1 + c] != 0) unresolved->push_back(c);
+  for (int c = 0; c < C; ++c) {
+    if (!want[c]) continue;
+    if (ctx->h_status[1 + c] != 0) { unresolved->push_back(c); continue; }
+    const size_t o = static_cast<size_t>(c) * k;
+    CU_OK(cudaMemcpyAsync(d_out_scores + o, w[0].as<float>() + o, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream));
+    CU_OK(cudaMemcpyAsync(d_out_rows + o, w[1].as<int64_t>() + o, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, stream));
+    if (d_out_t2i) CU_OK(cudaMemcpyAsync(d_out_t2i + o, w[2].as<float>() + o, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream));
+    CU_OK(cudaMemcpyAsync(d_out_counts + c, w[3].as<int32_t>() + c, 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  CU_OK(cudaStreamSynchronize(stream));
   return SWAT_OK;
 }
 
-// Targeted escalation: re-run only the classes whose T2I walk could not be proven exact, with a
-// wider over-fetch (and finally the exact in-pass predicate), then splice their rows into the result.
+// Targeted escalation: re-run only the classes whose walk could not be proven exact, with a wider over-fetch (and
+// finally the in-pass predicate), then splice their rows into the result.  Partitioned data (one class per row): the
+// sub-run gets a row_class array renumbered to the sub-query set's classes (rows of other classes become -1).
 int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
                          const std::vector<int>& classes, int32_t k_fetch_next, float* d_out_scores, int64_t* d_out_rows,
                          float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream, int depth) {
   const int n = static_cast<int>(classes.size());
+  if (depth > 3) return fail(SWAT_ERR_INCOMPLETE, "escalation nested too deep");
   std::vector<float> hq;
   std::vector<int32_t> coq;
   for (int i = 0; i < n; ++i) {
@@ -585,7 +712,6 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
       coq.push_back(i);
     }
   }
-  if (depth > 3) return fail(SWAT_ERR_INCOMPLETE, "escalation nested too deep");
   swat_queries* sub = nullptr;
   const bool cached = depth == 0;   // nested levels own their sub-query set: the cache entry is in use above them
   for (int i = 0; cached && i < 2 && !sub; ++i)
@@ -596,13 +722,40 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
     SW_OK(swat_queries_create(ctx, hq.data(), static_cast<int32_t>(coq.size()), coq.data(), n, q->reduce, &sub));
     if (cached) { ctx->esc_q[slot] = sub; ctx->esc_parent[slot] = q; ctx->esc_classes[slot] = classes; ctx->esc_next = slot ^ 1; }
   }
+  BankSrc sb = b;
+  int32_t rc = SWAT_OK;
+  std::vector<int32_t> h_sub_rc;
+  if (b.row_class != nullptr) {
+    std::vector<int32_t> map(q->C, -1);
+    for (int i = 0; i < n; ++i) map[classes[i]] = i;
+    if (b.host) {               // host banks carry a host row_class: renumber it here
+      h_sub_rc.resize(static_cast<size_t>(b.n_rows));
+      for (int64_t i = 0; i < b.n_rows; ++i) {
+        const int32_t c = b.row_class[i];
+        h_sub_rc[static_cast<size_t>(i)] = (c >= 0 && c < q->C) ? map[c] : -1;
+      }
+      sb.row_class = h_sub_rc.data();
+    } else {
+      DevBuf &m = ctx->e_remap[depth][0], &o = ctx->e_remap[depth][1];
+      rc = m.ensure(static_cast<size_t>(q->C) * 4);
+      if (rc == SWAT_OK) rc = o.ensure(static_cast<size_t>(std::max<int64_t>(b.n_rows, 1)) * 4);
+      if (rc == SWAT_OK) {
+        cudaError_t e = cudaMemcpyAsync(m.p, map.data(), static_cast<size_t>(q->C) * 4, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = launch_remap_classes(b.row_class, m.as<int32_t>(), q->C, b.n_rows, o.as<int32_t>(), stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);      // `map` is pageable and dies at scope end
+        if (e != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "renumbering row classes failed: %s", cudaGetErrorString(e));
+        ctx->launches += 1;
+      }
+      sb.row_class = o.as<int32_t>();
+    }
+  }
   DevBuf &o_s = ctx->e_bufs[depth][0], &o_r = ctx->e_bufs[depth][1], &o_t = ctx->e_bufs[depth][2], &o_c = ctx->e_bufs[depth][3];
-  int32_t rc = o_s.ensure(static_cast<size_t>(n) * k * 4);
+  if (rc == SWAT_OK) rc = o_s.ensure(static_cast<size_t>(n) * k * 4);
   if (rc == SWAT_OK) rc = o_r.ensure(static_cast<size_t>(n) * k * 8);
   if (rc == SWAT_OK) rc = o_t.ensure(static_cast<size_t>(n) * k * 4);
   if (rc == SWAT_OK) rc = o_c.ensure(static_cast<size_t>(n) * 4);
   if (rc == SWAT_OK)
-    rc = run_pipeline(ctx, sub, b, row_offset, k, thr, t2i_thr, o_s.as<float>(), o_r.as<int64_t>(), d_out_t2i ? o_t.as<float>() : nullptr,
+    rc = run_pipeline(ctx, sub, sb, row_offset, k, thr, t2i_thr, o_s.as<float>(), o_r.as<int64_t>(), d_out_t2i ? o_t.as<float>() : nullptr,
                       o_c.as<int32_t>(), stream, k_fetch_next, depth + 1);
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < n && rc == SWAT_OK && e == cudaSuccess; ++i) {
@@ -619,41 +772,53 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
   return rc;
 }
 
+int32_t round_up32(int64_t x) { return static_cast<int32_t>((x + 31) / 32 * 32); }
+
+// First over-fetch of a walk.  Without a predicate the candidates must reach 2 eps below the k-th score (the walk only
+// trusts rows above the list's frontier + eps); with one, deep enough for k rows to pass.
+int32_t default_k_fetch(const swat_ctx* ctx, int32_t k, bool want_t2i, bool host, float eps) {
+  const bool wide = eps > 10.0f * kEpsAccum;        // bf16-rounded scan of an fp32 bank: ~1e-2 of score between k-th and frontier
+  int64_t kf;
+  if (!want_t2i) kf = wide ? round_up32(k + std::max(1024, k)) : round_up32(k + std::max(64, k / 8));
+  else if (ctx->overfetch > 0) kf = ctx->overfetch;
+  // Host banks stream over PCIe (~20x slower than the scan): a second pass costs far more than a
+  // wider first one, so over-fetch 4k there; HBM-resident banks start at 2k.
+  else kf = (host ? std::max(4 * k, 2048) : std::max(2 * k, 1024)) + (wide ? 1024 : 0);
+  return static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(kf, k), kMaxKFetch));
+}
+
 // The whole pipeline.  Results land in d_out_* (device).  See swat_topk / swat_topk_host.
 int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_t row_offset, int32_t k, float thr, float t2i_thr,
                      float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, cudaStream_t stream,
                      int32_t k_fetch_init, int depth) {
   if (k < 1 || k > kMaxKFetch) return fail(SWAT_ERR_UNSUPPORTED, "k must be in [1, %d], got %d", kMaxKFetch, k);
+  if (row_offset < 0 || b.n_rows < 0 || row_offset + b.n_rows > 0xFFFFFFFEll)
+    return fail(SWAT_ERR_INVALID, "row_offset + n_rows = %lld exceeds the 32-bit row ids of one shard's keys", (long long)(row_offset + b.n_rows));
   const int C = q->C;
   const bool want_t2i = b.t2i != nullptr;
   if (depth == 0) for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
-  int32_t k_fetch = k;
-  bool dual = false;          // exact in-pass predicate fallback
-  if (want_t2i && k_fetch_init == kSwapPass && ctx->swap_pass && !b.host) {
+  const bool can_swap = want_t2i && ctx->swap_pass && !b.host;
+  if (k_fetch_init == kSwapPass && can_swap) {
     // escalation beyond the widest over-fetch: enumerate the T2I passers from the image bank (one tensor-core pass);
-    // classes with too many of them for that fall through to the exact in-pass predicate
+    // classes with too many of them for that fall through to the in-pass predicate
     std::vector<int> unresolved;
-    SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, &unresolved));
+    SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, nullptr, &unresolved));
     if (!unresolved.empty())
       SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
                              d_out_counts, stream, depth));
     q->last_k_fetch = kMaxKFetch;
     return SWAT_OK;
   }
-  if (want_t2i) {
-    if (k_fetch_init > kMaxKFetch) dual = true;   // exact in-pass predicate
-    else if (k_fetch_init > 0) k_fetch = k_fetch_init;
-    // Host banks stream over PCIe (~20x slower than the scan): a second pass costs far more than a
-    // wider first one, so over-fetch 4k there; HBM-resident banks start at 2k.
-    else k_fetch = ctx->overfetch > 0 ? ctx->overfetch : (b.host ? std::max(4 * k, 2048) : std::max(2 * k, 1024));
-    k_fetch = std::min(std::max(k_fetch, k), kMaxKFetch);
-  }
+  bool dual = want_t2i && k_fetch_init > kMaxKFetch;          // in-pass predicate (fp32-FMA kernel, both banks per row)
+  float eps = scan_eps(q, b.dtype, resolve_engine(q, b.dtype, dual));
+  // every candidate of the in-pass mode passed the (loosened) predicate: k plus slack for the frontier suffices
+  int32_t k_fetch = dual ? default_k_fetch(ctx, k, false, b.host, eps)
+                         : (k_fetch_init > 0 ? std::min(std::max(k_fetch_init, k), kMaxKFetch) : default_k_fetch(ctx, k, want_t2i, b.host, eps));
   // Classes whose walk needed a deeper over-fetch before start there: the depth is per class (one class
   // with a block of duplicates should not make the other 199 collect four times the candidates).
   // Shards of one dataset behave alike; an escalation re-reads the whole bank.
   std::vector<uint32_t> k_class;
-  const bool use_hint = want_t2i && !dual && depth == 0 && k_fetch_init == 0 && ctx->overfetch == 0 &&
-                        static_cast<int>(q->kclass_hint.size()) == C;
+  const bool use_hint = !dual && depth == 0 && k_fetch_init == 0 && ctx->overfetch == 0 && static_cast<int>(q->kclass_hint.size()) == C;
   if (use_hint) {
     int32_t deepest = k_fetch;
     for (int c = 0; c < C; ++c) deepest = std::max(deepest, q->kclass_hint[c]);
@@ -670,35 +835,33 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
   for (int rounds = 0;; ++rounds) {
     if (rounds > 24) return fail(SWAT_ERR_OVERFLOW, "retry budget exhausted (cap=%lld lists=%lld k_fetch=%d)", (long long)cap,
                                  (long long)list_entries, k_fetch);
-    const int32_t kf = dual ? k : k_fetch;
+    const int32_t kf = k_fetch;
     swat_job* job = nullptr;
-    SW_OK(acquire_job(ctx, q, kf, thr, cap, list_entries, &job));
-    if (!dual && !k_class.empty()) {
+    // the scan ranks by approximate scores: rows within eps below the user threshold may still qualify exactly
+    SW_OK(acquire_job(ctx, q, kf, thr - eps, cap, list_entries, &job));
+    if (!k_class.empty()) {
       CU_OK(cudaMemcpyAsync(job->d_k_class, k_class.data(), static_cast<size_t>(C) * 4, cudaMemcpyHostToDevice, stream));
       job->h_k_class.clear();
       job->st.k_class = job->d_k_class;
     }
     SW_OK(swat_job_reset(job, stream));
     CU_OK(cudaEventRecord(ctx->ev[0], stream));
-    SW_OK(scan_all(ctx, job, b, dual, t2i_thr, stream));
+    SW_OK(scan_all(ctx, job, b, dual, t2i_thr - eps, stream));
     CU_OK(cudaEventRecord(ctx->ev[1], stream));
-    const bool direct = !want_t2i || dual;     // select writes the final result
-    if (!direct) {
-      SW_OK(ctx->w_scores.ensure(static_cast<size_t>(C) * kf * 4));
-      SW_OK(ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8));
-      SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
-      SW_OK(ctx->w_trunc.ensure(static_cast<size_t>(C) * 4));
-    }
+    SW_OK(ctx->w_scores.ensure(static_cast<size_t>(C) * kf * 4));
+    SW_OK(ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8));
+    SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
+    SW_OK(ctx->w_trunc.ensure(static_cast<size_t>(C) * 4));
+    SW_OK(ctx->w_incomplete.ensure(static_cast<size_t>(C) * 4));
     // resident banks: rows leave the select as global ids (row_offset + shard-local row)
-    if (direct) CU_OK(launch_select(job->st, C, row_offset, d_out_scores, d_out_rows, d_out_counts, nullptr, stream));
-    else CU_OK(launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(),
-                             ctx->w_trunc.as<int32_t>(), stream));
+    CU_OK(launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(),
+                        ctx->w_trunc.as<int32_t>(), stream));
     job->last_stream = stream;
     ctx->launches += kSelectLaunches;
     CU_OK(cudaEventRecord(ctx->ev[2], stream));
-    // Resident banks with a T2I stage run it optimistically and read the overflow word together with the walk's
-    // `incomplete` flags: one host sync per step instead of two.  (Overflowed lists hold valid rows, just not all.)
-    const bool late_check = !direct && !b.host;
+    // Resident banks run the walk optimistically and read the overflow word together with its `incomplete` flags:
+    // one host sync per step instead of two.  (Overflowed lists hold valid rows, just not all.)
+    const bool late_check = !b.host;
     uint32_t flags = 0;
     auto account_scan = [&]() {
       float ms = 0;
@@ -719,94 +882,17 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       account_scan();
       if (flags & 3u) { SW_OK(grow_buffers()); continue; }
     }
-    if (direct && !(dual && d_out_t2i)) break;
-    // ---- T2I stage on the candidates
+    // ---- exact re-score of the candidates + accept walk
     CU_OK(cudaEventRecord(ctx->ev[3], stream));
-    T2iArgs t;
-    memset(&t, 0, sizeof(t));
-    t.dtype = b.dtype;
-    t.queries = (b.dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
-    t.class_begin = q->d_class_begin;
-    t.reduce = q->reduce;
-    t.n_classes = C;
-    // in-pass mode proved t2i >= threshold but did not keep the value: re-score the k winners
-    t.t2i_thr = direct ? -INFINITY : t2i_thr;
-    t.k = k;
-    t.k_fetch = direct ? k : kf;
-    t.cand_scores = direct ? d_out_scores : ctx->w_scores.as<float>();
-    t.cand_rows = direct ? d_out_rows : ctx->w_rows.as<int64_t>();
-    t.cand_counts = direct ? d_out_counts : ctx->w_counts.as<int32_t>();
-    t.truncated = direct ? nullptr : ctx->w_trunc.as<int32_t>();
-    SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(C) * t.k_fetch * 4));
-    t.t2i_scratch = ctx->w_t2i.as<float>();
-    SW_OK(ctx->w_out_scores.ensure(static_cast<size_t>(C) * k * 4));
-    SW_OK(ctx->w_out_rows.ensure(static_cast<size_t>(C) * k * 8));
-    SW_OK(ctx->w_out_counts.ensure(static_cast<size_t>(C) * 4));
-    SW_OK(ctx->w_incomplete.ensure(static_cast<size_t>(C) * 4));
-    // when re-scoring in place (direct) write to scratch outputs, then copy back
-    t.out_scores = direct ? ctx->w_out_scores.as<float>() : d_out_scores;
-    t.out_rows = direct ? ctx->w_out_rows.as<int64_t>() : d_out_rows;
-    t.out_t2i = d_out_t2i;
-    t.out_counts = direct ? ctx->w_out_counts.as<int32_t>() : d_out_counts;
-    t.incomplete = ctx->w_incomplete.as<int32_t>();
-    if (!b.host) {
-      t.img_bank = b.t2i;
-      t.img_rows = b.n_rows;
-      t.img_row_base = row_offset;
-      t.img_index = nullptr;
-    } else {
-      // gather only the candidates' image rows on the host, ship the compact block
-      const size_t n_slots = static_cast<size_t>(C) * t.k_fetch;
-      const size_t row_bytes = static_cast<size_t>(kDim) * elem_size(b.dtype);
-      std::vector<int64_t> h_rows(n_slots);
-      std::vector<int32_t> h_counts(C);
-      CU_OK(cudaMemcpyAsync(h_rows.data(), t.cand_rows, n_slots * 8, cudaMemcpyDeviceToHost, stream));
-      CU_OK(cudaMemcpyAsync(h_counts.data(), t.cand_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
-      CU_OK(cudaStreamSynchronize(stream));
-      ctx->timing[6] += static_cast<double>(n_slots * 8 + C * 4);
-      std::vector<int64_t> h_index(n_slots, -1);
-      std::vector<int64_t> src;
-      src.reserve(n_slots);
-      for (int c = 0; c < C; ++c)
-        for (int j = 0; j < h_counts[c]; ++j) {
-          h_index[static_cast<size_t>(c) * t.k_fetch + j] = static_cast<int64_t>(src.size());
-          src.push_back(h_rows[static_cast<size_t>(c) * t.k_fetch + j] - row_offset);
-        }
-      const size_t n_src = src.size();
-      SW_OK(ensure_pinned(ctx, std::max<size_t>(n_src, 1) * row_bytes));
-      char* stage = static_cast<char*>(ctx->h_pinned);
-      const char* img = static_cast<const char*>(b.t2i);
-      const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-      std::vector<std::thread> th;
-      for (unsigned w = 0; w < nt; ++w)
-        th.emplace_back([&, w]() {
-          for (size_t i = w; i < n_src; i += nt) memcpy(stage + i * row_bytes, img + static_cast<size_t>(src[i]) * row_bytes, row_bytes);
-        });
-      for (auto& x : th) x.join();
-      SW_OK(ctx->w_img.ensure(std::max<size_t>(n_src, 1) * row_bytes));
-      SW_OK(ctx->w_idx.ensure(n_slots * 8));
-      CU_OK(cudaMemcpyAsync(ctx->w_img.p, stage, n_src * row_bytes, cudaMemcpyHostToDevice, stream));
-      CU_OK(cudaMemcpyAsync(ctx->w_idx.p, h_index.data(), n_slots * 8, cudaMemcpyHostToDevice, stream));
-      CU_OK(cudaStreamSynchronize(stream));   // h_index is pageable and dies at scope end
-      ctx->timing[5] += static_cast<double>(n_src * row_bytes + n_slots * 8);
-      t.img_bank = ctx->w_img.p;
-      t.img_rows = static_cast<int64_t>(n_src);
-      t.img_row_base = 0;
-      t.img_index = ctx->w_idx.as<int64_t>();
-    }
-    CU_OK(launch_t2i_walk(t, stream));
-    ctx->launches += 2;
-    if (direct) {
-      CU_OK(cudaMemcpyAsync(d_out_scores, t.out_scores, static_cast<size_t>(C) * k * 4, cudaMemcpyDeviceToDevice, stream));
-      CU_OK(cudaMemcpyAsync(d_out_rows, t.out_rows, static_cast<size_t>(C) * k * 8, cudaMemcpyDeviceToDevice, stream));
-      CU_OK(cudaMemcpyAsync(d_out_counts, t.out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, stream));
-    }
+    CandLists cl{ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(), ctx->w_trunc.as<int32_t>(), kf};
+    SW_OK(walk_candidates(ctx, q, b, want_t2i, row_offset, cl, k, thr, t2i_thr, eps, false, d_out_scores, d_out_rows, d_out_t2i,
+                          d_out_counts, nullptr, ctx->w_incomplete.as<int32_t>(), stream));
     CU_OK(cudaEventRecord(ctx->ev[4], stream));
     SW_OK(ensure_status(ctx, 2 * static_cast<size_t>(C) + 1));
     ctx->h_status[0] = 0;
     if (late_check) CU_OK(cudaMemcpyAsync(ctx->h_status, job->st.flags, 4, cudaMemcpyDeviceToHost, stream));
-    CU_OK(cudaMemcpyAsync(ctx->h_status + 1, t.incomplete, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
-    CU_OK(cudaMemcpyAsync(ctx->h_status + 1 + C, t.out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaMemcpyAsync(ctx->h_status + 1, ctx->w_incomplete.p, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaMemcpyAsync(ctx->h_status + 1 + C, d_out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
     CU_OK(cudaStreamSynchronize(stream));
     const int32_t* inc = ctx->h_status + 1;
     {
@@ -819,19 +905,30 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       account_scan();
       if (flags & 3u) { SW_OK(grow_buffers()); continue; }
     }
-    if (direct) break;
     std::vector<int> bad;
     for (int c = 0; c < C; ++c) if (inc[c] != 0) bad.push_back(c);
     if (bad.empty()) break;
-    // some class ran out of candidates before k passed T2I although more rows were eligible:
-    // widen the over-fetch for those classes only, finally fall back to the exact in-pass predicate
+    // Some class ran out of trusted candidates before k rows were accepted although more rows were eligible: widen the
+    // over-fetch for those classes only, then (T2I walks) enumerate the passers from the image bank, finally the
+    // in-pass predicate.
     ctx->timing[7] += 1;
-    // whole-set escalation (every class short, or partitioned data): x4 per round; targeted sub-passes go x2
-    const int32_t next = (k_fetch < kMaxKFetch) ? std::min(kMaxKFetch, k_fetch * 4) : kMaxKFetch + 1;
-    if (b.row_class == nullptr && static_cast<int>(bad.size()) < C) {
+    if (dual) {
+      if (k_fetch >= kMaxKFetch)
+        return fail(SWAT_ERR_INCOMPLETE, "%d classes not provably exact at the widest over-fetch (%d candidates; more than that many "
+                                         "rows tie with the k-th score?)", (int)bad.size(), kMaxKFetch);
+      k_fetch = std::min(kMaxKFetch, k_fetch * 2);
+      k_class.clear();
+      cap = std::max(cap, auto_cap(ctx, k_fetch));
+      list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
+      continue;
+    }
+    if (static_cast<int>(bad.size()) < C) {
       int32_t from = k_fetch;                           // the escalated classes were walked to this depth
       if (!k_class.empty()) { from = kMaxKFetch; for (int c : bad) from = std::min<int32_t>(from, static_cast<int32_t>(k_class[c])); }
-      const int32_t nxt = (from < kMaxKFetch) ? std::min(kMaxKFetch, from * 2) : kSwapPass;
+      if (from >= kMaxKFetch && !want_t2i)
+        return fail(SWAT_ERR_INCOMPLETE, "%d classes not provably exact at the widest over-fetch (%d candidates; more than that many "
+                                         "rows tie with the k-th score?)", (int)bad.size(), kMaxKFetch);
+      const int32_t nxt = (from < kMaxKFetch) ? std::min(kMaxKFetch, from * 2) : (can_swap ? kSwapPass : kForceDual);
       // A class that accepted p of the d candidates walked so far needs about d*k/p of them.  Where that is beyond the
       // widest over-fetch the ladder would only waste passes: those classes go straight to the bank-swap pass.
       std::vector<int> deeper, few;
@@ -839,8 +936,8 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       for (int c : bad) {
         const int64_t d = k_class.empty() ? k_fetch : static_cast<int64_t>(k_class[c]);
         const int64_t p = accepted[c];
-        const bool hopeless = p <= 0 || d * k / p > 2 * kMaxKFetch;   // factor 2: borderline classes still try the ladder
-        (hopeless && nxt != kSwapPass && ctx->swap_pass && !b.host ? few : deeper).push_back(c);
+        const bool hopeless = want_t2i && (p <= 0 || d * k / p > 2 * kMaxKFetch);   // factor 2: borderline classes still try the ladder
+        (hopeless && nxt <= kMaxKFetch && can_swap ? few : deeper).push_back(c);
       }
       if (!deeper.empty()) {
         SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, deeper, nxt, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
@@ -855,22 +952,27 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
                                stream, depth));
       break;
     }
+    // every class is short: escalate the whole set, x4 per round
     k_class.clear();
-    if (next > kMaxKFetch && ctx->swap_pass && !b.host && depth < 3) {
+    if (k_fetch < kMaxKFetch) {
+      k_fetch = std::min(kMaxKFetch, k_fetch * 4);
+      cap = std::max(cap, auto_cap(ctx, k_fetch));
+      list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
+      continue;
+    }
+    if (!want_t2i)
+      return fail(SWAT_ERR_INCOMPLETE, "%d classes not provably exact at the widest over-fetch (%d candidates)", (int)bad.size(), kMaxKFetch);
+    if (can_swap && depth < 3) {
       std::vector<int> unresolved;
-      SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, &unresolved));
+      SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, &bad, &unresolved));
       if (!unresolved.empty())
         SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
                                d_out_counts, stream, depth));
-      k_fetch = kMaxKFetch;
       break;
     }
-    if (next > kMaxKFetch) dual = true;
-    else {
-      k_fetch = next;
-      cap = std::max(cap, auto_cap(ctx, k_fetch));
-      list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
-    }
+    dual = true;
+    eps = scan_eps(q, b.dtype, SWAT_ENGINE_SIMT);
+    k_fetch = default_k_fetch(ctx, k, false, b.host, eps);
   }
   q->last_k_fetch = dual ? 0 : k_fetch;
   if (depth == 0) {
@@ -915,12 +1017,16 @@ int32_t swat_ctx_create(int32_t device, swat_ctx** out) {
     return fail(SWAT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  CU_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  CU_OK(cudaStreamCreateWithFlags(&ctx->work_stream, cudaStreamNonBlocking));
-  for (auto& ev : ctx->ev) CU_OK(cudaEventCreate(&ev));
-  for (int i = 0; i < 3; ++i) {
-    CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
-    CU_OK(cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+  cudaError_t ce = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->work_stream, cudaStreamNonBlocking);
+  for (auto& ev : ctx->ev) if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
+  for (int i = 0; i < 3 && ce == cudaSuccess; ++i) {
+    ce = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming);
+  }
+  if (ce != cudaSuccess) {
+    swat_ctx_destroy(ctx);        // releases whatever was created
+    return fail(SWAT_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(ce));
   }
   *out = ctx;
   return SWAT_OK;
@@ -930,7 +1036,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   if (!ctx) return SWAT_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_t2i, &ctx->w_incomplete, &ctx->w_keys,
+  DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_exact, &ctx->w_aux, &ctx->w_incomplete, &ctx->w_keys,
                     &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
                     &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot,
@@ -940,6 +1046,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   if (ctx->cached_job) swat_job_destroy(ctx->cached_job);
   for (int i = 0; i < 2; ++i) if (ctx->esc_q[i]) { swat_queries* e = ctx->esc_q[i]; ctx->esc_q[i] = nullptr; swat_queries_destroy(e); }
   for (auto& lvl : ctx->e_bufs) for (auto& bf : lvl) bf.release();
+  for (auto& lvl : ctx->e_remap) for (auto& bf : lvl) bf.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -961,6 +1068,7 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   else if (n == "host_chunk_rows") ctx->host_chunk_rows = value;
   else if (n == "unit_plan") ctx->unit_plan = value != 0;
   else if (n == "swap_pass") ctx->swap_pass = value != 0;
+  else if (n == "zero_copy") ctx->zero_copy = value != 0;
   else if (n == "bootstrap_rows") ctx->bootstrap_rows = std::max<int64_t>(0, value);
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
   return SWAT_OK;
@@ -1029,6 +1137,28 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   for (int b = 0; b < q->n_qb; ++b) split[b] = std::min(split[b], q->n_blk);
   q->n_cols = q->n_qb * q->n_blk;
   q->n_stages = tc_pick_stages(q->n_blk, q->ctas, ctx->smem_optin);
+  q->n_fstages = tc_pick_fstages(q->n_blk, q->ctas, ctx->smem_optin, &q->n_opstages_f32);
+  {
+    // fp32 banks are scanned as bf16-rounded rows against bf16-rounded queries.  With x~ = bf16(x) (round to nearest
+    // even: |x~_i - x_i| <= 2^-8 |x_i|, 8 significant bits) and q~ = bf16(q):
+    //   |x.q - x~.q~| = |x.(q - q~) + (x - x~).q~| <= |x| |q - q~| + 2^-8 |x| |q~|
+    // |q - q~| and |q~| are computed here; rows are L2-normalised (extract_mined_feature.py:121,181), 0.1 % slack.
+    // Group reduces (mean / max / min over a class's queries) cannot move by more than their worst member.
+    double worst = 0.0;
+    for (int i = 0; i < n_queries; ++i) {
+      double d2 = 0.0, n2 = 0.0;
+      for (int j = 0; j < kDim; ++j) {
+        const float f = h_queries[static_cast<size_t>(i) * kDim + j];
+        const uint32_t bits = static_cast<uint32_t>(f32_to_bf16_rne(f)) << 16;
+        float r;
+        memcpy(&r, &bits, 4);
+        d2 += (static_cast<double>(f) - r) * (static_cast<double>(f) - r);
+        n2 += static_cast<double>(r) * r;
+      }
+      worst = std::max(worst, std::sqrt(d2) + std::sqrt(n2) / 256.0);
+    }
+    q->eps_conv = static_cast<float>(1.001 * worst) + kEpsAccum;
+  }
   // host staging: padded layouts
   const size_t Q = n_queries, NC = q->n_cols;
   std::vector<uint16_t> h_bf(Q * kDim), h_pbf(NC * kDim, 0);
@@ -1180,33 +1310,36 @@ int32_t swat_job_destroy(swat_job* job) {
   return SWAT_OK;
 }
 
-int32_t swat_t2i_walk(swat_ctx* ctx, const swat_queries* q, const void* d_img_bank, int32_t dtype, int64_t img_rows,
-                      int64_t img_row_base, const int64_t* d_img_index, const float* d_cand_scores, const int64_t* d_cand_rows,
-                      const int32_t* d_cand_counts, const int32_t* d_truncated, int32_t k_fetch, int32_t k, float t2i_threshold,
-                      float* d_out_scores, int64_t* d_out_rows, float* d_out_t2i, int32_t* d_out_counts, int32_t* d_incomplete,
-                      void* stream) {
-  if (!ctx || !q || !d_img_bank || !d_cand_scores || !d_cand_rows || !d_cand_counts || !d_out_scores || !d_out_rows || !d_out_counts)
-    return fail(SWAT_ERR_INVALID, "null argument");
-  if (k_fetch < 1 || k_fetch > kMaxKFetch || k < 1 || k > k_fetch) return fail(SWAT_ERR_INVALID, "need 1 <= k <= k_fetch <= %d", kMaxKFetch);
-  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
-  CU_OK(cudaSetDevice(ctx->device));
-  SW_OK(ctx->w_t2i.ensure(static_cast<size_t>(q->C) * k_fetch * 4));
-  T2iArgs t;
-  memset(&t, 0, sizeof(t));
-  t.img_bank = d_img_bank; t.dtype = dtype; t.img_rows = img_rows; t.img_row_base = img_row_base; t.img_index = d_img_index;
-  t.queries = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32);
-  t.class_begin = q->d_class_begin; t.reduce = q->reduce;
-  t.cand_scores = d_cand_scores; t.cand_rows = d_cand_rows; t.cand_counts = d_cand_counts; t.truncated = d_truncated;
-  t.k_fetch = k_fetch; t.k = k; t.t2i_thr = t2i_threshold; t.n_classes = q->C;
-  t.t2i_scratch = ctx->w_t2i.as<float>();
-  t.out_scores = d_out_scores; t.out_rows = d_out_rows; t.out_t2i = d_out_t2i; t.out_counts = d_out_counts; t.incomplete = d_incomplete;
-  CU_OK(launch_t2i_walk(t, static_cast<cudaStream_t>(stream)));
-  ctx->launches += 2;
+int32_t swat_scan_eps(const swat_queries* q, int32_t dtype, int32_t engine, float* eps) {
+  if (!q || !eps) return fail(SWAT_ERR_INVALID, "null argument");
+  if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
+  if (engine == SWAT_ENGINE_AUTO) engine = resolve_engine(q, dtype, false);
+  *eps = scan_eps(q, dtype, engine);
   return SWAT_OK;
 }
 
+int32_t swat_rescore_walk(swat_ctx* ctx, const swat_queries* q, const swat_queries* q_aux, const void* d_t2t_bank, const void* d_aux_bank, int32_t dtype,
+                          int64_t bank_rows, int64_t bank_row_base, const float* d_cand_scores, const int64_t* d_cand_rows,
+                          const int32_t* d_cand_counts, const int32_t* d_truncated, int32_t k_fetch, int32_t k, float t2t_threshold,
+                          float aux_threshold, float eps, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
+                          int32_t* d_out_counts, float* d_out_limit, int32_t* d_incomplete, void* stream) {
+  if (!ctx || !q || !d_t2t_bank || !d_cand_scores || !d_cand_rows || !d_cand_counts || !d_out_scores || !d_out_rows || !d_out_counts)
+    return fail(SWAT_ERR_INVALID, "null argument");
+  if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
+  if (k_fetch < 1 || k_fetch > kMaxKFetch || k < 1 || k > k_fetch) return fail(SWAT_ERR_INVALID, "need 1 <= k <= k_fetch <= %d", kMaxKFetch);
+  if (!(eps >= 0.0f)) return fail(SWAT_ERR_INVALID, "eps must be >= 0");
+  if (q_aux && q_aux->C != q->C) return fail(SWAT_ERR_INVALID, "the predicate's query set must cover the same %d classes (has %d)", q->C, q_aux->C);
+  (void)cudaGetLastError();   // drop stale errors left by other libraries in this process
+  CU_OK(cudaSetDevice(ctx->device));
+  BankSrc b;
+  b.host = false; b.t2t = d_t2t_bank; b.t2i = d_aux_bank; b.dtype = dtype; b.n_rows = bank_rows;
+  CandLists cl{d_cand_scores, d_cand_rows, d_cand_counts, d_truncated, k_fetch};
+  return walk_candidates(ctx, q, b, d_aux_bank != nullptr, bank_row_base, cl, k, t2t_threshold, aux_threshold, eps, false, d_out_scores,
+                         d_out_rows, d_out_aux, d_out_counts, d_out_limit, d_incomplete, static_cast<cudaStream_t>(stream), q_aux);
+}
+
 int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_rows, const float* d_aux, const int32_t* d_counts,
-                        const int32_t* d_truncated, int32_t n_shards, int64_t shard_stride_bytes, int32_t n_classes, int32_t k_in,
+                        const float* d_limit, int32_t n_shards, int64_t shard_stride_bytes, int32_t n_classes, int32_t k_in,
                         int32_t k_out, float aux_threshold, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
                         int32_t* d_out_counts, int32_t* d_incomplete, void* stream) {
   if (!ctx || !d_scores || !d_rows || !d_counts || !d_out_scores || !d_out_rows || !d_out_counts) return fail(SWAT_ERR_INVALID, "null argument");
@@ -1216,7 +1349,7 @@ int32_t swat_merge_topk(swat_ctx* ctx, const float* d_scores, const int64_t* d_r
   (void)cudaGetLastError();
   CU_OK(cudaSetDevice(ctx->device));
   SW_OK(ctx->w_keys.ensure(static_cast<size_t>(n_shards) * n_classes * k_in * 8));
-  CU_OK(launch_merge(d_scores, d_rows, d_aux, aux_threshold, d_counts, d_truncated, n_shards, shard_stride_bytes, n_classes, k_in, k_out,
+  CU_OK(launch_merge(d_scores, d_rows, d_aux, aux_threshold, d_counts, d_limit, n_shards, shard_stride_bytes, n_classes, k_in, k_out,
                      ctx->w_keys.as<uint64_t>(), d_out_scores, d_out_rows, d_out_aux, d_out_counts, d_incomplete,
                      static_cast<cudaStream_t>(stream)));
   ctx->launches += 2;
@@ -1245,6 +1378,20 @@ int32_t swat_scores_dense(swat_ctx* ctx, const swat_queries* q, const void* d_ba
   tmp.ctx = ctx; tmp.q = q;
   memset(&tmp.st, 0, sizeof(tmp.st));
   return scan_view(&tmp, d_bank, dtype, n_rows, 0, nullptr, 0.0f, nullptr, nullptr, engine, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int32_t swat_score_rows(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows,
+                        const int32_t* d_row_class, float* d_out, void* stream) {
+  if (!ctx || !q || (n_rows > 0 && (!d_bank || !d_row_class || !d_out))) return fail(SWAT_ERR_INVALID, "null argument");
+  if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
+  if (n_rows < 0) return fail(SWAT_ERR_INVALID, "n_rows must be >= 0");
+  (void)cudaGetLastError();
+  CU_OK(cudaSetDevice(ctx->device));
+  CU_OK(launch_score_rows(d_bank, dtype, d_row_class, n_rows,
+                          (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_q_bf16) : static_cast<const void*>(q->d_q_f32),
+                          q->d_class_begin, q->C, q->reduce, d_out, static_cast<cudaStream_t>(stream)));
+  ctx->launches += 1;
+  return SWAT_OK;
 }
 
 int32_t swat_zeroshot_predict(swat_ctx* ctx, const swat_queries* q, const void* d_bank, int32_t dtype, int64_t n_rows, int32_t* d_pred,
@@ -1298,6 +1445,10 @@ int32_t swat_topk_host(swat_ctx* ctx, const swat_queries* q, const void* h_t2t_b
   if (rc == SWAT_OK) rc = o_counts.ensure(C * 4);
   BankSrc b;
   b.host = true; b.t2t = h_t2t_bank; b.t2i = h_t2i_bank; b.dtype = dtype; b.n_rows = n_rows; b.row_class = h_row_class; b.exclude = h_exclude;
+  if (ctx->zero_copy) {          // pinned banks are visible to the device: candidates' rows are read in place
+    b.t2t_mapped = mapped_alias(h_t2t_bank);
+    b.t2i_mapped = mapped_alias(h_t2i_bank);
+  }
   cudaStream_t s = ctx->work_stream;
   if (rc == SWAT_OK)
     rc = run_pipeline(ctx, q, b, 0, k, t2t_threshold, t2i_threshold, o_scores.as<float>(), o_rows.as<int64_t>(),

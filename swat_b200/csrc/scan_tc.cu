@@ -12,6 +12,12 @@
 //                           buffer is released as soon as a warp's last chunk is in registers
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer (MMA <-> epilogue).
 //
+// fp32 banks (F32 = true; the reference's own dtype, utils/extras.py:163): the bank is streamed as fp32 (2 KB/row, TMA
+// boxes of 128 rows x 32 k into a second ring), warps 8-11 convert every staged box to bf16 (RNE) and write it into
+// the K-major SWIZZLE_128B operand ring the MMAs read; the epilogue has twice the time per row and runs on 4 warps.
+// The scores are those of bf16-rounded rows (|delta| <= swat_queries::eps_conv, proven in api.cu); the pipeline
+// re-scores every candidate exactly in fp32 afterwards (select.cu).
+//
 // Replaces caption_embeddings.cuda() @ class_prompt.t() + sorted() + walk,
 // /root/reference/retrieval/sample_retrieval.py:400, :754, :439-482 for every class at once.
 #include <cuda.h>
@@ -24,17 +30,17 @@ namespace swat {
 namespace {
 
 constexpr int kStageBytes = 128 * 128;   // 128 bank rows x 64 bf16
-constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant, interleaved 32-column chunks
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kThreads = 384;             // 4 control warps + 8 epilogue warps, or + 4 epilogue + 4 converter warps (F32)
 constexpr int kTailBytes = 5120;         // barriers + tables
 
 // ---------------------------------------------------------------------------------------- kernel
-template <int kCtas, int RED, bool PART, bool DENSE>
+template <int kCtas, int RED, bool PART, bool DENSE, bool F32>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constant__ CUtensorMap tm_q, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
+  constexpr int kEpiWarps = F32 ? 4 : 8;   // bf16: two per TMEM lane quadrant on interleaved 32-column chunks
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int pair_id = blockIdx.x / kCtas, n_pairs = gridDim.x / kCtas;
@@ -42,10 +48,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   // Unit plan (n_ranges > 0, several launches): unit u = unit_base + pair covers Q block u % n_qb and the tiles
   // r, r + R, r + 2R, ... of range r = u / n_qb.  The n_qb pairs of one range run in the same launch and walk the
   // same tiles in step (one HBM read, the rest L2 hits), and every pair gets the same number of equal units.
+  // Legacy launches cover the Q blocks [qb_base, qb_base + qb_count): more blocks than pairs take several launches.
   const int unit = p.unit_base + pair_id;
-  const int qb = unit % p.n_qb;
-  const int pair_in_qb = (p.n_ranges > 0) ? unit / p.n_qb : pair_id / p.n_qb;
-  const int pairs_qb = (p.n_ranges > 0) ? p.n_ranges : (n_pairs - qb + p.n_qb - 1) / p.n_qb;
+  const int qb = (p.n_ranges > 0) ? unit % p.n_qb : p.qb_base + pair_id % p.qb_count;
+  const int pair_in_qb = (p.n_ranges > 0) ? unit / p.n_qb : pair_id / p.qb_count;
+  const int pairs_qb = (p.n_ranges > 0) ? p.n_ranges : (n_pairs - pair_id % p.qb_count + p.qb_count - 1) / p.qb_count;
   const int NB = p.n_blk, NBC = NB / kCtas;
   const uint32_t b_chunk_bytes = static_cast<uint32_t>(NBC) * 128u;
   constexpr int kTileRows = 128 * kCtas;
@@ -60,16 +67,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   }
 
   uint8_t* sB = smem;
-  uint8_t* sA = smem + p.smem_b_bytes;
-  uint8_t* tail = sA + p.n_stages * kStageBytes;
+  uint8_t* sA = smem + p.smem_b_bytes;                        // operand ring (bf16, what the MMAs read)
+  uint8_t* sF = sA + p.n_stages * kStageBytes;                // F32: ring of staged fp32 boxes
+  uint8_t* tail = sF + (F32 ? p.n_fstages * kStageBytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [8]
   uint64_t* empty_bar = full_bar + 8;                         // [8]
   uint64_t* tfull_bar = empty_bar + 8;                        // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                       // [2]
   uint64_t* q_bar = tempty_bar + 2;                           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+  uint64_t* ffull_bar = q_bar + 1;                            // [8] F32
+  uint64_t* fempty_bar = ffull_bar + 8;                       // [8] F32
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fempty_bar + 8);
   uint32_t* s_done = tmem_slot + 1;                           // epilogue warps that finished
-  float* s_tau = reinterpret_cast<float*>(tail + 256);        // [256] (+256 spare)
+  float* s_tau = reinterpret_cast<float*>(tail + 512);        // [256] (+256 spare)
   int32_t* s_cls = reinterpret_cast<int32_t*>(s_tau + 512);   // [256]
   float* s_cnt = reinterpret_cast<float*>(s_cls + 256);       // [256]
   uint32_t* s_end = reinterpret_cast<uint32_t*>(s_cnt + 256); // [8]
@@ -77,7 +87,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_bank);
     prefetch_tmap(&tm_q);
-    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    // operand stage full: one TMA transaction (bf16) or, F32, the converter warps of both CTAs (4 warps x 2 half-boxes each)
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full_bar[i]), F32 ? 8 * kCtas : 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&ffull_bar[i]), 1); mbar_init(smem_u32(&fempty_bar[i]), 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull_bar[i]), 1); mbar_init(smem_u32(&tempty_bar[i]), kEpiWarps * kCtas); }
     mbar_init(smem_u32(q_bar), 1);
     *s_done = 0;
@@ -122,19 +134,38 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
                              0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
       }
-      const uint32_t sA_a = smem_u32(sA), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
-      const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
-      uint32_t stage = 0, phase = 0;
-      for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
-        const int row0 = static_cast<int>(t * kTileRows + rank * 128);
+      if (F32) {
+        // fp32 boxes of 128 rows x 32 k (16 KB) into this CTA's own ring; the converter warps free a stage as soon as
+        // its contents sit in their registers
+        const uint32_t sF_a = smem_u32(sF), ffull_a = smem_u32(ffull_bar), fempty_a = smem_u32(fempty_bar);
+        uint32_t stage = 0, phase = 0;
+        for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
+          const int row0 = static_cast<int>(t * kTileRows + rank * 128);
 #pragma unroll 1
-        for (int kc = 0; kc < 8; ++kc) {
-          mbar_wait(empty_a + stage * 8u, phase ^ 1u);
-          if (elect_one()) {
-            if (rank == 0) mbar_arrive_expect_tx(full_a + stage * 8u, static_cast<uint32_t>(kStageBytes) * kCtas);
-            tma_load_2d<kCtas>(sA_a + stage * kStageBytes, &tm_bank, full_lead + stage * 8u, kc * 64, row0, p.bank_hint);
+          for (int kc = 0; kc < 16; ++kc) {
+            mbar_wait(fempty_a + stage * 8u, phase ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(ffull_a + stage * 8u, static_cast<uint32_t>(kStageBytes));
+              tma_load_2d<1>(sF_a + stage * kStageBytes, &tm_bank, ffull_a + stage * 8u, kc * 32, row0, p.bank_hint);
+            }
+            if (++stage == static_cast<uint32_t>(p.n_fstages)) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
+        }
+      } else {
+        const uint32_t sA_a = smem_u32(sA), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+        const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
+        uint32_t stage = 0, phase = 0;
+        for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
+          const int row0 = static_cast<int>(t * kTileRows + rank * 128);
+#pragma unroll 1
+          for (int kc = 0; kc < 8; ++kc) {
+            mbar_wait(empty_a + stage * 8u, phase ^ 1u);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(full_a + stage * 8u, static_cast<uint32_t>(kStageBytes) * kCtas);
+              tma_load_2d<kCtas>(sA_a + stage * kStageBytes, &tm_bank, full_lead + stage * 8u, kc * 64, row0, p.bank_hint);
+            }
+            if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -159,7 +190,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         const uint32_t d_tmem = tmem_base + buf * 256u;
 #pragma unroll 1
         for (int kc = 0; kc < 8; ++kc) {
-          mbar_wait(full_a + stage * 8u, phase);
+          if (F32) mbar_wait_acquire_cluster(full_a + stage * 8u, phase);   // filled by converter warps of both CTAs
+          else mbar_wait(full_a + stage * 8u, phase);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a0 = a_base + stage * a_step;
@@ -191,6 +223,43 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         __nanosleep(2000);
       }
     }
+  } else if (F32 && warp >= 8) {
+    // ================================================================== fp32 -> bf16 converter (F32 only)
+    // Thread = one of the CTA's 128 tile rows.  A staged box holds 32 consecutive k of every row (128 B per row, the
+    // eight 16-byte chunks XOR-swizzled with row & 7); two boxes fill one 64-k operand stage in the same swizzle.
+    const int trow = (warp - 8) * 32 + lane;
+    const uint32_t sw = static_cast<uint32_t>(trow & 7);
+    const uint32_t src_row = smem_u32(sF) + static_cast<uint32_t>(trow) * 128u;
+    const uint32_t dst_row = smem_u32(sA) + static_cast<uint32_t>(trow) * 128u;
+    const uint32_t ffull_a = smem_u32(ffull_bar), fempty_a = smem_u32(fempty_bar);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
+    uint32_t fstage = 0, fphase = 0, stage = 0, phase = 0;
+    for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
+#pragma unroll 1
+      for (int kc = 0; kc < 16; ++kc) {
+        mbar_wait(ffull_a + fstage * 8u, fphase);
+        uint32_t w[16];
+#pragma unroll
+        for (uint32_t ch = 0; ch < 8; ++ch) {
+          const float4 v = lds_f32x4(src_row + fstage * kStageBytes + ((ch ^ sw) << 4));
+          w[2 * ch] = pack_bf16x2(v.x, v.y);
+          w[2 * ch + 1] = pack_bf16x2(v.z, v.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(fempty_a + fstage * 8u);      // the box is in registers: hand the stage back
+        if (++fstage == static_cast<uint32_t>(p.n_fstages)) { fstage = 0; fphase ^= 1u; }
+        const uint32_t half = static_cast<uint32_t>(kc & 1);
+        if (half == 0) mbar_wait(empty_a + stage * 8u, phase ^ 1u);   // MMAs that read this operand stage have retired
+#pragma unroll
+        for (uint32_t ch = 0; ch < 4; ++ch)
+          sts_u32x4(dst_row + stage * kStageBytes + (((half * 4u + ch) ^ sw) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_release_cluster(full_lead + stage * 8u);
+        if (half == 1 && ++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else if (warp >= 4) {
     // ================================================================== epilogue
     const int ew = warp - 4;          // 0..kEpiWarps-1
@@ -200,23 +269,34 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     EpiCtx cx;
     cx.cls_col = s_cls;
     cx.cnt_col = s_cnt;
-    const uint32_t list_id = blockIdx.x * static_cast<uint32_t>(kEpiWarps) + static_cast<uint32_t>(ew);   // private to this warp
+    const uint32_t list_id = blockIdx.x * static_cast<uint32_t>(kTcEpiWarps) + static_cast<uint32_t>(ew);   // private to this warp
     const SlowCtx sc = make_slow_ctx(p.s, DENSE ? 0u : list_id);
     cx.list_pos = DENSE ? 0u : p.s.st.list_count[list_id];
     cx.tau_col = s_tau;
-    const bool my_col_live = !DENSE && etid < NB && s_cls[etid] >= 0 && s_cnt[etid] > 0.0f;
-    const uint32_t* my_tau_src = &p.s.st.tau_enc[my_col_live ? s_cls[etid] : 0];
-    const float my_cnt = my_col_live ? s_cnt[etid] : 0.0f;
-    // each epilogue thread owns one column of the threshold table: the value for the NEXT tile is
+    // the epilogue threads own the columns of the threshold table between them: the values for the NEXT tile are
     // fetched while the current tile is processed
-    uint32_t tnext = 0;
-    if (my_col_live) tnext = ld_cg_u32(my_tau_src);
+    constexpr int kColsPer = 256 / (kEpiWarps * 32);
+    bool col_live[kColsPer];
+    const uint32_t* tau_src[kColsPer];
+    float col_cnt[kColsPer];
+    uint32_t tnext[kColsPer];
+#pragma unroll
+    for (int i = 0; i < kColsPer; ++i) {
+      const int col = etid + i * kEpiWarps * 32;
+      col_live[i] = !DENSE && col < NB && s_cls[col] >= 0 && s_cnt[col] > 0.0f;
+      tau_src[i] = &p.s.st.tau_enc[col_live[i] ? s_cls[col] : 0];
+      col_cnt[i] = col_live[i] ? s_cnt[col] : 0.0f;
+      tnext[i] = col_live[i] ? ld_cg_u32(tau_src[i]) : 0u;
+    }
     uint32_t it = 0;
     for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++it) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
-      if (my_col_live) {
-        s_tau[etid] = fast_tau<RED>(f32_dec(tnext), my_cnt);
-        tnext = ld_cg_u32(my_tau_src);
+#pragma unroll
+      for (int i = 0; i < kColsPer; ++i) {
+        if (col_live[i]) {
+          s_tau[etid + i * kEpiWarps * 32] = fast_tau<RED>(f32_dec(tnext[i]), col_cnt[i]);
+          tnext[i] = ld_cg_u32(tau_src[i]);
+        }
       }
       const int64_t row = t * kTileRows + rank * 128 + quad * 32 + lane;
       cx.row = static_cast<uint32_t>(row);
@@ -244,8 +324,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       // One-query-per-class: the two warps of a quadrant take interleaved 32-column chunks.
       // Grouped reduces walk columns in order, so the block is cut at a class boundary (`split`,
       // a multiple of 32 chosen by the host) and each warp takes one contiguous part.
-      constexpr bool kInterleave = (RED == RED_NONE);
-      const int split = kInterleave ? NB : p.blk_split[qb];
+      constexpr bool kInterleave = (RED == RED_NONE) && kEpiWarps == 8;
+      const int split = (kInterleave || kEpiWarps == 4) ? NB : p.blk_split[qb];
       const int first = kInterleave ? 32 * half : (half == 0 ? 0 : split);
       const int last = kInterleave ? NB : (half == 0 ? split : NB);
       constexpr int kStep = kInterleave ? 64 : 32;
@@ -288,9 +368,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   if (warp == 2) tmem_dealloc<kCtas>(tmem_base, 512);
 }
 
-template <int kCtas, int RED, bool PART, bool DENSE>
+template <int kCtas, int RED, bool PART, bool DENSE, bool F32>
 cudaError_t launch_one(const CUtensorMap& tm_bank, const CUtensorMap& tm_q, const TcArgs& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = scan_tc_kernel<kCtas, RED, PART, DENSE>;
+  auto kern = scan_tc_kernel<kCtas, RED, PART, DENSE, F32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -308,42 +388,55 @@ cudaError_t launch_one(const CUtensorMap& tm_bank, const CUtensorMap& tm_q, cons
   return cudaLaunchKernelEx(&cfg, kern, tm_bank, tm_q, p);
 }
 
-template <int kCtas, int RED>
+template <int kCtas, int RED, bool F32>
 cudaError_t launch_red(const CUtensorMap& a, const CUtensorMap& b, const TcArgs& p, bool part, bool dense, int grid, size_t smem, cudaStream_t s) {
-  if (dense) return launch_one<kCtas, RED, false, true>(a, b, p, grid, smem, s);
-  if (part) return launch_one<kCtas, RED, true, false>(a, b, p, grid, smem, s);
-  return launch_one<kCtas, RED, false, false>(a, b, p, grid, smem, s);
+  if (dense) return launch_one<kCtas, RED, false, true, F32>(a, b, p, grid, smem, s);
+  if (part) return launch_one<kCtas, RED, true, false, F32>(a, b, p, grid, smem, s);
+  return launch_one<kCtas, RED, false, false, F32>(a, b, p, grid, smem, s);
 }
-template <int kCtas>
+template <int kCtas, bool F32>
 cudaError_t launch_ctas(const CUtensorMap& a, const CUtensorMap& b, const TcArgs& p, int red, bool part, bool dense, int grid, size_t smem, cudaStream_t s) {
   switch (red) {
-    case RED_NONE: return launch_red<kCtas, RED_NONE>(a, b, p, part, dense, grid, smem, s);
-    case RED_MEAN: return launch_red<kCtas, RED_MEAN>(a, b, p, part, dense, grid, smem, s);
-    case RED_MAX: return launch_red<kCtas, RED_MAX>(a, b, p, part, dense, grid, smem, s);
-    default: return launch_red<kCtas, RED_MIN>(a, b, p, part, dense, grid, smem, s);
+    case RED_NONE: return launch_red<kCtas, RED_NONE, F32>(a, b, p, part, dense, grid, smem, s);
+    case RED_MEAN: return launch_red<kCtas, RED_MEAN, F32>(a, b, p, part, dense, grid, smem, s);
+    case RED_MAX: return launch_red<kCtas, RED_MAX, F32>(a, b, p, part, dense, grid, smem, s);
+    default: return launch_red<kCtas, RED_MIN, F32>(a, b, p, part, dense, grid, smem, s);
   }
 }
 
 }  // namespace
 
-size_t tc_smem_bytes(int n_blk, int ctas, int n_stages) {
+size_t tc_smem_bytes(int n_blk, int ctas, int n_stages, int n_fstages) {
   const size_t b = static_cast<size_t>(8) * (n_blk / ctas) * 128;
-  return 1024 /* alignment slack */ + b + static_cast<size_t>(n_stages) * kStageBytes + kTailBytes;
+  return 1024 /* alignment slack */ + b + static_cast<size_t>(n_stages + n_fstages) * kStageBytes + kTailBytes;
 }
 
 int tc_pick_stages(int n_blk, int ctas, size_t smem_limit) {
   for (int s = 8; s >= 2; --s)
-    if (tc_smem_bytes(n_blk, ctas, s) <= smem_limit) return s;
+    if (tc_smem_bytes(n_blk, ctas, s, 0) <= smem_limit) return s;
+  return 0;
+}
+
+// fp32 banks: `op` operand stages (64 k of bf16 each) + the returned number of staged fp32 boxes (32 k each)
+int tc_pick_fstages(int n_blk, int ctas, size_t smem_limit, int* op_stages) {
+  for (int op = 3; op >= 2; --op)
+    for (int f = 8; f >= (op == 3 ? 4 : 2); --f)
+      if (tc_smem_bytes(n_blk, ctas, op, f) <= smem_limit) { *op_stages = op; return f; }
+  *op_stages = 0;
   return 0;
 }
 
 cudaError_t launch_scan_tc(const void* tm_bank, const void* tm_q, const TcArgs& p, int ctas, int reduce, bool partitioned,
-                           bool dense, int grid, cudaStream_t stream) {
-  const size_t smem = tc_smem_bytes(p.n_blk, ctas, p.n_stages);
+                           bool dense, bool f32, int grid, cudaStream_t stream) {
+  const size_t smem = tc_smem_bytes(p.n_blk, ctas, p.n_stages, f32 ? p.n_fstages : 0);
   const CUtensorMap& a = *static_cast<const CUtensorMap*>(tm_bank);
   const CUtensorMap& b = *static_cast<const CUtensorMap*>(tm_q);
-  if (ctas == 2) return launch_ctas<2>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
-  return launch_ctas<1>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
+  if (f32) {
+    if (ctas == 2) return launch_ctas<2, true>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
+    return launch_ctas<1, true>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
+  }
+  if (ctas == 2) return launch_ctas<2, false>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
+  return launch_ctas<1, false>(a, b, p, reduce, partitioned, dense, grid, smem, stream);
 }
 
 }  // namespace swat

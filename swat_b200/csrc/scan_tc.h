@@ -10,20 +10,24 @@ struct TcArgs {
   ScanArgs s;
   int32_t n_qb;           // Q blocks (each keeps <=256 padded query columns resident in shared memory)
   int32_t n_blk;          // padded columns per Q block, multiple of 16
-  int32_t n_stages;       // bank-tile ring depth
+  int32_t n_stages;       // operand ring depth (stages of 128 rows x 64 k bf16)
+  int32_t n_fstages;      // fp32 banks: ring depth of the staged fp32 boxes (128 rows x 32 k)
   uint32_t smem_b_bytes;  // per-CTA bytes of the resident query block
   uint64_t bank_hint;     // L2 cache policy for bank tiles
   int32_t unit_base;      // unit plan: first unit of this launch (unit = unit_base + pair)
-  int32_t n_ranges;       // unit plan: tile ranges R (0 = single launch, Q block = pair % n_qb)
+  int32_t n_ranges;       // unit plan: tile ranges R (0 = legacy launch)
+  int32_t qb_base;        // legacy launch: covers the Q blocks [qb_base, qb_base + qb_count), block = qb_base + pair % qb_count
+  int32_t qb_count;
   const int32_t* blk_class;  // [n_qb+1] first class of each Q block
   const int32_t* blk_split;  // [n_qb] grouped reduces: column (multiple of 32) where the second epilogue warp set starts
 };
 
-size_t tc_smem_bytes(int n_blk, int ctas, int n_stages);
+size_t tc_smem_bytes(int n_blk, int ctas, int n_stages, int n_fstages);
 int tc_pick_stages(int n_blk, int ctas, size_t smem_limit);
-// tm_bank / tm_q: CUtensorMap*
+int tc_pick_fstages(int n_blk, int ctas, size_t smem_limit, int* op_stages);
+// tm_bank / tm_q: CUtensorMap*; f32: tm_bank describes an fp32 bank (boxes of 128 rows x 32 k)
 cudaError_t launch_scan_tc(const void* tm_bank, const void* tm_q, const TcArgs& p, int ctas, int reduce,
-                           bool partitioned, bool dense, int grid, cudaStream_t stream);
+                           bool partitioned, bool dense, bool f32, int grid, cudaStream_t stream);
 
 // SIMT fp32-FMA scan: any dtype, optional in-pass T2I predicate (bank2), exact reference arithmetic order
 cudaError_t launch_scan_simt(const ScanArgs& a, const void* bank, const void* bank2, const void* queries_padded,
@@ -36,21 +40,47 @@ cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset,
                           int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream);
 constexpr int kSelectLaunches = 3;
 
-struct T2iArgs {
-  const void* img_bank; int dtype; int64_t img_rows; int64_t img_row_base; const int64_t* img_index;
-  const void* queries;          // [Q,512] unpadded, same dtype as the bank
+// Exact re-score + accept walk over per-class candidate lists (select.cu).
+// The scan kernels rank rows by an APPROXIMATE score (tensor-core fp32 accumulation order; bf16-rounded operands for
+// fp32 banks): |approx - exact| <= eps.  Every candidate is re-scored with one fixed-order fp32 dot (the canonical
+// score: identical whichever engine produced the list), the list is re-sorted on (exact desc, row asc) and walked.
+// A truncated list (more eligible rows existed) only vouches for rows scoring above its frontier: the approximate
+// score of its last candidate plus eps.
+struct WalkArgs {
+  const void* t2t_bank;         // rows the candidates were ranked on (exact T2T re-score)
+  const void* aux_bank;         // nullable: predicate bank (image rows for T2T-rank-T2I-tshd, sample_retrieval.py:804-806)
+  int dtype;                    // of both banks
+  int64_t bank_rows;            // rows in the bank views
+  int64_t bank_row_base;        // id (as stored in cand_rows) of bank row 0
+  int64_t key_row_base;         // cand_rows - key_row_base fits 32 bits (the shard's row_offset): tie-break key
+  const int64_t* gather_index;  // nullable [C*stride]: the banks are compact gathers, candidate e reads row gather_index[e]
+  const void* queries;          // [Q,512] unpadded, same dtype as the banks
   const int32_t* class_begin;   // [C+1] first query of each class
   int reduce;
-  const float* cand_scores; const int64_t* cand_rows; const int32_t* cand_counts; const int32_t* truncated;
-  int k_fetch; int k; float t2i_thr; int n_classes;
-  float* t2i_scratch;           // [C, k_fetch]
-  float* out_scores; int64_t* out_rows; float* out_t2i; int32_t* out_counts; int32_t* incomplete;
+  // the predicate may have its own query set (few-shot image prompts, t2t_rank_i2t_tshd_sampler :831-890); same classes
+  const void* aux_queries; const int32_t* aux_class_begin; int aux_reduce;
+  const float* cand_scores; const int64_t* cand_rows; const int32_t* cand_counts; const int32_t* truncated;   // [C,stride] / [C]
+  int stride; int k; int n_classes;
+  float thr, aux_thr, eps;
+  int all_or_nothing;           // 1: a truncated list vouches for nothing (lists ranked on another metric: bank-swap pass)
+  float* exact_scratch; float* aux_scratch;      // [C,stride] each
+  float* out_scores; int64_t* out_rows; float* out_aux; int32_t* out_counts;   // [C,k] / [C]
+  float* out_limit;             // nullable [C]: -inf = proven exact, else rows scoring <= limit may be missing
+  int32_t* incomplete;          // nullable [C]: 1 = fewer than k accepted and the list cannot vouch for that
 };
-cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream);
+cudaError_t launch_rescore_walk(const WalkArgs& a, cudaStream_t stream);
+constexpr int kWalkLaunches = 2;
+
+// out[i] = canonical score of bank row i against the queries of class row_class[i] (-inf where row_class[i] < 0)
+cudaError_t launch_score_rows(const void* bank, int dtype, const int32_t* row_class, int64_t n_rows, const void* queries,
+                              const int32_t* class_begin, int n_classes, int reduce, float* out, cudaStream_t stream);
+// row_class of a sub-query run: out[i] = map[in[i]] (map: original class -> sub class or -1), -1 stays -1
+cudaError_t launch_remap_classes(const int32_t* in, const int32_t* map, int n_map, int64_t n, int32_t* out, cudaStream_t stream);
 
 cudaError_t launch_argmax_rows(const float* d_scores, int64_t n_rows, int n_classes, int32_t* d_pred, cudaStream_t stream);
+// d_limit [G,C] nullable: rows of shard g scoring <= d_limit[g][c] may be missing from its list
 cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, float aux_thr,
-                         const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int64_t shard_stride_bytes, int n_classes,
+                         const int32_t* d_counts, const float* d_limit, int n_shards, int64_t shard_stride_bytes, int n_classes,
                          int k, int k_out, uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
                          int32_t* d_out_counts, int32_t* d_incomplete, cudaStream_t stream);
 

@@ -252,56 +252,113 @@ template <> __device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfl
   }
 }
 
-// one warp per candidate: t2i = reduce over the class's queries of <image row, query>
-// (cal_t2i_similarity, sample_retrieval.py:335-353)
+// Canonical score of one (row, class) pair: per lane 16 consecutive elements in a sequential FMA chain, then an
+// xor-shuffle tree; group reduce over the class's queries in query order.  Every result the library returns is this
+// value, whichever scan engine ranked the row (t2t_similarity / cal_t2i_similarity, sample_retrieval.py:397-416, :335-353).
 template <typename T>
-__global__ void __launch_bounds__(256) t2i_rescore_kernel(const T2iArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t g = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (g >= static_cast<int64_t>(a.n_classes) * a.k_fetch) return;
-  const int c = static_cast<int>(g / a.k_fetch), j = static_cast<int>(g % a.k_fetch);
-  if (j >= a.cand_counts[c]) return;
-  const int64_t r = a.img_index ? a.img_index[g] : a.cand_rows[g] - a.img_row_base;
-  float t2i = 0.0f;
-  if (r >= 0 && r < a.img_rows) {
-    float x[16], q[16];
-    load16<T>(static_cast<const T*>(a.img_bank) + r * kDim + lane * 16, x);
-    const int q0 = a.class_begin[c], q1 = a.class_begin[c + 1];
-    float red = (a.reduce == RED_MAX) ? -INFINITY : (a.reduce == RED_MIN) ? INFINITY : 0.0f;
-    for (int qi = q0; qi < q1; ++qi) {
-      load16<T>(static_cast<const T*>(a.queries) + static_cast<size_t>(qi) * kDim + lane * 16, q);
-      float d = 0.0f;
+__device__ __forceinline__ float canonical_score(const float (&x)[16], const T* __restrict__ queries, int q0, int q1, int reduce, int lane) {
+  float red = (reduce == RED_MAX) ? -INFINITY : (reduce == RED_MIN) ? INFINITY : 0.0f;
+  for (int qi = q0; qi < q1; ++qi) {
+    float q[16];
+    load16<T>(queries + static_cast<size_t>(qi) * kDim + lane * 16, q);
+    float d = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) d = fmaf(x[i], q[i], d);
+    for (int i = 0; i < 16; ++i) d = fmaf(x[i], q[i], d);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-      if (a.reduce == RED_MAX) red = fmaxf(red, d);
-      else if (a.reduce == RED_MIN) red = fminf(red, d);
-      else if (a.reduce == RED_MEAN) red += d;
-      else red = d;
-    }
-    if (a.reduce == RED_MEAN) red = __fdiv_rn(red, static_cast<float>(q1 - q0));
-    t2i = red;
-  } else {
-    t2i = -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (reduce == RED_MAX) red = fmaxf(red, d);
+    else if (reduce == RED_MIN) red = fminf(red, d);
+    else if (reduce == RED_MEAN) red += d;
+    else red = d;
   }
-  if (lane == 0) a.t2i_scratch[g] = t2i;
+  if (reduce == RED_MEAN) red = __fdiv_rn(red, static_cast<float>(q1 - q0));
+  return red;
 }
 
-// accept walk of add_t2t_ranked_t2i_tshd_to_split (sample_retrieval.py:507-527): candidates are
-// already in T2T-descending order and pass the T2T threshold; keep those with t2i >= thr, stop at k.
-__global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) {
+// one warp per candidate: exact T2T score from the ranking bank and, with a predicate bank, the exact aux (T2I) score.
+// Both rows are requested before either is consumed.
+template <typename T>
+__global__ void __launch_bounds__(256) rescore_kernel(const WalkArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (g >= static_cast<int64_t>(a.n_classes) * a.stride) return;
+  const int c = static_cast<int>(g / a.stride), j = static_cast<int>(g % a.stride);
+  if (j >= a.cand_counts[c]) return;
+  const int64_t r = a.gather_index ? a.gather_index[g] : a.cand_rows[g] - a.bank_row_base;
+  float t2t = -INFINITY, aux = -INFINITY;
+  if (r >= 0 && r < a.bank_rows) {
+    float x[16], y[16];
+    load16<T>(static_cast<const T*>(a.t2t_bank) + r * kDim + lane * 16, x);
+    if (a.aux_bank) load16<T>(static_cast<const T*>(a.aux_bank) + r * kDim + lane * 16, y);
+    const int q0 = a.class_begin[c], q1 = a.class_begin[c + 1];
+    t2t = canonical_score<T>(x, static_cast<const T*>(a.queries), q0, q1, a.reduce, lane);
+    if (a.aux_bank)
+      aux = canonical_score<T>(y, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
+  }
+  if (lane == 0) {
+    a.exact_scratch[g] = t2t;
+    if (a.aux_bank) a.aux_scratch[g] = aux;
+  }
+}
+
+// Accept walk (add_to_split :439-482, add_t2t_ranked_t2i_tshd_to_split :507-527) over the re-scored candidates of one
+// class: order by (exact score desc, row asc), accept rows with exact >= thr and aux >= aux_thr, stop at k.  A
+// truncated list vouches only for rows above its frontier (approximate score of its last candidate + eps): anything
+// the scan left out scores at most that.
+__global__ void __launch_bounds__(kSelThreads) walk_kernel(const WalkArgs a) {
+  __shared__ uint64_t s_keys[kSortCap];
+  __shared__ uint16_t s_idx[kSortCap];
   __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_total;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = a.cand_counts[c];
-  constexpr int kPer = kMaxKFetch / kSelThreads;   // 4 consecutive candidates per thread
+  const uint32_t n = static_cast<uint32_t>(min(a.cand_counts[c], a.stride));
+  const size_t base = static_cast<size_t>(c) * a.stride;
+  const bool trunc = a.truncated != nullptr && a.truncated[c] != 0;
+  float frontier = -INFINITY;
+  if (trunc) frontier = a.all_or_nothing ? INFINITY : (n > 0 ? a.cand_scores[base + n - 1] + a.eps : INFINITY);
+  uint32_t P = 2;
+  while (P < n) P <<= 1;
+  for (uint32_t i = tid; i < P; i += kSelThreads) {
+    uint64_t key = 0ull;
+    if (i < n) {
+      const float e = a.exact_scratch[base + i];
+      if (e > -INFINITY) key = make_key(e + 0.0f, static_cast<uint32_t>(a.cand_rows[base + i] - a.key_row_base));
+    }
+    s_keys[i] = key;
+    s_idx[i] = static_cast<uint16_t>(i);
+  }
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < P; i += kSelThreads) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = s_keys[i], y = s_keys[ixj];
+          const bool desc = (i & kk) == 0;
+          if ((x < y) == desc) {
+            s_keys[i] = y; s_keys[ixj] = x;
+            const uint16_t t = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  constexpr int kPer = kSortCap / kSelThreads;   // 4 consecutive sorted positions per thread
   bool pass[kPer];
   uint32_t mine = 0;
 #pragma unroll
   for (int i = 0; i < kPer; ++i) {
-    const int j = tid * kPer + i;
-    pass[i] = (j < n) && (j < a.k_fetch) && (a.t2i_scratch[static_cast<size_t>(c) * a.k_fetch + j] >= a.t2i_thr);
-    mine += pass[i] ? 1u : 0u;
+    const uint32_t p = tid * kPer + i;
+    bool ok = false;
+    if (p < n) {
+      const uint64_t key = s_keys[p];
+      const float e = key_score(key);
+      ok = key != 0ull && e > frontier && e >= a.thr;
+      if (ok && a.aux_bank) ok = a.aux_scratch[base + s_idx[p]] >= a.aux_thr;
+    }
+    pass[i] = ok;
+    mine += ok ? 1u : 0u;
   }
   uint32_t inc = mine;
 #pragma unroll
@@ -322,7 +379,6 @@ __global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) 
   }
   __syncthreads();
   uint32_t pos = s_warp[warp] + inc - mine;
-  __shared__ uint32_t s_total;
   if (tid == kSelThreads - 1) s_total = pos + mine;
   __syncthreads();
   const uint32_t total = s_total;
@@ -330,11 +386,12 @@ __global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) 
   for (int i = 0; i < kPer; ++i) {
     if (pass[i]) {
       if (pos < static_cast<uint32_t>(a.k)) {
-        const size_t src = static_cast<size_t>(c) * a.k_fetch + tid * kPer + i;
+        const uint32_t p = tid * kPer + i;
+        const size_t src = base + s_idx[p];
         const size_t dst = static_cast<size_t>(c) * a.k + pos;
-        a.out_scores[dst] = a.cand_scores[src];
+        a.out_scores[dst] = key_score(s_keys[p]);
         a.out_rows[dst] = a.cand_rows[src];
-        if (a.out_t2i) a.out_t2i[dst] = a.t2i_scratch[src];
+        if (a.out_aux) a.out_aux[dst] = a.aux_bank ? a.aux_scratch[src] : 0.0f;
       }
       ++pos;
     }
@@ -344,12 +401,40 @@ __global__ void __launch_bounds__(kSelThreads) t2i_walk_kernel(const T2iArgs a) 
     const size_t dst = static_cast<size_t>(c) * a.k + i;
     a.out_scores[dst] = 0.0f;
     a.out_rows[dst] = -1;
-    if (a.out_t2i) a.out_t2i[dst] = 0.0f;
+    if (a.out_aux) a.out_aux[dst] = 0.0f;
   }
   if (tid == 0) {
     a.out_counts[c] = static_cast<int32_t>(cnt);
-    if (a.incomplete) a.incomplete[c] = (total < static_cast<uint32_t>(a.k) && a.truncated && a.truncated[c]) ? 1 : 0;
+    const bool complete = !trunc || total >= static_cast<uint32_t>(a.k);
+    if (a.out_limit) a.out_limit[c] = complete ? -INFINITY : frontier;
+    if (a.incomplete) a.incomplete[c] = complete ? 0 : 1;
   }
+}
+
+// canonical score of every row against the queries of ITS OWN class (partitioned data): one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) score_rows_kernel(const T* __restrict__ bank, const int32_t* __restrict__ row_class, int64_t n_rows,
+                                                          const T* __restrict__ queries, const int32_t* __restrict__ class_begin,
+                                                          int n_classes, int reduce, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int c = row_class[r];
+  float s = -INFINITY;
+  if (c >= 0 && c < n_classes) {
+    float x[16];
+    load16<T>(bank + r * kDim + lane * 16, x);
+    s = canonical_score<T>(x, queries, class_begin[c], class_begin[c + 1], reduce, lane);
+  }
+  if (lane == 0) out[r] = s;
+}
+
+__global__ void remap_classes_kernel(const int32_t* __restrict__ in, const int32_t* __restrict__ map, int n_map, int64_t n,
+                                     int32_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t c = in[i];
+  out[i] = (c >= 0 && c < n_map) ? map[c] : -1;
 }
 
 // ---------------------------------------------------------------------------------- shard merge
@@ -387,12 +472,12 @@ __global__ void merge_keys_kernel(const float* __restrict__ scores, const int64_
   keys[(static_cast<size_t>(c) * G + g) * k + j] = key;
 }
 
-// Global accept walk over the shards' candidate lists: the k_out best predicate-passing entries
-// under (score desc, row asc).  A shard whose list was truncated may hold unseen rows below its
-// last candidate; the result is proven exact only if it stays at or above every such frontier.
+// Global accept walk over the shards' lists: the k_out best predicate-passing entries under (score desc, row asc).
+// Shard g vouches only for rows scoring above limit[g][c] (-inf: its list is complete); the result is proven exact
+// only if all of it stays above every shard's limit.
 __global__ void __launch_bounds__(kSelThreads)
 merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores, const int64_t* __restrict__ rows,
-             const float* __restrict__ aux, const int32_t* __restrict__ counts, const int32_t* __restrict__ truncated,
+             const float* __restrict__ aux, const int32_t* __restrict__ counts, const float* __restrict__ limit,
              int G, ShardView sv, int C, int k, int k_out, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
              float* __restrict__ out_aux, int32_t* __restrict__ out_counts, int32_t* __restrict__ incomplete) {
   __shared__ uint64_t s_keys[kSortCap];
@@ -421,18 +506,10 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
   if (tid == 0) {
     out_counts[c] = static_cast<int32_t>(cnt);
     if (incomplete) {
-      uint64_t frontier = 0;
-      if (truncated) {
-        for (int g = 0; g < G; ++g) {
-          const int m = shard_ptr(counts, g, sv.small)[c];
-          if (shard_ptr(truncated, g, sv.small)[c] && m > 0) {
-            const size_t last = static_cast<size_t>(c) * k + (m - 1);
-            const uint64_t fk = make_key(shard_ptr(scores, g, sv.big_f32)[last] + 0.0f, static_cast<uint32_t>(shard_ptr(rows, g, sv.big_i64)[last]));
-            frontier = fk > frontier ? fk : frontier;
-          }
-        }
-      }
-      incomplete[c] = (frontier != 0ull && (cnt < static_cast<uint32_t>(k_out) || s_keys[cnt - 1] < frontier)) ? 1 : 0;
+      float lim = -INFINITY;
+      if (limit)
+        for (int g = 0; g < G; ++g) lim = fmaxf(lim, shard_ptr(limit, g, sv.small)[c]);
+      incomplete[c] = (lim > -INFINITY && (cnt < static_cast<uint32_t>(k_out) || key_score(s_keys[cnt - 1]) <= lim)) ? 1 : 0;
     }
   }
   if (out_aux && aux) {
@@ -526,15 +603,34 @@ cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t str
   return cudaGetLastError();
 }
 
-cudaError_t launch_t2i_walk(const T2iArgs& a, cudaStream_t stream) {
-  const int64_t n = static_cast<int64_t>(a.n_classes) * a.k_fetch;
+cudaError_t launch_rescore_walk(const WalkArgs& a, cudaStream_t stream) {
+  const int64_t n = static_cast<int64_t>(a.n_classes) * a.stride;
   if (n <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((n + 7) / 8);
-  if (a.dtype == 0) t2i_rescore_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
-  else t2i_rescore_kernel<float><<<grid, 256, 0, stream>>>(a);
+  if (a.dtype == 0) rescore_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
+  else rescore_kernel<float><<<grid, 256, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  t2i_walk_kernel<<<a.n_classes, kSelThreads, 0, stream>>>(a);
+  walk_kernel<<<a.n_classes, kSelThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_score_rows(const void* bank, int dtype, const int32_t* row_class, int64_t n_rows, const void* queries,
+                              const int32_t* class_begin, int n_classes, int reduce, float* out, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((n_rows + 7) / 8);
+  if (dtype == 0)
+    score_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(bank), row_class, n_rows,
+                                                              static_cast<const __nv_bfloat16*>(queries), class_begin, n_classes, reduce, out);
+  else
+    score_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(bank), row_class, n_rows,
+                                                        static_cast<const float*>(queries), class_begin, n_classes, reduce, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_remap_classes(const int32_t* in, const int32_t* map, int n_map, int64_t n, int32_t* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  remap_classes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, map, n_map, n, out);
   return cudaGetLastError();
 }
 
@@ -568,7 +664,7 @@ cudaError_t launch_argmax_rows(const float* d_scores, int64_t n_rows, int n_clas
 }
 
 cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const float* d_aux, float aux_thr,
-                         const int32_t* d_counts, const int32_t* d_truncated, int n_shards, int64_t shard_stride_bytes, int n_classes,
+                         const int32_t* d_counts, const float* d_limit, int n_shards, int64_t shard_stride_bytes, int n_classes,
                          int k, int k_out, uint64_t* d_key_scratch, float* d_out_scores, int64_t* d_out_rows, float* d_out_aux,
                          int32_t* d_out_counts, int32_t* d_incomplete, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(n_shards) * n_classes * k;
@@ -578,7 +674,7 @@ cudaError_t launch_merge(const float* d_scores, const int64_t* d_rows, const flo
                                                                                   n_shards, sv, n_classes, k, d_key_scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_scores, d_rows, d_aux, d_counts, d_truncated, n_shards, sv,
+  merge_kernel<<<n_classes, kSelThreads, 0, stream>>>(d_key_scratch, d_scores, d_rows, d_aux, d_counts, d_limit, n_shards, sv,
                                                       n_classes, k, k_out, d_out_scores, d_out_rows, d_out_aux, d_out_counts,
                                                       d_incomplete);
   return cudaGetLastError();

@@ -260,17 +260,19 @@ def _flatten(pre_extracted_feats, classes: List[str]):
     return torch.cat(caps), torch.cat(imgs), paths, torch.cat(rc)
 
 
-def _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_images_dict):
+def _exclusion_sets(duplicates_dict, filtered_images_dict):
     sets = {}
     for d in (duplicates_dict, filtered_images_dict):
         if d:
             for k, v in d.items():
                 if v:
                     sets.setdefault(str(k), set()).update(v)
-    if not sets:
-        return None
-    if row_class is None:
-        raise NotImplementedError("per-class exclusion sets need the partitioned layout (one class per row)")
+    return sets
+
+
+def _exclusion_bitmap(paths, classes, row_class, sets):
+    """Row-level bitmap for the partitioned layout (a row belongs to one class, so "excluded for its class" is a row
+    property): bit set = never accept (``add_to_split`` :454-456)."""
     index = {p: i for i, p in enumerate(paths)}
     ex = np.zeros(len(paths), dtype=bool)
     for k, v in sets.items():
@@ -280,7 +282,7 @@ def _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_image
                 ex[i] = True
     bits = np.packbits(ex, bitorder="little")
     bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)]).view(np.int32)
-    return torch.from_numpy(bits.copy())
+    return torch.from_numpy(bits.copy()), ex
 
 
 def check_caption(caption_map, img_path):
@@ -302,6 +304,64 @@ def _fewshot_queries(fewshot_fea, classes):
     return torch.cat(rows), torch.tensor(coq, dtype=torch.int32)
 
 
+def _load_caption_map(args):
+    cmap_path = getattr(args, "caption_map_path", None)
+    if cmap_path is None:
+        try:
+            from .config import CAPTION_MAP_DICT
+            cmap_path = CAPTION_MAP_DICT.get(args.dataset)
+        except Exception:
+            cmap_path = None
+    if cmap_path and os.path.exists(cmap_path):
+        with open(cmap_path, "rb") as f:                                              # :730-732
+            return pickle.load(f)
+    return None
+
+
+def _score_own_class(ctx, qs, bank, row_class, device, chunk=1 << 20):
+    """Per-row canonical score against the row's own class (``swat_score_rows``); host banks go through the device in chunks."""
+    if bank.is_cuda:
+        return _lib.score_rows(ctx, qs, bank.contiguous(), row_class.to(bank.device)).cpu()
+    out = []
+    for s0 in range(0, bank.shape[0], chunk):
+        out.append(_lib.score_rows(ctx, qs, bank[s0:s0 + chunk].contiguous().cuda(device), row_class[s0:s0 + chunk].cuda(device)).cpu())
+    return torch.cat(out) if out else torch.zeros(0)
+
+
+def _filtered_lines(classes, row_class, paths, t2t_all, pred_all, excluded, num_samples, threshold, t2i_threshold, caption_map):
+    """The reference's ``filtered_list`` (:463-469, :521-527) for partitioned data: per class, walk the class's rows in
+    (score desc, row asc) order until ``num_samples`` are accepted and report every rejected row met on the way --
+    all remaining rows when the class never fills."""
+    rc = row_class.numpy()
+    order = np.argsort(rc, kind="stable")
+    starts = np.searchsorted(rc[order], np.arange(len(classes) + 1))
+    t2t_np = t2t_all.numpy()
+    pred_np = None if pred_all is None else pred_all.numpy()
+    lines: List[str] = []
+    for i, _cls in enumerate(classes):
+        rows = order[starts[i]:starts[i + 1]]
+        if rows.size == 0:
+            continue
+        s = t2t_np[rows]
+        o = np.lexsort((rows, -s.astype(np.float64)))
+        rows, s = rows[o], s[o]
+        ok = s >= threshold
+        if pred_np is not None:
+            ok &= pred_np[rows] >= t2i_threshold
+        if excluded is not None:
+            ok &= ~excluded[rows]
+        filled = np.nonzero(np.cumsum(ok) == num_samples)[0]
+        end = int(filled[0]) + 1 if filled.size else rows.size
+        for j in np.nonzero(~ok[:end])[0].tolist():
+            r = int(rows[j]); p = paths[r]
+            caption = check_caption(caption_map, p) if caption_map is not None else ""
+            if pred_np is not None:
+                lines.append(f"{round(float(s[j]), 4)}/{threshold}, {round(float(pred_np[r]), 4)}/{t2i_threshold}, {p}, {caption}")
+            else:
+                lines.append(f"{round(float(s[j]), 4)}/{threshold}, {p}, {caption}")
+    return lines
+
+
 def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extracted_feats, duplicates_dict,
                  filtered_images_dict, with_t2i: bool, t2i_threshold: float = 0.25, rank_on_images: bool = False,
                  rank_fewshot=None, pred_fewshot=None, pred_on_captions: bool = False, file_prefix: Optional[bool] = None):
@@ -313,6 +373,9 @@ def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extra
                     few-shot vectors (``pred_fewshot``) against the image / caption bank, ``>= t2i_threshold``.
     """
     classes = sorted(list(pre_extracted_feats.keys()), key=lambda x: int(x))          # :734-735
+    empty = set()
+    if not isinstance(pre_extracted_feats, RegroupedFeats):
+        empty = {c for c in classes if pre_extracted_feats[c]["file_paths"] is None}   # :743-745: skipped, no dict entry
     cap, img, paths, row_class = _flatten(pre_extracted_feats, classes)
     feat_bank = img                                          # feature_list always carries the image features (:753, :1225)
     bank_dtype = getattr(args, "bank_dtype", None)
@@ -321,6 +384,7 @@ def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extra
     elif cap.dtype not in (torch.float32, torch.bfloat16):
         cap = cap.float(); img = img.float()
     rank_bank = img if rank_on_images else cap               # T2I-rank / I2I-rank score the image bank (:1224, :1049)
+    pred_bank = cap if pred_on_captions else img             # what the accept predicate is evaluated on
     device = int(getattr(args, "device_index", 0))
     ctx = get_context(device)
     if rank_fewshot is not None:                             # I2I-rank / I2T-rank: mean over the few-shot columns (:1049, :1112)
@@ -329,83 +393,114 @@ def _run_sampler(args, logger, prompt_tensors, num_samples, threshold, pre_extra
     else:
         q = torch.stack([torch.as_tensor(prompt_tensors[c]["mean"]).detach().float().cpu().reshape(-1) for c in classes])  # :749
         qs = _lib.Queries(ctx, q)
-    exclude = _exclusion_bitmap(paths, classes, row_class, duplicates_dict, filtered_images_dict)
+    sets = _exclusion_sets(duplicates_dict, filtered_images_dict)
+    exclude, excluded_rows, k_run = None, None, int(num_samples)
+    if sets and row_class is not None:
+        exclude, excluded_rows = _exclusion_bitmap(paths, classes, row_class, sets)
+    elif sets:
+        # unpartitioned (every class scans the whole bank): a path excluded for one class stays eligible for the others,
+        # so walk deep enough to cover the largest exclusion set and drop the excluded paths on the host
+        k_run = num_samples + max(len(v) for v in sets.values())
+        if k_run > 4096:
+            raise NotImplementedError(f"per-class exclusion sets of up to {k_run - num_samples} files on an unpartitioned bank "
+                                      "exceed the walk depth; regroup the features by label (transform_extracted_fea)")
+    qs_pred = None
     if pred_fewshot is None:
         t2i_bank = img if with_t2i else None
         if rank_bank.is_cuda:
-            res = _lib.topk(ctx, qs, rank_bank.contiguous(), num_samples, threshold,
+            res = _lib.topk(ctx, qs, rank_bank.contiguous(), k_run, threshold,
                             t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(), t2i_threshold=t2i_threshold,
                             row_class=None if row_class is None else row_class.cuda(device),
                             exclude=None if exclude is None else exclude.cuda(device))
             scores, rows, t2i, counts = [None if x is None else x.cpu() for x in res]
         else:
-            scores, rows, t2i, counts = _lib.topk_host(ctx, qs, rank_bank.contiguous(), num_samples, threshold,
+            scores, rows, t2i, counts = _lib.topk_host(ctx, qs, rank_bank.contiguous(), k_run, threshold,
                                                       t2i_bank=None if t2i_bank is None else t2i_bank.contiguous(),
                                                       t2i_threshold=t2i_threshold, row_class=row_class, exclude=exclude)
     else:
         # predicate with its own query set: max over the class's few-shot vectors (:869, :929), on the
         # caption bank (I2T) or the image bank (I2I).  Composed from the job / walk entry points; the
         # over-fetch deepens until every class is provably exact (candidate list not truncated, or k accepted).
-        from . import dist as _dist
         pq, pcoq = _fewshot_queries(pred_fewshot, classes)
         qs_pred = _lib.Queries(ctx, pq, pcoq, len(classes), "max")
         d_rank = rank_bank.contiguous().cuda(device)
-        d_pred = (cap if pred_on_captions else img).contiguous().cuda(device)
+        d_pred = pred_bank.contiguous().cuda(device)
         d_rc = None if row_class is None else row_class.cuda(device)
         d_ex = None if exclude is None else exclude.cuda(device)
-        kf = min(4096, max(1024, 2 * num_samples))
+        eps = _lib.scan_eps(qs, d_rank.dtype)
+        kf = min(4096, max(1024, 2 * k_run))
         while True:
-            sc, rw, _, cn, tr = _dist.local_candidates(ctx, qs, d_rank, kf, threshold, None, 0, d_rc, d_ex)
-            o_s, o_r, o_t, o_c, o_i = _lib.t2i_walk(ctx, qs_pred, d_pred, sc, rw, cn, tr, num_samples, t2i_threshold)
+            job = _lib.Job(ctx, qs, kf, threshold - eps)
+            job.scan(d_rank, row_class=d_rc, exclude=d_ex)
+            sc, rw, cn, tr = job.select()
+            over = job.overflowed()
+            job.close()
+            if over:
+                ctx.set_option("cand_cap", 8 * kf + 16384); ctx.set_option("list_entries", 64 << 20)
+                continue
+            o_s, o_r, o_t, o_c, _, o_i = _lib.rescore_walk(ctx, qs, d_rank, sc, rw, cn, tr, k_run, threshold, aux_bank=d_pred,
+                                                          aux_threshold=t2i_threshold, eps=eps, aux_queries=qs_pred)
             if int(o_i.sum()) == 0:
                 break
             if kf >= 4096:
                 raise _lib.SwatError(-5, "few-shot predicate walk not provably exact at k_fetch=4096 "
                                          "(more than 4096 eligible rows in a class and fewer than k pass)")
             kf = min(4096, kf * 2)
+        ctx.set_option("cand_cap", 0); ctx.set_option("list_entries", 0)
         scores, rows, t2i, counts = o_s.cpu(), o_r.cpu(), o_t.cpu(), o_c.cpu()
-        qs_pred.close()
         with_t2i = True
-    qs.close()
-    caption_map = None
-    cmap_path = getattr(args, "caption_map_path", None)
-    if cmap_path is None:
-        try:
-            from .config import CAPTION_MAP_DICT
-            cmap_path = CAPTION_MAP_DICT.get(args.dataset)
-        except Exception:
-            cmap_path = None
-    if cmap_path and os.path.exists(cmap_path):
-        with open(cmap_path, "rb") as f:                                              # :730-732
-            caption_map = pickle.load(f)
+    caption_map = _load_caption_map(args)
     mined_split = {"feature_list": [], "label_list": [], "file_list": []}
     num_imgs_sampled_dict = {}
     sampled_list: List[str] = []
     img = feat_bank
     img_host = img if not img.is_cuda else None
     for i, cls in enumerate(classes):
+        if cls in empty:
+            logger.info(f"class {cls} has no images. Continue")                       # :744
+            continue
         n = int(counts[i])
+        r = rows[i, :n]
+        sc = scores[i, :n].tolist()
+        ti = t2i[i, :n].tolist() if t2i is not None else None
+        if k_run != num_samples:                             # host-side exclusion (unpartitioned): drop, keep the first num_samples
+            bad = sets.get(str(cls), ())
+            keep = [j for j, row in enumerate(r.tolist()) if paths[row] not in bad][:num_samples]
+            r = r[keep]; sc = [sc[j] for j in keep]; ti = None if ti is None else [ti[j] for j in keep]
+            n = len(keep)
         num_imgs_sampled_dict[cls] = n
         if n == 0:
             continue                                                                  # :472-474
-        r = rows[i, :n]
         files = [paths[j] for j in r.tolist()]
         feats = (img_host[r] if img_host is not None else img[r.to(img.device)].cpu()).float()
         mined_split["feature_list"].append(feats)
         mined_split["label_list"].append(torch.full((n,), int(cls), dtype=torch.int64))
         mined_split["file_list"].append(files)
-        sc = scores[i, :n].tolist()
-        ti = t2i[i, :n].tolist() if t2i is not None else None
         for j, p in enumerate(files):
             caption = check_caption(caption_map, p) if caption_map is not None else ""
             if with_t2i:
                 sampled_list.append(f"{round(sc[j], 4)}/{threshold}, {round(ti[j], 4)}/{t2i_threshold}, {p}, {caption}")
             else:
                 sampled_list.append(f"{round(sc[j], 4)}/{threshold}, {p}, {caption}")
-    logger.info(f"len(sampled_list): {len(sampled_list)}")
     prefixed = (not with_t2i) if file_prefix is None else file_prefix                 # :763,768,1236,1241 vs :817,822
     prefix = f"{args.prefix}_" if prefixed else ""
     os.makedirs(args.output_folder, exist_ok=True)
+    # filtered_list (:761-764, :815-818): the rejected rows the walk met.  Partitioned data only (per class it lists up to
+    # every row of the class); args.filtered_list = False skips this diagnostic and its extra pass over the bank.
+    if row_class is not None and getattr(args, "filtered_list", True):
+        t2t_all = _score_own_class(ctx, qs, rank_bank, row_class, device)
+        pred_all = None
+        if with_t2i:
+            pred_all = _score_own_class(ctx, qs_pred if qs_pred is not None else qs, pred_bank, row_class, device)
+        filtered_list = _filtered_lines(classes, row_class, paths, t2t_all, pred_all, excluded_rows, num_samples, threshold,
+                                        t2i_threshold, caption_map)
+        logger.info(f"len(filtered_list): {len(filtered_list)}")
+        with open(f"{args.output_folder}/{prefix}filtered_list.txt", "w") as f:
+            f.write("\n".join(filtered_list))
+    if qs_pred is not None:
+        qs_pred.close()
+    qs.close()
+    logger.info(f"len(sampled_list): {len(sampled_list)}")
     with open(f"{args.output_folder}/{prefix}sampled_list.txt", "w") as f:
         f.write("\n".join(sampled_list))
     return mined_split, num_imgs_sampled_dict
@@ -576,10 +671,34 @@ def save_sample_file_list(args, final_file_list, label_tensor, logger=None, copy
     return fn
 
 
-def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=None, copy_to: Optional[str] = None):
-    """The hot part of ``sampling`` (:1471-1670): load + regroup the mined features, dispatch on
-    ``args.sampling_method`` (T2T-rank :1571-1579, T2T-rank-T2I-tshd :1581-1589, T2I-rank :1610-1617), write
-    ``{prefix}.txt`` and ``{prefix}_num_imgs_sampled.json``.  Returns ``(file_list_path, sample_ct)``."""
+# Module globals of the reference script that ``sampling`` reads (set under ``__main__`` there, :1736-1740): the CLI
+# (swat_b200/sample_retrieval.py) or the embedding application assigns them before calling ``sampling``.
+prompt_tensors_dict: Dict[str, dict] = {}
+
+
+def _zeroshot_head_weight(prompt_tensors) -> torch.Tensor:
+    """``features.prompt_sampler(prompt_tensors, sample_by='mean')`` (utils/features.py:12-24): the class prompts stacked
+    in dict order -> weights of the zero-shot head ``MyLinear(weights=..., bias=False)`` (:1489-1490)."""
+    return torch.stack([torch.as_tensor(prompt_tensors[k]["mean"]).detach().float().cpu().reshape(-1) for k in prompt_tensors.keys()], dim=0)
+
+
+def sampling(args, logger, model=None, preprocess=None, metrics=None, dataset_root=None, *, prompt_tensors=None,
+             pre_extracted_feats=None, copy_to: Optional[str] = "default"):
+    """``sampling(args, logger, model, preprocess, metrics, dataset_root)`` (:1471-1670), same positional signature and
+    return value ``(file_list_path, sample_ct)``: load + regroup the mined features, optional zero-shot filtering
+    (:1484-1497) and near-duplicate removal (:1499-1507) feeding the exclusion sets of every sampler, dispatch on
+    ``args.sampling_method`` (:1517-1617), write ``{prefix}.txt`` and ``{prefix}_num_imgs_sampled.json``.
+
+    ``model`` / ``preprocess`` / ``metrics`` are accepted for signature compatibility and unused on this path (the
+    reference passes them on to code that requires pre-extracted features anyway, :293-297).  The prompt tensors come
+    from the module global ``prompt_tensors_dict[args.prompt_name]`` like in the reference (:1489, :1519), or from the
+    keyword ``prompt_tensors``.  Keyword extensions: ``pre_extracted_feats`` (skip the load), ``copy_to`` (where the
+    split txt is copied; default ``../data/{dataset}/`` :1466, ``None`` = no copy)."""
+    if prompt_tensors is None:
+        if getattr(args, "prompt_name", None) not in prompt_tensors_dict:
+            raise KeyError(f"prompt tensors for prompt_name={getattr(args, 'prompt_name', None)!r} not set: assign "
+                           "swat_b200.retrieval.prompt_tensors_dict (the reference's module global) or pass prompt_tensors=")
+        prompt_tensors = prompt_tensors_dict[args.prompt_name]
     if pre_extracted_feats is None:
         fn = f"{dataset_root}/{args.dataset}_{args.model_cfg}_mined.pth"
         if not os.path.exists(fn):
@@ -589,26 +708,46 @@ def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=Non
         pre_extracted_feats = load_mined_pth(fn)
         logger.info(f"Loaded pre-extracted mined features from: {fn}")
     feats = transform_extracted_fea(pre_extracted_feats) if "labels" in pre_extracted_feats else pre_extracted_feats
+    # ---------- zero-shot CLIP image filtering (:1484-1497)
+    if not getattr(args, "zeroshot_img_filter", False):
+        logger.info("No zeroshot image filtering!")
+        filtered_images_dict = defaultdict(set)
+    else:
+        logger.info("Doing zeroshot image filtering!")
+        filtered_images_dict = zeroshot_clip_img_filter(model=model, preprocess=preprocess, root_folder=getattr(args, "root_folder", None),
+                                                        pre_extracted_feats=feats, head=_zeroshot_head_weight(prompt_tensors))
+    # ---------- image de-duplication (:1499-1507)
+    if not getattr(args, "image_dedup", False):
+        logger.info("No image deduplication!")
+        duplicate_images_dict = defaultdict(set)
+    else:
+        logger.info("Doing image deduplication!")
+        duplicate_images_dict, dup_images_fraction, avg_dup_images_fraction = remove_near_duplicates2(feats)
+        logger.info(f"dup_images_fraction: {dup_images_fraction}")
+        logger.info(f"avg_dup_images_fraction: {avg_dup_images_fraction}")
     logger.info(f"Sampling method: {args.sampling_method}, sampling number: {args.num_samples}, "
                 f"sampling threshold: {args.sampling_threshold}")
-    if args.sampling_method == "Random":                                             # :1517-1526
-        mined_split, num_imgs_sampled_dict = random_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "T2T-rank":
-        mined_split, num_imgs_sampled_dict = t2t_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "T2T-rank-T2I-tshd":
-        mined_split, num_imgs_sampled_dict = t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "T2I-rank":                                         # :1610-1617
-        mined_split, num_imgs_sampled_dict = t2i_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "I2I-rank":                                         # :1538-1551
-        mined_split, num_imgs_sampled_dict = i2i_ranked_sampler_p2p(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "I2T-rank":                                         # :1553-1560
-        mined_split, num_imgs_sampled_dict = i2t_rank_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "T2T-rank-I2T-tshd":                                # :1591-1598
-        mined_split, num_imgs_sampled_dict = t2t_rank_i2t_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
-    elif args.sampling_method == "T2T-rank-I2I-tshd":                                # :1600-1607
-        mined_split, num_imgs_sampled_dict = t2t_rank_i2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats)
+    kw = dict(duplicates_dict=duplicate_images_dict, filtered_images_dict=filtered_images_dict)
+    m = args.sampling_method
+    if m == "Random":                                                                # :1517-1526
+        mined_split, num_imgs_sampled_dict = random_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, tail_head=False, **kw)
+    elif m == "T2T-rank":                                                            # :1571-1579
+        mined_split, num_imgs_sampled_dict = t2t_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
+    elif m == "T2T-rank-T2I-tshd":                                                   # :1581-1589
+        mined_split, num_imgs_sampled_dict = t2t_ranked_t2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
+    elif m == "T2I-rank":                                                            # :1610-1617
+        mined_split, num_imgs_sampled_dict = t2i_ranked_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
+    elif m == "I2I-rank":                                                            # :1538-1551
+        mined_split, num_imgs_sampled_dict = i2i_ranked_sampler_p2p(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
+    elif m == "I2T-rank":                                                            # :1553-1560
+        mined_split, num_imgs_sampled_dict = i2t_rank_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
+    elif m == "T2T-rank-I2T-tshd":                                                   # :1591-1598
+        mined_split, num_imgs_sampled_dict = t2t_rank_i2t_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
+    elif m == "T2T-rank-I2I-tshd":                                                   # :1600-1607
+        mined_split, num_imgs_sampled_dict = t2t_rank_i2i_tshd_sampler(args, logger, prompt_tensors, args.num_samples, 0.0, feats, **kw)
     else:
-        raise NotImplementedError(f"sampling method {args.sampling_method} is outside the accelerated hot path")
+        raise NotImplementedError(f"sampling method {m} is outside the accelerated hot path")
+    logger.info(f"len(file_list): {len(mined_split['file_list'])}")
     final_file_list = [p for fl in mined_split["file_list"] for p in fl]
     logger.info(f"len(final_file_list): {len(final_file_list)}")
     labels_tensor = torch.cat(mined_split["label_list"], dim=0) if mined_split["label_list"] else torch.zeros(0, dtype=torch.int64)
@@ -616,6 +755,8 @@ def sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=Non
         feature_tensor = torch.cat(mined_split["feature_list"], dim=0)
         logger.info(f"feature_tensor.shape: {feature_tensor.shape}")
     logger.info(f"labels_tensor.shape: {labels_tensor.shape}")
+    if copy_to == "default":
+        copy_to = f"../data/{args.dataset}/"                                         # :1466
     file_list_path = save_sample_file_list(args, final_file_list, labels_tensor, logger, copy_to)
     with open(f"{args.output_folder}/{args.prefix}_num_imgs_sampled.json", "w") as f:
         json.dump(num_imgs_sampled_dict, f, indent=4)                               # :1666-1668

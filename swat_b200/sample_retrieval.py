@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Drop-in for ``python retrieval/sample_retrieval.py`` (reference CLI at ``sample_retrieval.py:1673-1747``)
-for the ranked sampling methods: ``T2T-rank``, ``T2T-rank-T2I-tshd``, ``T2I-rank``, ``I2I-rank``, ``I2T-rank``,
-``T2T-rank-I2T-tshd``, ``T2T-rank-I2I-tshd``.
+for ``Random`` and the ranked sampling methods: ``T2T-rank``, ``T2T-rank-T2I-tshd``, ``T2I-rank``, ``I2I-rank``,
+``I2T-rank``, ``T2T-rank-I2T-tshd``, ``T2T-rank-I2I-tshd``, with ``--zeroshot_img_filter`` / ``--image_dedup``.
 
 Same flags and defaults, same outputs: ``output/{dataset}_{model_cfg}_{prefix}/{prefix}.txt``
 (``"<path> <label> 0"`` per accepted row, class-major), ``{prefix}_num_imgs_sampled.json``,
 ``sampling.log``, and a copy of the txt in ``../data/{dataset}/``.  Additive flags: ``--bank_dtype``
-(``f32`` keeps the reference's fp32 features and the exact fp32 kernel, ``bf16`` uses the tcgen05
-path), ``--prompt_tensors`` (a cached prompt-tensor ``.pth`` as written by ``cal_prompt_tensors``
+(``f32`` keeps the reference's fp32 features: the tcgen05 scan converts them to bf16 on the fly and every
+candidate is re-scored exactly in fp32; ``bf16`` rounds the features once and halves the bytes streamed), ``--prompt_tensors`` (a cached prompt-tensor ``.pth`` as written by ``cal_prompt_tensors``
 ``:1433-1450``; the OpenCLIP text encoder that produces it is outside this package), ``--mined_pth``
 / ``--flat_shard`` to point at the feature file directly.
 """
@@ -74,12 +74,10 @@ def build_parser():
 def main(argv=None):
     time_start = time()
     args = build_parser().parse_args(argv)
-    if args.sampling_method not in ("T2T-rank", "T2T-rank-T2I-tshd", "T2I-rank", "I2I-rank", "I2T-rank", "T2T-rank-I2T-tshd",
-                                    "T2T-rank-I2I-tshd"):
+    if args.sampling_method not in ("Random", "T2T-rank", "T2T-rank-T2I-tshd", "T2I-rank", "I2I-rank", "I2T-rank",
+                                    "T2T-rank-I2T-tshd", "T2T-rank-I2I-tshd"):
         raise NotImplementedError(f"--sampling_method {args.sampling_method} is outside the accelerated hot path; "
                                   "use the reference script for it")
-    if args.zeroshot_img_filter or args.image_dedup:
-        raise NotImplementedError("--zeroshot_img_filter / --image_dedup are outside the accelerated hot path (SURVEY.md 8f)")
     os.makedirs("output", exist_ok=True)
     random.seed(args.seed)
     torch.manual_seed(args.seed)
@@ -97,13 +95,15 @@ def main(argv=None):
     if not os.path.exists(prompts_fn):
         raise FileNotFoundError(f"prompt tensors not found: {prompts_fn} (produce them with the reference's cal_prompt_tensors)")
     prompt_tensors_dict = torch.load(prompts_fn, map_location="cpu", weights_only=False)       # saved as CUDA tensors (:52)
-    prompt_tensors = prompt_tensors_dict.get(args.prompt_name, prompt_tensors_dict)
+    if args.prompt_name not in prompt_tensors_dict:              # a bare {cls: {'mean', 'all'}} dict
+        prompt_tensors_dict = {args.prompt_name: prompt_tensors_dict}
+    retrieval.prompt_tensors_dict = prompt_tensors_dict          # the reference's module global (:1740)
     feats = None
     if args.flat_shard:
         feats = shards.FlatShard(args.flat_shard).as_mined_dict()
     elif args.mined_pth:
         feats = shards.load_mined_pth(args.mined_pth)
-    file_list_path, sample_ct = retrieval.sampling(args, logger, prompt_tensors, dataset_root, pre_extracted_feats=feats,
+    file_list_path, sample_ct = retrieval.sampling(args, logger, None, None, None, dataset_root, pre_extracted_feats=feats,
                                                    copy_to=os.path.join(args.data_dir, args.dataset))
     logger.info(f"sample_ct: {sample_ct}")
     logger.info(f"file_list_path: {file_list_path}")

@@ -42,8 +42,8 @@ def main():
             bit = torch.equal(res[1], full[1]) and torch.equal(res[3], full[3]) and torch.equal(res[0], full[0])
             if t2i is not None:
                 bit = bit and torch.equal(res[2], full[2])
-            # parity rule when a class fell back to the fp32 in-pass predicate on one side only (tensor-core
-            # and fp32-FMA scores differ in the last bits): same counts, same rows up to near-tie swaps
+            # scores are canonical (one fixed-order fp32 dot per returned row), so sharded and single-GPU results must
+            # agree bit for bit whichever engine or escalation path either side took; `same` only explains a failure
             same = torch.equal(res[3], full[3]) and torch.allclose(res[0], full[0], atol=2e-5)
             mism = int(((res[1] != full[1]) & (full[1] >= 0)).sum())
             for c in ((res[1] != full[1]).any(1)).nonzero().flatten().tolist():
@@ -51,7 +51,7 @@ def main():
                 same = same and set(res[1][c, :n].tolist()) == set(full[1][c, :n].tolist())
             print(f"world={world} {'T2T+T2I' if t2i is not None else 'T2T'}: sharded == single-GPU: bit-identical {bit}, parity {same} "
                   f"({mism} positions swapped between near-ties); accepted {int(full[3].sum())}", flush=True)
-            ok = ok and same
+            ok = ok and bit
             del fcap, fimg
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)

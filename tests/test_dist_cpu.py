@@ -1,5 +1,5 @@
 """Host-side logic of the row-sharded multi-GPU path on CPU: world_size-2 gloo all-gather of packed
-candidate lists + merge walk (the CUDA merge is replaced by the oracle through `merge_fn`)."""
+per-shard walk results + merge (the CUDA merge is replaced by the oracle through `merge_fn`)."""
 import os
 import sys
 
@@ -29,57 +29,86 @@ def test_pack_unpack_roundtrip():
     C, k, W = 5, 7, 3
     parts = []
     for w in range(W):
+        lim = torch.randn(C, generator=g); lim[w] = float("-inf")
         parts.append((torch.randn(C, k, generator=g), torch.randint(-1, 2 ** 40, (C, k), generator=g),
-                      torch.randn(C, k, generator=g), torch.randint(0, k + 1, (C,), generator=g, dtype=torch.int32),
-                      torch.randint(0, 2, (C,), generator=g, dtype=torch.int32)))
+                      torch.randn(C, k, generator=g), torch.randint(0, k + 1, (C,), generator=g, dtype=torch.int32), lim))
     buf = torch.cat([pack(*p) for p in parts])
-    s, r, t, c, tr = unpack(buf, W, C, k, True)
+    s, r, t, c, lim = unpack(buf, W, C, k, True)
     for w in range(W):
         assert torch.equal(s[w], parts[w][0]) and torch.equal(r[w], parts[w][1]) and torch.equal(t[w], parts[w][2])
-        assert torch.equal(c[w], parts[w][3]) and torch.equal(tr[w], parts[w][4])
+        assert torch.equal(c[w], parts[w][3]) and torch.equal(lim[w], parts[w][4])
     buf = torch.cat([pack(p[0], p[1], None, p[3], p[4]) for p in parts])
-    s, r, t, c, tr = unpack(buf, W, C, k, False)
+    s, r, t, c, lim = unpack(buf, W, C, k, False)
     assert t is None and torch.equal(r[2], parts[2][1])
 
 
 def test_packed_layout_alignment():
     """int64 rows must stay 8-byte aligned in every rank's slice of the gathered buffer; views alias the buffer."""
-    from swat_b200.dist import PackedCandidates, packed_layout
-    for C, k, t in ((5, 7, True), (5, 7, False), (3, 1, False), (200, 1024, True), (1, 1, True)):
+    from swat_b200.dist import PackedResults, packed_layout
+    for C, k, t in ((5, 7, True), (5, 7, False), (3, 1, False), (200, 500, True), (1, 1, True)):
         lay = packed_layout(C, k, t)
         assert lay["len"] % 2 == 0 and lay["rows"] == 0 and lay["flags"] < lay["len"]
-        p = PackedCandidates(C, k, t, "cpu")
-        p.rows.fill_(2 ** 40 + 3); p.scores.fill_(1.5); p.counts.fill_(k); p.trunc.fill_(1); p.flags.fill_(3)
+        p = PackedResults(C, k, t, "cpu")
+        p.rows.fill_(2 ** 40 + 3); p.scores.fill_(1.5); p.counts.fill_(k); p.limit.fill_(float("-inf")); p.flags.fill_(3)
         if t:
             p.t2i.fill_(0.25)
-        q = PackedCandidates(C, k, t, "cpu", buf=p.buf.clone())
+        q = PackedResults(C, k, t, "cpu", buf=p.buf.clone())
         assert int(q.rows[C - 1, k - 1]) == 2 ** 40 + 3 and float(q.scores[0, 0]) == 1.5 and int(q.flags[0]) == 3
-        assert int(q.counts[C - 1]) == k and int(q.trunc[0]) == 1 and (not t or float(q.t2i[C - 1, 0]) == 0.25)
+        assert int(q.counts[C - 1]) == k and float(q.limit[0]) == float("-inf") and (not t or float(q.t2i[C - 1, 0]) == 0.25)
 
 
-def _oracle_merge(scores, rows, t2i, counts, trunc, k, thr):
-    """CPU stand-in for swat_merge_topk with the same contract (predicate walk + frontier check)."""
-    G, C, kf = scores.shape
+def test_default_k_fetch_mirrors_the_library():
+    from swat_b200.dist import default_k_fetch
+    assert default_k_fetch(500, False, 1e-4) == 576 and default_k_fetch(500, True, 1e-4) == 1024
+    assert default_k_fetch(500, False, 5e-3) == 1536 and default_k_fetch(500, True, 5e-3) == 2048
+    assert default_k_fetch(4096, False, 1e-4) == 4096 and default_k_fetch(1, False, 1e-4) == 96
+
+
+def _oracle_merge(scores, rows, t2i, counts, limit, k):
+    """CPU stand-in for swat_merge_topk with the same contract: k best of the union under (score desc, row asc);
+    incomplete when the result reaches down to some shard's limit."""
+    G, C, kin = scores.shape
     out_s = torch.zeros(C, k); out_r = torch.full((C, k), -1, dtype=torch.int64); out_t = torch.zeros(C, k)
     out_c = torch.zeros(C, dtype=torch.int32); inc = torch.zeros(C, dtype=torch.int32)
     for c in range(C):
-        ent, frontier = [], None
+        ent = []
         for g in range(G):
-            n = int(counts[g, c])
-            for j in range(n):
-                if t2i is None or float(t2i[g, c, j]) >= thr:
-                    ent.append((-float(scores[g, c, j]), int(rows[g, c, j]), float(t2i[g, c, j]) if t2i is not None else 0.0))
-            if int(trunc[g, c]) and n > 0:
-                f = (-float(scores[g, c, n - 1]), int(rows[g, c, n - 1]))
-                frontier = f if frontier is None or f < frontier else frontier
+            for j in range(int(counts[g, c])):
+                ent.append((-float(scores[g, c, j]), int(rows[g, c, j]), float(t2i[g, c, j]) if t2i is not None else 0.0))
         ent.sort()
         ent = ent[:k]
         for i, (ns, r, t) in enumerate(ent):
             out_s[c, i], out_r[c, i], out_t[c, i] = -ns, r, t
         out_c[c] = len(ent)
-        if frontier is not None and (len(ent) < k or (ent[-1][0], ent[-1][1]) > frontier):
+        lim = float(limit[:, c].max())
+        if lim > float("-inf") and (len(ent) < k or -ent[-1][0] <= lim):
             inc[c] = 1
     return out_s, out_r, out_t if t2i is not None else None, out_c, inc
+
+
+def _local_walk(S, I, a, k, kf, t2i_thr):
+    """Oracle stand-in for one rank's local stage: T2T top-kf candidates, accept walk, limit = score of the last
+    candidate when the list was truncated and fewer than k were accepted."""
+    C = S.shape[1]
+    from oracle import swat_oracle as so
+    rows = torch.full((C, k), -1, dtype=torch.int64); sc = torch.zeros(C, k); ti = torch.zeros(C, k)
+    cnt = torch.zeros(C, dtype=torch.int32); lim = torch.full((C,), float("-inf"))
+    for c in range(C):
+        sel = so.select_walk(S[:, c], kf, 0.0)
+        trunc = int((S[:, c] >= 0).sum()) > kf
+        acc = [r for r in sel.tolist() if I is None or I[r, c] >= t2i_thr]
+        if trunc and len(sel):          # rows at or below the frontier are not vouched for
+            acc = [r for r in acc if S[r, c] > S[sel[-1], c]]
+        acc = acc[:k]
+        n = len(acc)
+        rows[c, :n] = torch.tensor(acc, dtype=torch.int64) + a
+        sc[c, :n] = torch.from_numpy(S[acc, c]) if n else sc[c, :n]
+        if I is not None and n:
+            ti[c, :n] = torch.from_numpy(I[acc, c])
+        cnt[c] = n
+        if trunc and n < k:
+            lim[c] = float(S[sel[-1], c])
+    return sc, rows, (ti if I is not None else None), cnt, lim
 
 
 def _worker(rank, world, port, ret):
@@ -92,30 +121,30 @@ def _worker(rank, world, port, ret):
     cap, img, _ = synth.make_bank(N, qc, seed=2, dtype=torch.bfloat16, rho=0.4, tie_block=60, chunk=1 << 12)
     capf, imgf, qf = cap.float().numpy(), img.float().numpy(), queries.float().numpy()
     a, b = sdist.shard_range(N, rank, world)
-    # local stage computed by the oracle on this rank's rows: T2T top-kf candidates + their T2I
+    # local stage computed by the oracle on this rank's rows: walked T2T top-kf candidates + the shard's limit
     S = so.score_matrix(capf[a:b], qf); I = so.score_matrix(imgf[a:b], qf)
-    rows = torch.full((C, kf), -1, dtype=torch.int64); sc = torch.zeros(C, kf); ti = torch.zeros(C, kf)
-    cnt = torch.zeros(C, dtype=torch.int32); tr = torch.zeros(C, dtype=torch.int32)
-    for c in range(C):
-        sel = so.select_walk(S[:, c], kf, 0.0)
-        rows[c, :sel.size] = torch.from_numpy(sel + a); sc[c, :sel.size] = torch.from_numpy(S[sel, c]); ti[c, :sel.size] = torch.from_numpy(I[sel, c])
-        cnt[c] = sel.size; tr[c] = int((S[:, c] >= 0).sum() > kf)
-    res = sdist.gather_merge((sc, rows, ti, cnt, tr), k, 0.25, world, merge_fn=_oracle_merge)
+    local = _local_walk(S, I, a, k, kf, 0.25)
+    res = sdist.gather_merge(local, k, world, merge_fn=_oracle_merge)
     full = so.topk_walk(capf, qf, k, 0.0, t2i_bank=imgf, t2i_threshold=0.25)
     ok = all(res[1][c, :int(res[3][c])].tolist() == full[0][c, :full[3][c]].tolist() for c in range(C))
     ok = ok and res[3].tolist() == full[3].tolist() and int(res[4].sum()) == 0
     # T2T only path (no aux): top-k of the union
-    res2 = sdist.gather_merge((sc[:, :k].contiguous(), rows[:, :k].contiguous(), None, torch.minimum(cnt, torch.tensor(k, dtype=torch.int32)), tr),
-                              k, 0.25, world, merge_fn=_oracle_merge)
+    local2 = _local_walk(S, None, a, k, kf, 0.0)
+    res2 = sdist.gather_merge(local2, k, world, merge_fn=_oracle_merge)
     full2 = so.topk_walk(capf, qf, k, 0.0)
     ok = ok and all(res2[1][c, :int(res2[3][c])].tolist() == full2[0][c, :full2[3][c]].tolist() for c in range(C))
+    # a walk that is too shallow must be reported: 12 candidates per shard cannot yield 30 accepted rows
+    local3 = _local_walk(S, I, a, k, 12, 0.25)
+    res3 = sdist.gather_merge(local3, k, world, merge_fn=_oracle_merge)
+    ok = ok and int(res3[4].sum()) > 0
     # packed exchange buffer written in place (what the GPU path does): same result, and every rank sees every rank's flags
-    pk = sdist.PackedCandidates(C, kf, True, "cpu")
-    pk.scores.copy_(sc); pk.rows.copy_(rows); pk.t2i.copy_(ti); pk.counts.copy_(cnt); pk.trunc.copy_(tr); pk.flags.fill_(rank * 2)
+    pk = sdist.PackedResults(C, k, True, "cpu")
+    pk.scores.copy_(local[0]); pk.rows.copy_(local[1]); pk.t2i.copy_(local[2]); pk.counts.copy_(local[3]); pk.limit.copy_(local[4])
+    pk.flags.fill_(rank * 2)
     gathered = sdist.gather_packed(pk.buf, world)
-    res3 = sdist.merge_packed(gathered, pk.lay, world, k, 0.25, merge_fn=_oracle_merge)
-    ok = ok and torch.equal(res3[1], res[1]) and torch.equal(res3[3], res[3]) and torch.equal(res3[0], res[0])
-    ok = ok and sdist.unpack_flags(gathered, world, C, kf, True).tolist() == [2 * r for r in range(world)]
+    res4 = sdist.merge_packed(gathered, pk.lay, world, k, merge_fn=_oracle_merge)
+    ok = ok and torch.equal(res4[1], res[1]) and torch.equal(res4[3], res[3]) and torch.equal(res4[0], res[0])
+    ok = ok and sdist.unpack_flags(gathered, world, C, k, True).tolist() == [2 * r for r in range(world)]
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -270,6 +270,9 @@ def test_bank_swap_escalation(lib):
 
 
 def test_host_pipeline_equals_resident(lib, ctx2):
+    """Scores are canonical (one fixed-order fp32 dot per returned row), so the resident pipeline, the host pipeline
+    with pinned banks (candidates' rows read in place over PCIe) and the host pipeline with pageable banks (host-side
+    gather) agree bit for bit, whichever escalation path each of them took."""
     from swat_b200 import synth
     qc, queries, _ = synth.make_queries(40, 1, seed=31, dtype=torch.bfloat16)
     cap, img, labels = synth.make_bank(70_000, qc, seed=31, dtype=torch.bfloat16, rho=0.2, tie_block=200, chunk=1 << 16)
@@ -277,28 +280,26 @@ def test_host_pipeline_equals_resident(lib, ctx2):
     ctx2.set_option("host_chunk_rows", 8192)
     capf, imgf, qf = cap.float().numpy(), img.float().numpy(), queries.float().numpy()
     S = so.score_matrix(capf, qf)
-    for t2i_dev, t2i_host in ((None, None), (img.cuda(), img.pin_memory())):
+    for t2i_dev, t2i_pin, t2i_page in ((None, None, None), (img.cuda(), img.pin_memory(), img.clone())):
         r = lib.topk(ctx2, qs, cap.cuda(), 300, 0.0, t2i_bank=t2i_dev, row_offset=1000)
-        h = lib.topk_host(ctx2, qs, cap.pin_memory(), 300, 0.0, t2i_bank=t2i_host, row_offset=1000)
-        assert torch.equal(r[3].cpu(), h[3])
-        if t2i_dev is None:
-            assert torch.equal(r[1].cpu(), h[1]) and torch.equal(r[0].cpu(), h[0])
-        else:
-            # fewer than k rows pass T2I in every class here: the resident pipeline ends in the bank-swap pass (exact
-            # re-scores), the host pipeline in the in-pass predicate (fp32 FMA) -- same rows up to near-ties, scores to 1e-6
-            o = so.topk_walk(capf, qf, 300, 0.0, t2i_bank=imgf, t2i_threshold=0.25)
-            for g in (r, h):
-                rows = torch.where(g[1] >= 0, g[1] - 1000, g[1])
-                check_result(g[0], rows, g[3], o[0], o[1], o[3], S, TIE_TOL, what="host vs resident")
-            np.testing.assert_allclose(r[0].cpu().numpy(), h[0].numpy(), atol=2e-6)
-            np.testing.assert_allclose(r[2].cpu().numpy(), h[2].numpy(), atol=2e-6)
+        h = lib.topk_host(ctx2, qs, cap.pin_memory(), 300, 0.0, t2i_bank=t2i_pin, row_offset=1000)
+        ctx2.set_option("zero_copy", 0)
+        g = lib.topk_host(ctx2, qs, cap.clone(), 300, 0.0, t2i_bank=t2i_page, row_offset=1000)
+        ctx2.set_option("zero_copy", 1)
+        for x in (h, g):
+            assert torch.equal(r[3].cpu(), x[3]) and torch.equal(r[1].cpu(), x[1]) and torch.equal(r[0].cpu(), x[0])
+            if t2i_dev is not None:
+                assert torch.equal(r[2].cpu(), x[2])
+        o = so.topk_walk(capf, qf, 300, 0.0, t2i_bank=None if t2i_dev is None else imgf, t2i_threshold=0.25)
+        rows = torch.where(r[1] >= 0, r[1] - 1000, r[1])
+        check_result(r[0], rows, r[3], o[0], o[1], o[3], S, TIE_TOL, what="host vs resident")
     ctx2.set_option("host_chunk_rows", 1 << 18)
 
 
 def test_merge_and_shard_invariance(lib, ctx2):
     """Row-sharded scan + one gather + merge equals the single-shard result for any shard count
-    (SURVEY 8e), bit for bit.  T2T-only shards exchange their top-k; with the T2I walk they exchange
-    candidates and the accept walk runs in the merge (swat_b200/dist.py)."""
+    (SURVEY 8e), bit for bit: every shard walks its own candidates and ships at most k accepted rows per class
+    plus its limit (swat_b200/dist.py); the merge keeps the k best of the union."""
     from swat_b200 import dist, synth
     qc, queries, _ = synth.make_queries(30, 1, seed=41, dtype=torch.bfloat16)
     cap, img, _ = synth.make_bank(90_000, qc, seed=41, dtype=torch.bfloat16, rho=0.2, tie_block=500, chunk=1 << 16)
@@ -306,22 +307,21 @@ def test_merge_and_shard_invariance(lib, ctx2):
     d_cap, d_img = cap.cuda(), img.cuda()
     full_t2t = lib.topk(ctx2, qs, d_cap, 250, 0.0)
     full = lib.topk(ctx2, qs, d_cap, 250, 0.0, t2i_bank=d_img)
-    assert ctx2.last_timing()["escalations"] == 0
     for G in (1, 2, 3, 8):
         bounds = [dist.shard_range(90_000, r, G) for r in range(G)]
         assert bounds[0][0] == 0 and bounds[-1][1] == 90_000 and all(a[1] == b[0] for a, b in zip(bounds[:-1], bounds[1:]))
         # T2T only
-        parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 250, 0.0, None, row_offset=a) for a, b in bounds]
+        parts = [dist.local_walk(ctx2, qs, d_cap[a:b], 250, 1024, 0.0, None, row_offset=a) for a, b in bounds]     # deep enough to see past the block of 500 ties
         buf = torch.cat([dist.pack(*p) for p in parts])
-        s, r, t, c, tr = dist.unpack(buf, G, 30, 250, False)
-        ms, mr, mt, mc, inc = lib.merge_topk(ctx2, s, r, c, truncated=tr, k_out=250)
+        s, r, t, c, lim = dist.unpack(buf, G, 30, 250, False)
+        ms, mr, mt, mc, inc = lib.merge_topk(ctx2, s, r, c, limit=lim, k_out=250)
+        assert int(inc.sum()) == 0, f"T2T G={G}"
         assert torch.equal(mr, full_t2t[1]) and torch.equal(mc, full_t2t[3]) and torch.equal(ms, full_t2t[0]), f"T2T G={G}"
-        assert int(inc.sum()) == 0
-        # T2I walk over gathered candidates
-        parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 1024, 0.0, d_img[a:b], row_offset=a) for a, b in bounds]
+        # T2I walk per shard, merged
+        parts = [dist.local_walk(ctx2, qs, d_cap[a:b], 250, 1024, 0.0, d_img[a:b], 0.25, row_offset=a) for a, b in bounds]
         buf = torch.cat([dist.pack(*p) for p in parts])
-        s, r, t, c, tr = dist.unpack(buf, G, 30, 1024, True)
-        ms, mr, mt, mc, inc = lib.merge_topk(ctx2, s, r, c, aux=t, truncated=tr, k_out=250, aux_threshold=0.25)
+        s, r, t, c, lim = dist.unpack(buf, G, 30, 250, True)
+        ms, mr, mt, mc, inc = lib.merge_topk(ctx2, s, r, c, aux=t, limit=lim, k_out=250)
         assert int(inc.sum()) == 0, f"G={G}"
         assert torch.equal(mr, full[1]) and torch.equal(mc, full[3]), f"T2I G={G}"
         assert torch.equal(ms, full[0]) and torch.equal(mt, full[2])
@@ -329,21 +329,27 @@ def test_merge_and_shard_invariance(lib, ctx2):
         # merge reads the gathered buffer in place through the per-shard stride
         pks = []
         for a, b in bounds:
-            pk = dist.PackedCandidates(30, 1024, True, d_cap.device)
-            dist.local_candidates(ctx2, qs, d_cap[a:b], 1024, 0.0, d_img[a:b], row_offset=a, packed=pk, check=False)
+            pk = dist.PackedResults(30, 250, True, d_cap.device)
+            dist.local_walk(ctx2, qs, d_cap[a:b], 250, 1024, 0.0, d_img[a:b], 0.25, row_offset=a, packed=pk, check=False)
             pks.append(pk)
         gathered = torch.cat([pk.buf for pk in pks])
-        ps, pr, pt, pc, pinc = dist.merge_packed(gathered, pks[0].lay, G, 250, 0.25, ctx=ctx2)
+        ps, pr, pt, pc, pinc = dist.merge_packed(gathered, pks[0].lay, G, 250, ctx=ctx2)
         assert torch.equal(pr, full[1]) and torch.equal(pc, full[3]) and torch.equal(ps, full[0]) and torch.equal(pt, full[2])
-        assert int(pinc.sum()) == 0 and dist.unpack_flags(gathered, G, 30, 1024, True).tolist() == [0] * G
+        assert int(pinc.sum()) == 0 and dist.unpack_flags(gathered, G, 30, 250, True).tolist() == [0] * G
     # a frontier violation must be reported: k_fetch too small to find 250 passing rows
-    parts = [dist.local_candidates(ctx2, qs, d_cap[a:b], 64, 0.0, d_img[a:b], row_offset=a) for a, b in bounds]
-    s, r, t, c, tr = dist.unpack(torch.cat([dist.pack(*p) for p in parts]), 8, 30, 64, True)
-    inc = lib.merge_topk(ctx2, s, r, c, aux=t, truncated=tr, k_out=250, aux_threshold=0.25)[4]
+    parts = [dist.local_walk(ctx2, qs, d_cap[a:b], 250, 256, 0.0, d_img[a:b], 0.25, row_offset=a) for a, b in bounds[:2]]
+    s, r, t, c, lim = dist.unpack(torch.cat([dist.pack(*p) for p in parts]), 2, 30, 250, True)
+    assert bool((lim > float("-inf")).any())
+    inc = lib.merge_topk(ctx2, s, r, c, aux=t, limit=lim, k_out=250)[4]
     assert int(inc.sum()) > 0
-    # single-process world: the whole sharded pipeline
+    # single-process world: the whole sharded pipeline, including partitioned data with an exclusion bitmap
     res = dist.topk_sharded(ctx2, qs, d_cap, 250, 0.0, t2i_bank=d_img, world=1)
     assert torch.equal(res[1], full[1]) and torch.equal(res[0], full[0])
+    rc = torch.randint(0, 30, (90_000,), generator=torch.Generator().manual_seed(3), dtype=torch.int32).cuda()
+    ex = torch.randint(-2 ** 31, 2 ** 31 - 1, ((90_000 + 31) // 32,), generator=torch.Generator().manual_seed(4), dtype=torch.int64).to(torch.int32).cuda()
+    one = lib.topk(ctx2, qs, d_cap, 60, 0.0, t2i_bank=d_img, row_class=rc, exclude=ex)
+    res = dist.topk_sharded(ctx2, qs, d_cap, 60, 0.0, t2i_bank=d_img, world=1, row_class=rc, exclude=ex)
+    assert torch.equal(res[1], one[1]) and torch.equal(res[0], one[0]) and torch.equal(res[3], one[3])
 
 
 def test_streaming_job_matches_single_view(lib, ctx2):

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/swat_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.swat_version() == 100
+    assert lib.swat_version() == 200
     deps = os.popen(f"ldd {_lib.LIB_PATH}").read()
     assert "libcuda.so" not in deps          # driver entry points are resolved at run time
 

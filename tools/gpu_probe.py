@@ -40,12 +40,14 @@ for name, kw in (("t2t", {}), ("t2t+t2i", {"t2i_bank": img})):
         _lib.topk(ctx, qs, cap, 500, 0.0, **kw)
         dt = time.perf_counter() - t0
         print(name, f"wall {dt*1e3:.2f} ms", json.dumps(ctx.last_timing()))
-# which classes need escalation, and how many of the top-1024 T2T candidates pass T2I
+# tail breakdown: candidates -> exact re-score + walk
 from swat_b200 import dist as sdist
-sc, rows, t2i, counts, trunc = sdist.local_candidates(ctx, qs, cap, 1024, 0.0, img)
-passers = ((t2i >= 0.25) & (torch.arange(1024, device=dev)[None, :] < counts[:, None])).sum(1)
-print("passers among top-1024: min", int(passers.min()), "argmin", int(passers.argmin()), "median", int(passers.median()),
-      "classes below 500:", (passers < 500).nonzero().flatten().tolist())
+job = _lib.Job(ctx, qs, 1024, -1e-4)
+job.reset(); job.scan(cap)
+sc, rw, cn, tr = job.select()
+t = ev_time(lambda: _lib.rescore_walk(ctx, qs, cap, sc, rw, cn, tr, 500, 0.0, aux_bank=img))
+print("rescore+walk (1024 candidates x 200 classes, both banks):", t)
+job.close()
 for _ in range(3):
     t0 = time.perf_counter(); _lib.topk(ctx, qs, cap, 500, 0.0, t2i_bank=img); dt = time.perf_counter() - t0
     print("t2t+t2i", f"wall {dt*1e3:.2f} ms", json.dumps(ctx.last_timing()))
