@@ -17,6 +17,11 @@ One step = one pass of the whole pipeline (scan + select + T2I walk [+ gather + 
            results are all-gathered and merged, all inside the timed region.
 `roofline`: scan kernel, HBM bound for Q <= 209: 1 KB/row over the measured copy
            bandwidth in MEASURED_PEAKS.json.
+`configs` : the other BASELINE.json configs, driver-timed in the same run (each entry: CUDA-event ms per whole step,
+           scan-kernel ms, rows/s and both roofline fractions): at every N the config-4 shape (imagenet C = Q = 1000,
+           T2T top-500, 50 M rows per GPU, NCCL merge), the strong-scaling point of config 5 (100 M rows split over
+           the N GPUs, Q = 200) and `cold_call_ms` (first call on a fresh context, allocation and escalation included);
+           at N = 1 also the query-count sweep Q in {64, 200, 400, 1000} over 50 M rows and config 1 (fp32 banks).
 """
 import argparse
 import json
@@ -47,7 +52,16 @@ def parse():
     ap.add_argument("--t2t-only", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--overfetch", type=int, default=0, help="first k_fetch of the T2I walk (0 = library default)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `configs` object (other BASELINE configs, cold call)")
+    ap.add_argument("--extra-rows", type=int, default=50_000_000, help="rows per GPU of the config-4 / Q-sweep bank")
+    ap.add_argument("--strong-rows", type=int, default=100_000_000, help="total rows of the strong-scaling point")
     return ap.parse_args()
+
+
+def config_dict(a, world):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": workload_name(a, world), "rows_per_gpu": a.rows, "classes": a.classes, "k": a.k,
+            "l2": f"inputs ({a.rows * 1024 / 1e9:.1f} GB per bank per GPU) far larger than the 126 MB L2; no flush needed"}
 
 
 def workload_name(a, world):
@@ -165,33 +179,36 @@ def cpu_verbatim(a, n_rows, n_cls=None):
     return dt * (a.classes / C), dt
 
 
+REF_SAMPLE_ROWS = 50_000      # fixed: every run of the reference arm scores the same 50 000-row sample of the workload
+
+
 def run_reference(a, rank, world):
     """--impl reference: the reference's own CPU path for this workload, timed on the host cores.
     /root/reference is Python + needs open_clip stubs and does not exist on the GPU box, so the arm
-    runs the oracle's verbatim port (kind = "port")."""
+    runs the oracle's verbatim port (kind = "port") of sample_retrieval.py:774-825: per class a GEMV over the whole
+    sample, Python sorted on the zipped tuples, the accept walk.  One step = one pass over a FIXED 50 000-row sample
+    of the workload's bank (same generator, same 200 classes, unpartitioned like the GPU arm); the per-row rate does
+    not depend on the sample size beyond the O(log n) of the sort."""
     if rank != 0:
         return
     import torch
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    total_steps = a.steps + a.warmup
-    budget = float(os.environ.get("SWAT_BENCH_REF_BUDGET_S", 150.0)) / max(total_steps, 1)     # seconds per step
-    n_rows = 2048
-    est, _ = cpu_verbatim(a, n_rows, n_cls=8)                   # calibrate on 8 classes
-    n_rows = int(max(1024, min(200_000, n_rows * budget / max(est, 1e-6))))
+    n_rows = int(os.environ.get("SWAT_BENCH_REF_ROWS", REF_SAMPLE_ROWS))
     for _ in range(a.warmup):
         cpu_verbatim(a, n_rows)
-    t0 = time.perf_counter()
+    dt = 0.0
     for _ in range(a.steps):
-        cpu_verbatim(a, n_rows)
-    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+        dt += cpu_verbatim(a, n_rows)[1]            # the sampler call only, not the generation of the sample
+    dt /= max(a.steps, 1)
     value = n_rows / dt
     vec, vec_sample = (None, None) if a.no_cpu else cpu_vectorised(a)
-    sample = f"{n_rows} rows x {a.classes} classes per step, unpartitioned, verbatim port of sample_retrieval.py:774-825"
+    sample = (f"{n_rows} rows x {a.classes} classes per step (fixed sample of the {a.rows}-row bank), unpartitioned, verbatim port of "
+              f"sample_retrieval.py:774-825")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a, a.gpus), "sample_rows": n_rows},
+        "dtype": "f32", "data": "synthetic", "config": config_dict(a, a.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "vectorised_value": vec, "vectorised_sample": vec_sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,6 +216,138 @@ def run_reference(a, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------
+def roof_rows_per_s(q_cols, bytes_per_row, hbm, tf):
+    """the slower of bytes_per_row at HBM bandwidth and 2*512*Q flop/row at dense bf16."""
+    h, t = hbm * 1e9 / bytes_per_row, tf * 1e12 / (1024.0 * q_cols)
+    return (h, "hbm") if h <= t else (t, "tensor")
+
+
+def run_extras(a, rank, world, dev, main):
+    """The `configs` object: the other BASELINE.json configs and the cold call, timed like the main workload
+    (warm-up, barrier + synchronize on both sides, CUDA events, max over ranks).  `main` = (cap, img, queries) of the
+    main workload, still resident; they are released here."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    from swat_b200 import _lib, synth
+    from swat_b200 import dist as sdist
+    hbm, tf, src = peaks()
+    out = {"peaks": f"{src}: hbm {hbm} GB/s, bf16 sustained {tf} TFLOP/s"}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(ctx, step, n_local, q_cols, bytes_per_row, warm=2, reps=3):
+        for _ in range(warm):
+            step()
+        scans = ctx.__dict__["_time_scans"] = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kern = []
+        e0.record()
+        for _ in range(reps):
+            step()
+            if world == 1:
+                tm = ctx.last_timing()
+                kern.append(tm["scan_ms"] / max(tm["scan_launches"], 1.0))      # one pass over the bank (all of its launches)
+        e1.record()
+        barrier()
+        ctx.__dict__["_time_scans"] = None
+        ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        if world > 1:
+            kern = [x.elapsed_time(y) for x, y in scans]
+        kern.sort()
+        kms = max_over_ranks(kern[len(kern) // 2]) if kern else None
+        roof, bound = roof_rows_per_s(q_cols, bytes_per_row, hbm, tf)
+        return {"rows_per_gpu": n_local, "Q": q_cols, "ms_per_step": ms, "scan_kernel_ms": kms,
+                "rows_per_s": n_local * world / (ms * 1e-3),
+                "roofline": {"bound": bound, "roof_rows_per_s_per_gpu": roof, "step_frac": n_local / (ms * 1e-3) / roof,
+                             "kernel_frac": None if not kms else n_local / (kms * 1e-3) / roof}}
+
+    def t2t_step(ctx, qs, cap, row_offset):
+        if world == 1:
+            return lambda: _lib.topk(ctx, qs, cap, a.k, 0.0, row_offset=row_offset)
+        return lambda: sdist.topk_sharded(ctx, qs, cap, a.k, 0.0, row_offset=row_offset, world=world)
+
+    # ---- cold call: fresh context + query set, first call of the main workload (allocation, threshold bootstrap and
+    # any over-fetch escalation included; the banks are resident)
+    cap, img, queries = main
+    main.clear()
+    barrier()
+    t0 = time.perf_counter()
+    ctx_c = _lib.Context(dev.index)
+    qs_c = _lib.Queries(ctx_c, queries.float())
+    if world == 1:
+        _lib.topk(ctx_c, qs_c, cap, a.k, 0.0, t2i_bank=img, t2i_threshold=0.25)
+    else:
+        sdist.topk_sharded(ctx_c, qs_c, cap, a.k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=rank * a.rows, world=world)
+    torch.cuda.synchronize(dev)
+    out["cold_call_ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    out["cold_call_note"] = "wall clock: swat_ctx_create + swat_queries_create + first whole-pipeline call on the main workload"
+    qs_c.close(); ctx_c.close()
+    del cap, img
+    gc.collect(); torch.cuda.empty_cache()
+
+    ctx = _lib.Context(dev.index)
+    # ---- config 4 shape: imagenet C = Q = 1000, T2T top-500, `extra_rows` rows per GPU (+ NCCL merge for N > 1);
+    # at N = 1 the same bank serves the query-count sweep (config 5 on one GPU)
+    n_x = a.extra_rows
+    qc, q1000, _ = synth.make_queries(1000, 1, seed=a.seed + 1, dtype=torch.bfloat16)
+    capx, _, _ = synth.make_bank(n_x, qc, seed=a.seed + 1, device=dev, dtype=torch.bfloat16, chunk=1 << 20, with_images=False,
+                                 row_offset=rank * n_x)
+    sweep = (64, 200, 400, 1000) if world == 1 else (1000,)
+    out["cfg5_qsweep"] = []
+    for Q in sweep:
+        qs = _lib.Queries(ctx, q1000[:Q].float())
+        e = timed(ctx, t2t_step(ctx, qs, capx, rank * n_x), n_x, Q, 1024.0)
+        e["workload"] = f"C = Q = {Q}, T2T top-{a.k}, {n_x} x 512 bf16 rows per GPU, {world} GPU(s)"
+        if Q == 1000:
+            e["workload"] = f"imagenet-shaped (BASELINE config 4): " + e["workload"]
+            out["cfg4_imagenet"] = e
+        out["cfg5_qsweep"].append(e)
+        qs.close()
+    del capx
+    gc.collect(); torch.cuda.empty_cache()
+    # ---- strong scaling (config 5): a fixed 100 M-row bank split over the N GPUs, Q = 200
+    n_s = a.strong_rows // world
+    qc2, q200, _ = synth.make_queries(200, 1, seed=a.seed + 2, dtype=torch.bfloat16)
+    caps, _, _ = synth.make_bank(n_s, qc2, seed=a.seed + 2, device=dev, dtype=torch.bfloat16, chunk=1 << 20, with_images=False,
+                                 row_offset=rank * n_s)
+    qs = _lib.Queries(ctx, q200.float())
+    e = timed(ctx, t2t_step(ctx, qs, caps, rank * n_s), n_s, 200, 1024.0)
+    e["workload"] = f"strong scaling: {a.strong_rows} rows in total over {world} GPU(s), C = Q = 200, T2T top-{a.k}"
+    e["total_rows"] = n_s * world
+    out["cfg5_strong_scaling"] = e
+    qs.close()
+    del caps
+    gc.collect(); torch.cuda.empty_cache()
+    # ---- config 1 (N = 1): fp32 banks, the reference's dtype, 2 KB/row
+    if world == 1:
+        out["cfg1_fp32"] = []
+        qc3, q3, _ = synth.make_queries(200, 1, seed=a.seed + 3, dtype=torch.float32)
+        for n1 in (1_000_000, 10_000_000):
+            c32, i32, _ = synth.make_bank(n1, qc3, seed=a.seed + 3, device=dev, dtype=torch.float32, chunk=1 << 18)
+            qs = _lib.Queries(ctx, q3)
+            for name, kw in (("T2T", {}), ("T2T+T2I0.25", {"t2i_bank": i32})):
+                e = timed(ctx, lambda: _lib.topk(ctx, qs, c32, a.k, 0.0, **kw), n1, 200, 2048.0)
+                e["workload"] = f"semi-aves C = Q = 200 {name} top-{a.k}, {n1} x 512 fp32 rows (BASELINE config 1 dtype), 1 GPU"
+                e["escalations_per_step"] = ctx.last_timing()["escalations"]
+                out["cfg1_fp32"].append(e)
+            qs.close()
+            del c32, i32
+            gc.collect(); torch.cuda.empty_cache()
+    ctx.close()
+    return out
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -345,16 +494,23 @@ def run_ours(a, rank, world, local_rank):
                "verbatim_value": 50_000 / est,
                "verbatim_sample": f"50000 rows x 8 of {a.classes} classes scaled x{a.classes / 8:.0f}, verbatim port of "
                                   f"sample_retrieval.py:774-825 ({dt8:.1f} s)"}
+    counts = res[3]
+    accepted = int(counts.sum().item())
+    extras = None
+    if not a.no_extras:
+        main = [cap, img, queries]
+        del cap, img, res, counts
+        qs.close()
+        extras = run_extras(a, rank, world, dev, main)
     if rank == 0:
-        counts = res[3]
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload_name(a, world), "rows_per_gpu": n_local, "classes": a.classes, "k": k,
-                       "l2": f"inputs ({n_local * 1024 / 1e9:.1f} GB per bank per GPU) far larger than the 126 MB L2; no flush needed",
-                       "accepted_rows": int(counts.sum().item()), "t2i_escalations_per_step": escalations},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
+            "config": config_dict(a, world),
+            "stats": {"accepted_rows": accepted, "t2i_escalations_per_step": escalations,
+                      "step_frac_of_roofline": (n_local / (ms / a.steps * 1e-3)) / roof_rows_per_s(q_cols, bytes_per_row, hbm, tf)[0]},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "configs": extras}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -74,7 +74,10 @@ def run_samplers(sr, raw, prompt_tensors, k, tmp, dataset, unpartitioned=False):
             fl_name, sl_name = f"{tmp}/T2T_filtered_list.txt", f"{tmp}/T2T_sampled_list.txt"   # :763,768
         else:
             fl_name, sl_name = f"{tmp}/filtered_list.txt", f"{tmp}/sampled_list.txt"           # :817,822
-        out[name] = dict(rows=rows, labels=labels, counts=nd, featsum=featsum,
+        # rows of the reference's filtered_list (the rejected rows its walk met, in walk order): "..., <path>, <caption>"
+        fl_text = open(fl_name).read()
+        filtered_rows = np.asarray([path_to_row[l.split(", ")[-2]] for l in fl_text.split("\n")] if fl_text else [], dtype=np.int64)
+        out[name] = dict(rows=rows, labels=labels, counts=nd, featsum=featsum, filtered_rows=filtered_rows,
                          filtered_sha=hashlib.sha256(open(fl_name, "rb").read()).hexdigest(),
                          sampled_sha=hashlib.sha256(open(sl_name, "rb").read()).hexdigest(),
                          sampled_head=open(sl_name).read().split("\n")[:3],
@@ -146,6 +149,8 @@ def case_bank(sr, name, n_rows, C, k, seed, dtype, partitioned, rho, tie_block):
             arrays[f"{tag}_{m}_rows"] = res[m]["rows"]
             arrays[f"{tag}_{m}_labels"] = res[m]["labels"]
             arrays[f"{tag}_{m}_featsum"] = res[m]["featsum"]
+            if tag == "part":
+                arrays[f"{tag}_{m}_filtered_rows"] = res[m]["filtered_rows"]
     for i, kk in enumerate(regroup_keys):
         arrays[f"regroup_rows_{i}"] = regroup_rows[i]
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)

@@ -225,7 +225,8 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
   if (dtype != SWAT_BF16 && dtype != SWAT_F32) return fail(SWAT_ERR_INVALID, "dtype must be SWAT_BF16 or SWAT_F32");
   if ((reinterpret_cast<uintptr_t>(d_bank) & 15) != 0) return fail(SWAT_ERR_INVALID, "bank pointer must be 16-byte aligned");
   const bool f32 = dtype == SWAT_F32;
-  if (engine == SWAT_ENGINE_AUTO) engine = resolve_engine(q, dtype, d_t2i_bank != nullptr);
+  // dense scores are the S1 primitives (t2t_similarity :397-416) and the zero-shot logits: exact fp32 arithmetic for fp32 banks
+  if (engine == SWAT_ENGINE_AUTO) engine = (dense_out != nullptr && f32) ? SWAT_ENGINE_SIMT : resolve_engine(q, dtype, d_t2i_bank != nullptr);
   if (engine == SWAT_ENGINE_TC && d_t2i_bank != nullptr)
     return fail(SWAT_ERR_UNSUPPORTED, "the tcgen05 engine does not evaluate the in-pass T2I predicate");
   ScanArgs a;

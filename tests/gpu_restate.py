@@ -112,37 +112,51 @@ def restate_topk_walk(t2t_bank: torch.Tensor, queries: torch.Tensor, k: int, thr
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def compare_walks(got, ref, tie_tol: float, boundary_tol: float = 1e-3, what: str = ""):
+def compare_walks(got, ref, tie_tol: float, boundary_tol: float = 1e-3, what: str = "", aux_thr: Optional[float] = None,
+                  flip_tol: float = 2e-6):
     """``got`` = (scores, rows, t2i | None, counts) from the product (device or host tensors), ``ref`` = (rows, scores,
-    t2i | None, counts) from an oracle (numpy).  The north star's parity rule per class (same counts; rows equal up to
-    swaps among scores within ``tie_tol``; rows present on one side only sit within ``boundary_tol`` of the k-th score);
-    scores within 1e-3.  Returns (interior swaps, boundary differences, positions compared)."""
+    t2i | None, counts) from an oracle (numpy).  The north star's parity rule per class:
+
+    * same counts, scores within 1e-3, each side descending;
+    * rows on one side only are either at the k-th boundary (score within ``boundary_tol`` of the last accepted score)
+      or *predicate flips*: their T2I score sits within ``flip_tol`` of the threshold, so two fp32 summation orders
+      legitimately disagree on ``t2i >= 0.25`` (each flip also moves one row across the k-th boundary);
+    * the rows both sides accepted appear in the same order up to swaps among scores that agree to ``tie_tol``.
+
+    Returns (interior swaps, boundary differences, predicate flips, positions compared)."""
     g_s, g_r, g_t, g_c = [None if x is None else (x.cpu().numpy() if torch.is_tensor(x) else np.asarray(x)) for x in got]
     r_r, r_s, r_t, r_c = ref
-    assert g_c.tolist() == np.asarray(r_c).tolist(), f"{what}: counts differ in classes {np.nonzero(g_c != r_c)[0][:10].tolist()}"
-    swaps = boundary = total = 0
+    r_c = np.asarray(r_c)
+    swaps = boundary = flips = total = 0
     for c in range(g_r.shape[0]):
-        n = int(g_c[c])
+        n, m = int(g_c[c]), int(r_c[c])
         total += n
         assert np.all(g_r[c, n:] == -1), f"{what} class {c}: padding"
-        if n == 0:
-            continue
-        np.testing.assert_allclose(g_s[c, :n], r_s[c, :n], atol=1e-3, err_msg=f"{what} class {c} scores")
-        if g_t is not None and r_t is not None:
-            pass
+        a, b = g_r[c, :n], r_r[c, :m]
         assert np.all(np.diff(g_s[c, :n]) <= 0), f"{what} class {c}: scores not descending"
-        a, b = g_r[c, :n], r_r[c, :n]
-        if np.array_equal(a, b):
+        if n == m and np.array_equal(a, b):
+            np.testing.assert_allclose(g_s[c, :n], r_s[c, :m], atol=1e-3, err_msg=f"{what} class {c} scores")
             continue
-        d = np.abs(g_s[c, :n].astype(np.float64) - r_s[c, :n].astype(np.float64))
-        assert d.max() <= tie_tol, f"{what} class {c}: position-wise score gap {d.max()} > {tie_tol}"
-        only = set(a.tolist()) ^ set(b.tolist())
-        if only:
-            last = min(float(g_s[c, n - 1]), float(r_s[c, n - 1]))
-            sa = dict(zip(a.tolist(), g_s[c, :n].tolist())); sb = dict(zip(b.tolist(), r_s[c, :n].tolist()))
-            for r in only:
-                s = sa.get(r, sb.get(r))
-                assert abs(s - last) <= boundary_tol, f"{what} class {c}: row {r} differs away from the k-th boundary"
-            boundary += len(only) // 2
-        swaps += int((a != b).sum())
-    return swaps, boundary, total
+        sa = dict(zip(a.tolist(), g_s[c, :n].tolist())); sb = dict(zip(b.tolist(), r_s[c, :m].tolist()))
+        only_a, only_b = set(sa) - set(sb), set(sb) - set(sa)
+        flipped = set()
+        if aux_thr is not None and g_t is not None and r_t is not None:
+            ta = dict(zip(a.tolist(), g_t[c, :n].tolist())); tb = dict(zip(b.tolist(), r_t[c, :m].tolist()))
+            flipped = {r for r in only_a if abs(ta[r] - aux_thr) <= flip_tol} | {r for r in only_b if abs(tb[r] - aux_thr) <= flip_tol}
+        assert abs(n - m) <= len(flipped), f"{what} class {c}: count {n} != {m}"
+        last = min(float(g_s[c, n - 1]) if n else 1.0, float(r_s[c, m - 1]) if m else 1.0)
+        for r in (only_a | only_b) - flipped:
+            s_ = sa.get(r, sb.get(r))
+            assert abs(s_ - last) <= boundary_tol, f"{what} class {c}: row {r} (score {s_}) differs away from the k-th boundary ({last})"
+        boundary += (len((only_a | only_b) - flipped) + 1) // 2
+        flips += len(flipped)
+        common = set(sa) & set(sb)
+        a2 = [r for r in a.tolist() if r in common]; b2 = [r for r in b.tolist() if r in common]
+        for x, y in zip(a2, b2):
+            if x != y:
+                swaps += 1
+                assert abs(sa[x] - sb[y]) <= tie_tol and abs(sa[x] - sa[y]) <= tie_tol, \
+                    f"{what} class {c}: rows {x} / {y} out of order beyond a near-tie ({sa[x]} vs {sb[y]})"
+        for r in common:
+            assert abs(sa[r] - sb[r]) <= 1e-3, f"{what} class {c}: score of row {r}"
+    return swaps, boundary, flips, total

@@ -28,10 +28,13 @@ TIE_TOL = 2e-6          # canonical fp32 scores vs the oracle's fp32 GEMM: summa
 K = 500
 
 
-def _report(tag, swaps, boundary, total):
-    print(f"[parity] {tag}: {total} rows compared, {swaps} positions swapped between near-ties (<= {TIE_TOL}), {boundary} boundary rows differ")
+def _report(tag, res):
+    swaps, boundary, flips, total = res
+    print(f"[parity] {tag}: {total} rows compared, {swaps} positions swapped between near-ties (<= {TIE_TOL}), "
+          f"{boundary} boundary rows differ, {flips} predicate flips (|T2I - 0.25| <= 2e-6)")
     assert swaps <= max(8, total // 500), f"{tag}: {swaps} near-tie swaps in {total} rows"
     assert boundary <= max(4, total // 5000), f"{tag}: {boundary} boundary differences"
+    assert flips <= 3, f"{tag}: {flips} predicate flips"
 
 
 # ----------------------------------------------------------------------------------------------- config 1
@@ -70,11 +73,10 @@ def test_config1_fp32_1M_vs_cpu_oracle(cfg1, qcfg, part):
         g = lib.topk(ctx, qs, cap, K, 0.0, t2i_bank=img if with_t2i else None, t2i_threshold=0.25, row_class=rc)
         o = so.topk_walk(capf, qf, K, 0.0, t2i_bank=imgf if with_t2i else None, t2i_threshold=0.25, class_of_query=coq_np,
                          n_classes=200, reduce=red, row_labels=lab_np)
-        swaps, boundary, total = compare_walks(g, o, TIE_TOL, what=f"cfg1 {qcfg} part={part} t2i={with_t2i}")
-        _report(f"cfg1 {qcfg} part={part} t2i={with_t2i} launches={ctx.launch_count - l0} esc={ctx.last_timing()['escalations']}",
-                swaps, boundary, total)
+        res = compare_walks(g, o, TIE_TOL, what=f"cfg1 {qcfg} part={part} t2i={with_t2i}", aux_thr=0.25 if with_t2i else None)
+        _report(f"cfg1 {qcfg} part={part} t2i={with_t2i} launches={ctx.launch_count - l0} esc={ctx.last_timing()['escalations']}", res)
         if with_t2i:
-            np.testing.assert_allclose(g[2].cpu().numpy()[g[1].cpu().numpy() >= 0], o[2][o[0] >= 0], atol=1e-3)
+            assert np.all(g[2].cpu().numpy()[g[1].cpu().numpy() >= 0] >= 0.25)
     qs.close()
 
 
@@ -97,19 +99,23 @@ def test_config1_verbatim_port(cfg1):
     for with_t2i, fn in ((False, so.verbatim_t2t_ranked_sampler), (True, so.verbatim_t2t_ranked_t2i_tshd_sampler)):
         ms, nd = fn(prompts, K, 0.0, feats)[:2]
         g = lib.topk(ctx, qs, cap, K, 0.0, t2i_bank=img if with_t2i else None, row_class=labels)
-        rows, counts = g[1].cpu().numpy(), g[3].cpu().numpy()
-        got_files = {c: [f"/s/{c}/{r}.jpg" for r in rows[c, :counts[c]].tolist()] for c in range(200)}
+        # the port's per-class lists (indices into the class's regrouped rows) -> [C,K] arrays of global rows
+        r_rows = np.full((200, K), -1, dtype=np.int64); r_s = np.zeros((200, K), np.float32); r_t = np.zeros((200, K), np.float32)
+        r_c = np.zeros(200, np.int32)
         i = 0
-        diff = 0
         for c in range(200):
-            assert int(nd[str(c)]) == int(counts[c]), f"class {c}"
-            if counts[c] == 0:
+            n = int(nd[str(c)])
+            r_c[c] = n
+            if n == 0:
                 continue
-            ref_files = ms["file_list"][i]; i += 1
-            diff += sum(a != b for a, b in zip(got_files[c], ref_files))
-            assert set(got_files[c]) == set(ref_files) or diff < 50
-        print(f"[parity] cfg1 verbatim partitioned t2i={with_t2i}: {int(counts.sum())} rows, {diff} positions differ (near-ties)")
-        assert diff <= max(8, int(counts.sum()) // 500)
+            cls_rows = order[starts[c]:starts[c + 1]]
+            r_rows[c, :n] = cls_rows[ms["row_list"][i]]; r_s[c, :n] = ms["score_list"][i]
+            if with_t2i:
+                r_t[c, :n] = ms["t2i_list"][i]
+            i += 1
+        res = compare_walks(g, (r_rows, r_s, r_t if with_t2i else None, r_c), TIE_TOL, what=f"cfg1 verbatim part t2i={with_t2i}",
+                            aux_thr=0.25 if with_t2i else None)
+        _report(f"cfg1 verbatim port, Zipf-partitioned, t2i={with_t2i}", res)
     # unpartitioned: classes 5 and 117
     cap, img, _ = w["banks"][False]
     capf, imgf = cap.cpu().numpy(), img.cpu().numpy()
@@ -153,16 +159,16 @@ def test_restatement_equals_cpu_oracle_at_1M(cfg2):
     for t2i in (False, True):
         o = so.topk_walk(capf, qf, K, 0.0, t2i_bank=imgf if t2i else None, t2i_threshold=0.25)
         r = restate_topk_walk(cap, q.cuda(), K, 0.0, t2i_bank=img if t2i else None, t2i_threshold=0.25)
-        swaps, boundary, total = compare_walks((r[1], r[0], r[2], r[3]), o, TIE_TOL, what=f"restatement t2i={t2i}")
-        _report(f"restatement vs CPU oracle t2i={t2i}", swaps, boundary, total)
+        res = compare_walks((r[1], r[0], r[2], r[3]), o, TIE_TOL, what=f"restatement t2i={t2i}", aux_thr=0.25 if t2i else None)
+        _report(f"restatement vs CPU oracle t2i={t2i}", res)
     # synonym groups with MAX and MEAN on a 200 k prefix
     from swat_b200 import synth
     _, q400, coq = synth.make_queries(C2, 2, seed=0, dtype=torch.bfloat16)
     for red in ("max", "mean"):
         o = so.topk_walk(capf[:200_000], q400.float().numpy(), 100, 0.0, class_of_query=coq.numpy(), n_classes=C2, reduce=red)
         r = restate_topk_walk(cap[:200_000], q400.float().cuda(), 100, 0.0, class_of_query=coq, n_classes=C2, reduce=red)
-        swaps, boundary, total = compare_walks((r[1], r[0], r[2], r[3]), o, TIE_TOL, what=f"restatement {red}")
-        _report(f"restatement vs CPU oracle {red}", swaps, boundary, total)
+        res = compare_walks((r[1], r[0], r[2], r[3]), o, TIE_TOL, what=f"restatement {red}")
+        _report(f"restatement vs CPU oracle {red}", res)
 
 
 def _invariants(scores, rows, counts, k, n_rows, n_cls):
@@ -200,10 +206,9 @@ def test_config2_10M_bf16_vs_restatement(cfg2):
         _invariants(g[0], g[1], g[3], K, N2, C2)
         _check_needles(w, g[1], g[0])
         r = restate_topk_walk(cap, q, K, 0.0, t2i_bank=img if t2i else None, t2i_threshold=0.25)
-        swaps, boundary, total = compare_walks(g, r, TIE_TOL, what=f"cfg2 t2i={t2i}")
-        _report(f"cfg2 10M bf16 t2i={t2i} esc={ctx.last_timing()['escalations']}", swaps, boundary, total)
+        res = compare_walks(g, r, TIE_TOL, what=f"cfg2 t2i={t2i}", aux_thr=0.25 if t2i else None)
+        _report(f"cfg2 10M bf16 t2i={t2i} esc={ctx.last_timing()['escalations']}", res)
         if t2i:
-            np.testing.assert_allclose(g[2].cpu().numpy()[g[1].cpu().numpy() >= 0], r[2][r[0] >= 0], atol=1e-3)
             assert np.all(g[2].cpu().numpy()[g[1].cpu().numpy() >= 0] >= 0.25)
         again = lib.topk(ctx, qs, cap, K, 0.0, t2i_bank=img if t2i else None, t2i_threshold=0.25)       # idempotence (steady state)
         assert torch.equal(again[1], g[1]) and torch.equal(again[0], g[0]) and torch.equal(again[3], g[3])
@@ -282,7 +287,7 @@ def test_config3_50M_lines_vs_restatement(cfg3, line):
     qs = lib.Queries(ctx, q, coq, C, red)
     g = lib.topk(ctx, qs, cap, K, 0.0)
     r = restate_topk_walk(cap, q.cuda(), K, 0.0, class_of_query=coq, n_classes=C, reduce=red)
-    swaps, boundary, total = compare_walks(g, r, TIE_TOL, what=f"cfg3 {line}")
-    _report(f"cfg3 50M {line} esc={ctx.last_timing()['escalations']}", swaps, boundary, total)
+    res = compare_walks(g, r, TIE_TOL, what=f"cfg3 {line}")
+    _report(f"cfg3 50M {line} esc={ctx.last_timing()['escalations']}", res)
     _invariants(g[0], g[1], g[3], K, 50_000_000, C)
     qs.close()

@@ -126,10 +126,16 @@ def test_bench_reference_arm_line_shape():
     import subprocess, sys
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                           "--classes", "8", "--k", "20", "--no-cpu"], capture_output=True, text=True, timeout=600,
-                         env={**os.environ, "SWAT_BENCH_REF_BUDGET_S": "3"})
+                         env={**os.environ, "SWAT_BENCH_REF_ROWS": "3000"})
     line = json.loads(out.stdout.strip().split("\n")[-1])
     assert line["impl"] == "reference" and line["unit"] == "rows/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # both arms must describe the same workload: the driver compares the `config` objects
+    import argparse, importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    ours = bench.config_dict(argparse.Namespace(rows=10_000_000, classes=8, k=20, t2t_only=False), 1)
+    assert line["config"] == ours
 
 
 def test_random_sampler_threshold0_is_host_only(tmp_path):
