@@ -132,6 +132,7 @@ struct swat_queries {
   std::vector<float> h_q;             // host copy (sub-query sets for targeted escalation)
   mutable std::vector<int32_t> kclass_hint;   // per class: deepest over-fetch its T2I walk has needed so far (0 = default)
   mutable int32_t last_k_fetch = 0;   // over-fetch at which the last pipeline run completed
+  mutable bool all_few_hint = false;  // every class had too few T2I passers for a T2T-ordered walk: start with the bank-swap pass
   int ctas = 2, n_qb = 1, n_blk = 16, n_cols = 16, n_stages = 0;
   int n_fstages = 0, n_opstages_f32 = 0;   // fp32 banks on the tcgen05 engine: staged fp32 boxes / bf16 operand stages
   // |score of bf16-rounded row and bf16-rounded queries - fp32 score| <= eps_conv for every L2-normalised row (see swat_queries_create)
@@ -573,6 +574,7 @@ int32_t walk_candidates(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, 
     w.bank_rows = b.n_rows;
     w.bank_row_base = row_offset;
     w.gather_index = nullptr;
+    w.lazy_t2t = (b.host && use_aux) ? 1 : 0;
     if (b.host) ctx->timing[5] += static_cast<double>(n_slots) * kDim * elem_size(b.dtype) * (use_aux ? 2 : 1);   // upper bound: every slot filled
   } else {
     // pageable host banks: gather the candidates' rows on the host, ship the compact blocks
@@ -799,16 +801,31 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
   const bool want_t2i = b.t2i != nullptr;
   if (depth == 0) for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
   const bool can_swap = want_t2i && ctx->swap_pass && !b.host;
-  if (k_fetch_init == kSwapPass && can_swap) {
-    // escalation beyond the widest over-fetch: enumerate the T2I passers from the image bank (one tensor-core pass);
-    // classes with too many of them for that fall through to the in-pass predicate
+  const bool hinted_swap = k_fetch_init == 0 && depth == 0 && q->all_few_hint && ctx->overfetch == 0;
+  if ((k_fetch_init == kSwapPass || hinted_swap) && can_swap) {
+    // escalation beyond the widest over-fetch (or a query set whose classes all had too few T2I passers last time):
+    // enumerate the T2I passers from the image bank (one tensor-core pass); classes with too many of them for that fall
+    // through to the in-pass predicate
+    cudaEvent_t ev_b = ctx->ev[6];
+    if (depth == 0) CU_OK(cudaEventRecord(ev_b, stream));
     std::vector<int> unresolved;
     SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, nullptr, &unresolved));
-    if (!unresolved.empty())
-      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
-                             d_out_counts, stream, depth));
-    q->last_k_fetch = kMaxKFetch;
-    return SWAT_OK;
+    if (hinted_swap && !unresolved.empty()) {
+      q->all_few_hint = false;          // a different bank: plenty of passers here, run the T2T-ordered walk after all
+    } else {
+      if (!unresolved.empty())
+        SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
+                               d_out_counts, stream, depth));
+      q->last_k_fetch = kMaxKFetch;
+      if (depth == 0) {
+        CU_OK(cudaEventRecord(ctx->ev[7], stream));
+        CU_OK(cudaStreamSynchronize(stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_b, ctx->ev[7]);
+        ctx->timing[3] = ms;
+      }
+      return SWAT_OK;
+    }
   }
   bool dual = want_t2i && k_fetch_init > kMaxKFetch;          // in-pass predicate (fp32-FMA kernel, both banks per row)
   float eps = scan_eps(q, b.dtype, resolve_engine(q, b.dtype, dual));
@@ -923,57 +940,65 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
       continue;
     }
-    if (static_cast<int>(bad.size()) < C) {
-      int32_t from = k_fetch;                           // the escalated classes were walked to this depth
-      if (!k_class.empty()) { from = kMaxKFetch; for (int c : bad) from = std::min<int32_t>(from, static_cast<int32_t>(k_class[c])); }
-      if (from >= kMaxKFetch && !want_t2i)
-        return fail(SWAT_ERR_INCOMPLETE, "%d classes not provably exact at the widest over-fetch (%d candidates; more than that many "
-                                         "rows tie with the k-th score?)", (int)bad.size(), kMaxKFetch);
-      const int32_t nxt = (from < kMaxKFetch) ? std::min(kMaxKFetch, from * 2) : (can_swap ? kSwapPass : kForceDual);
-      // A class that accepted p of the d candidates walked so far needs about d*k/p of them.  Where that is beyond the
-      // widest over-fetch the ladder would only waste passes: those classes go straight to the bank-swap pass.
-      std::vector<int> deeper, few;
-      const int32_t* accepted = ctx->h_status + 1 + C;           // copied out before any nested call reuses the buffer
-      for (int c : bad) {
-        const int64_t d = k_class.empty() ? k_fetch : static_cast<int64_t>(k_class[c]);
-        const int64_t p = accepted[c];
-        const bool hopeless = want_t2i && (p <= 0 || d * k / p > 2 * kMaxKFetch);   // factor 2: borderline classes still try the ladder
-        (hopeless && nxt <= kMaxKFetch && can_swap ? few : deeper).push_back(c);
-      }
-      if (!deeper.empty()) {
-        SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, deeper, nxt, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
-                               stream, depth));
-        if (depth == 0 && ctx->overfetch == 0 && q->last_k_fetch > 0) {      // remember the depth that worked, per class
-          if (static_cast<int>(q->kclass_hint.size()) != C) q->kclass_hint.assign(C, 0);
-          for (int c : deeper) q->kclass_hint[c] = std::max(q->kclass_hint[c], q->last_k_fetch);
-        }
-      }
-      if (!few.empty())      // no depth hint for these: walking them deeper in the main pass would not help
+    int32_t from = k_fetch;                           // the escalated classes were walked to this depth
+    if (!k_class.empty()) { from = kMaxKFetch; for (int c : bad) from = std::min<int32_t>(from, static_cast<int32_t>(k_class[c])); }
+    const bool ladder_left = from < kMaxKFetch;
+    // A class that accepted p of the d candidates walked so far needs about d*k/p of them.  Where that is beyond the
+    // widest over-fetch the ladder would only waste passes: those classes go straight to the bank-swap pass.
+    std::vector<int> deeper, few;
+    const int32_t* accepted = ctx->h_status + 1 + C;           // copied out before any nested call reuses the buffer
+    for (int c : bad) {
+      const int64_t d = k_class.empty() ? k_fetch : static_cast<int64_t>(k_class[c]);
+      const int64_t p = accepted[c];
+      const bool hopeless = p <= 0 || d * k / p > 2 * kMaxKFetch;   // factor 2: borderline classes still try the ladder
+      ((hopeless || !ladder_left) && can_swap ? few : deeper).push_back(c);
+    }
+    if (!few.empty()) {
+      if (static_cast<int>(few.size()) == C) {
+        std::vector<int> unresolved;
+        SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, nullptr, &unresolved));
+        if (!unresolved.empty())
+          SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
+                                 d_out_counts, stream, depth));
+        if (depth == 0 && unresolved.empty()) q->all_few_hint = true;     // next call on this query set starts here
+      } else {
         SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, few, kSwapPass, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
                                stream, depth));
+      }
+    }
+    if (deeper.empty()) break;
+    if (!ladder_left) {
+      // widest over-fetch and no bank-swap pass to fall back on
+      if (!want_t2i)
+        return fail(SWAT_ERR_INCOMPLETE, "%d classes not provably exact at the widest over-fetch (%d candidates; more than that many "
+                                         "rows tie with the k-th score?)", (int)deeper.size(), kMaxKFetch);
+      if (static_cast<int>(deeper.size()) == C) {
+        dual = true;
+        eps = scan_eps(q, b.dtype, SWAT_ENGINE_SIMT);
+        k_fetch = default_k_fetch(ctx, k, false, b.host, eps);
+        k_class.clear();
+        continue;
+      }
+      SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, deeper, kForceDual, d_out_scores, d_out_rows, d_out_t2i, d_out_counts,
+                             stream, depth));
       break;
     }
-    // every class is short: escalate the whole set, x4 per round
-    k_class.clear();
-    if (k_fetch < kMaxKFetch) {
+    if (static_cast<int>(deeper.size()) == C) {
+      // every class is short: escalate the whole set, x4 per round
+      k_class.clear();
       k_fetch = std::min(kMaxKFetch, k_fetch * 4);
       cap = std::max(cap, auto_cap(ctx, k_fetch));
       list_entries = std::max(list_entries, auto_list_entries(ctx, C, k_fetch));
       continue;
     }
-    if (!want_t2i)
-      return fail(SWAT_ERR_INCOMPLETE, "%d classes not provably exact at the widest over-fetch (%d candidates)", (int)bad.size(), kMaxKFetch);
-    if (can_swap && depth < 3) {
-      std::vector<int> unresolved;
-      SW_OK(swap_pass(ctx, q, b, row_offset, k, thr, t2i_thr, d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream, &bad, &unresolved));
-      if (!unresolved.empty())
-        SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, unresolved, kForceDual, d_out_scores, d_out_rows, d_out_t2i,
-                               d_out_counts, stream, depth));
-      break;
+    // targeted: a sub-query set of just those classes, twice as deep
+    SW_OK(escalate_classes(ctx, q, b, row_offset, k, thr, t2i_thr, deeper, std::min(kMaxKFetch, from * 2), d_out_scores, d_out_rows,
+                           d_out_t2i, d_out_counts, stream, depth));
+    if (depth == 0 && ctx->overfetch == 0 && q->last_k_fetch > 0) {      // remember the depth that worked, per class
+      if (static_cast<int>(q->kclass_hint.size()) != C) q->kclass_hint.assign(C, 0);
+      for (int c : deeper) q->kclass_hint[c] = std::max(q->kclass_hint[c], q->last_k_fetch);
     }
-    dual = true;
-    eps = scan_eps(q, b.dtype, SWAT_ENGINE_SIMT);
-    k_fetch = default_k_fetch(ctx, k, false, b.host, eps);
+    break;
   }
   q->last_k_fetch = dual ? 0 : k_fetch;
   if (depth == 0) {

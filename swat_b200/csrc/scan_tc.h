@@ -62,6 +62,7 @@ struct WalkArgs {
   const float* cand_scores; const int64_t* cand_rows; const int32_t* cand_counts; const int32_t* truncated;   // [C,stride] / [C]
   int stride; int k; int n_classes;
   float thr, aux_thr, eps;
+  int lazy_t2t;                 // 1: fetch a candidate's ranking row only if its predicate row passes (rows over PCIe)
   int all_or_nothing;           // 1: a truncated list vouches for nothing (lists ranked on another metric: bank-swap pass)
   float* exact_scratch; float* aux_scratch;      // [C,stride] each
   float* out_scores; int64_t* out_rows; float* out_aux; int32_t* out_counts;   // [C,k] / [C]

@@ -275,29 +275,120 @@ __device__ __forceinline__ float canonical_score(const float (&x)[16], const T* 
   return red;
 }
 
-// one warp per candidate: exact T2T score from the ranking bank and, with a predicate bank, the exact aux (T2I) score.
-// Both rows are requested before either is consumed.
-template <typename T>
-__global__ void __launch_bounds__(256) rescore_kernel(const WalkArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t g = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (g >= static_cast<int64_t>(a.n_classes) * a.stride) return;
-  const int c = static_cast<int>(g / a.stride), j = static_cast<int>(g % a.stride);
-  if (j >= a.cand_counts[c]) return;
-  const int64_t r = a.gather_index ? a.gather_index[g] : a.cand_rows[g] - a.bank_row_base;
-  float t2t = -INFINITY, aux = -INFINITY;
-  if (r >= 0 && r < a.bank_rows) {
-    float x[16], y[16];
-    load16<T>(static_cast<const T*>(a.t2t_bank) + r * kDim + lane * 16, x);
-    if (a.aux_bank) load16<T>(static_cast<const T*>(a.aux_bank) + r * kDim + lane * 16, y);
-    const int q0 = a.class_begin[c], q1 = a.class_begin[c + 1];
-    t2t = canonical_score<T>(x, static_cast<const T*>(a.queries), q0, q1, a.reduce, lane);
-    if (a.aux_bank)
-      aux = canonical_score<T>(y, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
+// 16 consecutive elements of a row as loaded (packed): unpacked to fp32 only when consumed, so that several rows can
+// be in flight per lane without running out of registers
+template <typename T> struct Raw16;
+template <> struct Raw16<float> {
+  float4 v[4];
+  __device__ __forceinline__ void load(const float* p) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = reinterpret_cast<const float4*>(p)[i];
   }
-  if (lane == 0) {
-    a.exact_scratch[g] = t2t;
-    if (a.aux_bank) a.aux_scratch[g] = aux;
+  __device__ __forceinline__ void unpack(float (&x)[16]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[4 * i] = v[i].x; x[4 * i + 1] = v[i].y; x[4 * i + 2] = v[i].z; x[4 * i + 3] = v[i].w; }
+  }
+};
+template <> struct Raw16<__nv_bfloat16> {
+  uint4 v[2];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    v[0] = reinterpret_cast<const uint4*>(p)[0];
+    v[1] = reinterpret_cast<const uint4*>(p)[1];
+  }
+  __device__ __forceinline__ void unpack(float (&x)[16]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+        x[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+    }
+  }
+};
+
+// Exact scores of the candidates: one warp per NC consecutive candidates of a class.  All of their rows (ranking bank
+// and, with a predicate bank, the aux rows) are requested before any is consumed -- the kernel is bound by the latency
+// of those scattered 1-2 KB reads, not by bandwidth.
+template <typename T, int NC>
+__global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int groups = (a.stride + NC - 1) / NC;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (w >= static_cast<int64_t>(a.n_classes) * groups) return;
+  const int c = static_cast<int>(w / groups), j0 = static_cast<int>(w % groups) * NC;
+  const int n = min(a.cand_counts[c], a.stride);
+  if (j0 >= n) return;
+  const size_t base = static_cast<size_t>(c) * a.stride;
+  int64_t r[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    r[i] = -1;
+    if (j0 + i < n) r[i] = a.gather_index ? a.gather_index[base + j0 + i] : a.cand_rows[base + j0 + i] - a.bank_row_base;
+    if (r[i] >= a.bank_rows) r[i] = -1;
+  }
+  Raw16<T> x[NC], y[NC];
+  const int q0 = a.class_begin[c], q1 = a.class_begin[c + 1];
+  float aux[NC];
+  if (a.lazy_t2t && a.aux_bank) {
+    // rows are expensive to fetch (pinned host memory over PCIe): predicate rows first, ranking rows only for the
+    // candidates that pass it -- the others can never be accepted and need no exact score
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (r[i] >= 0) y[i].load(static_cast<const T*>(a.aux_bank) + r[i] * kDim + lane * 16);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      aux[i] = -INFINITY;
+      if (r[i] >= 0) {
+        float f[16];
+        y[i].unpack(f);
+        aux[i] = canonical_score<T>(f, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (r[i] >= 0 && aux[i] >= a.aux_thr) x[i].load(static_cast<const T*>(a.t2t_bank) + r[i] * kDim + lane * 16);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      if (j0 + i >= n) break;                    // warp-uniform
+      float t2t = -INFINITY;
+      if (r[i] >= 0 && aux[i] >= a.aux_thr) {
+        float f[16];
+        x[i].unpack(f);
+        t2t = canonical_score<T>(f, static_cast<const T*>(a.queries), q0, q1, a.reduce, lane);
+      }
+      if (lane == 0) {
+        a.exact_scratch[base + j0 + i] = t2t;
+        a.aux_scratch[base + j0 + i] = aux[i];
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    if (r[i] >= 0) {
+      x[i].load(static_cast<const T*>(a.t2t_bank) + r[i] * kDim + lane * 16);
+      if (a.aux_bank) y[i].load(static_cast<const T*>(a.aux_bank) + r[i] * kDim + lane * 16);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    if (j0 + i >= n) break;                      // warp-uniform
+    float t2t = -INFINITY, ax = -INFINITY;
+    if (r[i] >= 0) {
+      float f[16];
+      x[i].unpack(f);
+      t2t = canonical_score<T>(f, static_cast<const T*>(a.queries), q0, q1, a.reduce, lane);
+      if (a.aux_bank) {
+        y[i].unpack(f);
+        ax = canonical_score<T>(f, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
+      }
+    }
+    if (lane == 0) {
+      a.exact_scratch[base + j0 + i] = t2t;
+      if (a.aux_bank) a.aux_scratch[base + j0 + i] = ax;
+    }
   }
 }
 
@@ -604,11 +695,13 @@ cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t str
 }
 
 cudaError_t launch_rescore_walk(const WalkArgs& a, cudaStream_t stream) {
-  const int64_t n = static_cast<int64_t>(a.n_classes) * a.stride;
+  constexpr int kBf16Cands = 4, kF32Cands = 2;          // candidates per warp
+  const int per = a.dtype == 0 ? kBf16Cands : kF32Cands;
+  const int64_t n = static_cast<int64_t>(a.n_classes) * ((a.stride + per - 1) / per);
   if (n <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((n + 7) / 8);
-  if (a.dtype == 0) rescore_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
-  else rescore_kernel<float><<<grid, 256, 0, stream>>>(a);
+  if (a.dtype == 0) rescore_kernel<__nv_bfloat16, kBf16Cands><<<grid, 256, 0, stream>>>(a);
+  else rescore_kernel<float, kF32Cands><<<grid, 256, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   walk_kernel<<<a.n_classes, kSelThreads, 0, stream>>>(a);

