@@ -481,11 +481,15 @@ def run_ours(a, rank, world, local_rank):
             r, h2d, d2h = e2e_step()
         barrier()
         dt = time.perf_counter() - t0
+        e2e_tm = ctx.last_timing()
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_rows * steps_e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "steps": steps_e,
+               "d2h_bytes_per_step": int(d2h) * world, "steps": steps_e, "ms_per_step": dt / steps_e * 1e3,
+               "last_step_device_ms": {"caption_stream_and_scan": e2e_tm["scan_ms"], "select": e2e_tm["select_ms"],
+                                       "rescore_and_walk": e2e_tm["t2i_ms"], "total": e2e_tm["total_ms"],
+                                       "escalations": e2e_tm["escalations"]},
                "api": "swat_topk_host (C-ABI, pinned host banks)" if world == 1 else
                       "swat_topk_host per rank on its pinned host shard + one NCCL all-gather + swat_merge_topk"}
         del h_cap, h_img

@@ -99,6 +99,9 @@ struct swat_ctx {
   DevBuf w_scores, w_rows, w_counts, w_trunc, w_exact, w_aux, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
   DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
   DevBuf w_swap[10];                // bank-swap escalation pass: two re-score stages
+  int lock_window = 0;              // several Q blocks: pairs sharing a tile range stay within this many tiles of each other (0 = off)
+  DevBuf w_progress;
+  int f32_op_stages = 3;            // fp32 banks: bf16 operand stages (the rest of the shared memory stages fp32 boxes); before swat_queries_create
   bool zero_copy = true;            // host pipeline: read candidates' rows from pinned host banks in place
   bool swap_pass = true;            // classes with fewer than k rows passing T2I: enumerate the passers from the image bank
   cudaStream_t copy_stream = nullptr, work_stream = nullptr;
@@ -314,7 +317,14 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
       }
     }
     if (p.n_ranges == 0 && q->n_qb > pairs) launches = (q->n_qb + pairs - 1) / pairs;   // legacy plan: `pairs` Q blocks per launch
+    const bool lockstep = ctx->lock_window > 0 && q->n_qb > 1 && dense_out == nullptr;
+    if (lockstep) {
+      SW_OK(ctx->w_progress.ensure(static_cast<size_t>(launches) * pairs * 4));
+      CU_OK(cudaMemsetAsync(ctx->w_progress.p, 0, static_cast<size_t>(launches) * pairs * 4, stream));
+      p.lock_window = ctx->lock_window;
+    }
     for (int i = 0; i < launches; ++i) {
+      p.progress = lockstep ? ctx->w_progress.as<uint32_t>() + static_cast<size_t>(i) * pairs : nullptr;
       if (p.n_ranges > 0) {
         p.unit_base = i * pairs;
       } else {
@@ -1065,7 +1075,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_exact, &ctx->w_aux, &ctx->w_incomplete, &ctx->w_keys,
                     &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
-                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot,
+                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot, &ctx->w_progress,
                     &ctx->w_swap[0], &ctx->w_swap[1], &ctx->w_swap[2], &ctx->w_swap[3], &ctx->w_swap[4], &ctx->w_swap[5], &ctx->w_swap[6],
                     &ctx->w_swap[7], &ctx->w_swap[8], &ctx->w_swap[9]};
   for (DevBuf* b : bufs) b->release();
@@ -1095,6 +1105,8 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   else if (n == "unit_plan") ctx->unit_plan = value != 0;
   else if (n == "swap_pass") ctx->swap_pass = value != 0;
   else if (n == "zero_copy") ctx->zero_copy = value != 0;
+  else if (n == "f32_op_stages") { if (value < 2 || value > 4) return fail(SWAT_ERR_INVALID, "f32_op_stages must be 2..4"); ctx->f32_op_stages = static_cast<int>(value); }
+  else if (n == "lock_window") ctx->lock_window = static_cast<int>(std::max<int64_t>(0, value));
   else if (n == "bootstrap_rows") ctx->bootstrap_rows = std::max<int64_t>(0, value);
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
   return SWAT_OK;
@@ -1163,7 +1175,7 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   for (int b = 0; b < q->n_qb; ++b) split[b] = std::min(split[b], q->n_blk);
   q->n_cols = q->n_qb * q->n_blk;
   q->n_stages = tc_pick_stages(q->n_blk, q->ctas, ctx->smem_optin);
-  q->n_fstages = tc_pick_fstages(q->n_blk, q->ctas, ctx->smem_optin, &q->n_opstages_f32);
+  q->n_fstages = tc_pick_fstages(q->n_blk, q->ctas, ctx->smem_optin, &q->n_opstages_f32, ctx->f32_op_stages);
   {
     // fp32 banks are scanned as bf16-rounded rows against bf16-rounded queries.  With x~ = bf16(x) (round to nearest
     // even: |x~_i - x_i| <= 2^-8 |x_i|, 8 significant bits) and q~ = bf16(q):

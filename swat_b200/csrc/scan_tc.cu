@@ -66,6 +66,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     qb_rank = (unit - first_u) / p.n_qb;
   }
 
+  // Pairs that walk the same tiles (one per Q block of a tile range) keep in step so that a tile is read from HBM once
+  // and served to the others from L2: launch-local ids [grp_first, grp_first + grp_size) share this pair's tiles.
+  int grp_first = pair_id, grp_size = 1;
+  if (p.progress != nullptr) {
+    if (p.n_ranges > 0) {
+      const int lo = max(pair_in_qb * p.n_qb, p.unit_base), hi = min((pair_in_qb + 1) * p.n_qb, p.unit_base + n_pairs);
+      grp_first = lo - p.unit_base; grp_size = hi - lo;
+    } else {
+      grp_first = pair_in_qb * p.qb_count; grp_size = min(p.qb_count, n_pairs - grp_first);
+    }
+  }
+
   uint8_t* sB = smem;
   uint8_t* sA = smem + p.smem_b_bytes;                        // operand ring (bf16, what the MMAs read)
   uint8_t* sF = sA + p.n_stages * kStageBytes;                // F32: ring of staged fp32 boxes
@@ -134,12 +146,27 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
                              0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
       }
+      // lockstep: before requesting tile `it`, wait (bounded) until every pair of the group has requested tile it - window
+      const bool lockstep = p.progress != nullptr && grp_size > 1 && rank == 0;
+      auto keep_in_step = [&](uint32_t it) {
+        if (!lockstep) return;
+        if (lane == 0) st_relaxed_gpu_u32(p.progress + pair_id, it);
+        if (it < static_cast<uint32_t>(p.lock_window) || (it & 1u)) return;
+        const uint32_t need = it - static_cast<uint32_t>(p.lock_window);
+        for (int spin = 0; spin < 256; ++spin) {
+          const uint32_t mine = lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu;
+          if (__reduce_min_sync(0xffffffffu, mine) >= need) break;
+          __nanosleep(100);
+        }
+      };
+      uint32_t tile_it = 0;
       if (F32) {
         // fp32 boxes of 128 rows x 32 k (16 KB) into this CTA's own ring; the converter warps free a stage as soon as
         // its contents sit in their registers
         const uint32_t sF_a = smem_u32(sF), ffull_a = smem_u32(ffull_bar), fempty_a = smem_u32(fempty_bar);
         uint32_t stage = 0, phase = 0;
-        for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
+        for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++tile_it) {
+          keep_in_step(tile_it);
           const int row0 = static_cast<int>(t * kTileRows + rank * 128);
 #pragma unroll 1
           for (int kc = 0; kc < 16; ++kc) {
@@ -155,7 +182,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         const uint32_t sA_a = smem_u32(sA), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
         const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
         uint32_t stage = 0, phase = 0;
-        for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
+        for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++tile_it) {
+          keep_in_step(tile_it);
           const int row0 = static_cast<int>(t * kTileRows + rank * 128);
 #pragma unroll 1
           for (int kc = 0; kc < 8; ++kc) {
@@ -168,6 +196,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           }
         }
       }
+      if (lockstep && lane == 0) st_relaxed_gpu_u32(p.progress + pair_id, 0xffffffffu);   // done: nobody waits for this pair any more
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (leader CTA)
@@ -190,8 +219,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         const uint32_t d_tmem = tmem_base + buf * 256u;
 #pragma unroll 1
         for (int kc = 0; kc < 8; ++kc) {
-          if (F32) mbar_wait_acquire_cluster(full_a + stage * 8u, phase);   // filled by converter warps of both CTAs
-          else mbar_wait(full_a + stage * 8u, phase);
+          mbar_wait(full_a + stage * 8u, phase);      // TMA transaction (bf16) / converter warps of both CTAs (F32)
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a0 = a_base + stage * a_step;
@@ -256,7 +284,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           sts_u32x4(dst_row + stage * kStageBytes + (((half * 4u + ch) ^ sw) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) mbar_arrive_release_cluster(full_lead + stage * 8u);
+        // Plain arrive on the leader's barrier (release at CTA scope): the tile lives in THIS CTA's shared memory and is
+        // read by this SM's half of the tensor-core pair, so CTA-scope visibility plus the proxy fence is what the MMA
+        // needs.  (A .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL per stage: ncu showed the
+        // converter warps spending most of their time in those, 2.2 TB/s instead of the HBM rate.)
+        if (lane == 0) mbar_arrive_cluster(full_lead + stage * 8u);
         if (half == 1 && ++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
       }
     }
@@ -418,9 +450,9 @@ int tc_pick_stages(int n_blk, int ctas, size_t smem_limit) {
 }
 
 // fp32 banks: `op` operand stages (64 k of bf16 each) + the returned number of staged fp32 boxes (32 k each)
-int tc_pick_fstages(int n_blk, int ctas, size_t smem_limit, int* op_stages) {
-  for (int op = 3; op >= 2; --op)
-    for (int f = 8; f >= (op == 3 ? 4 : 2); --f)
+int tc_pick_fstages(int n_blk, int ctas, size_t smem_limit, int* op_stages, int prefer_op) {
+  for (int op = prefer_op; op >= 2; --op)
+    for (int f = 8; f >= (op >= 3 ? 4 : 2); --f)
       if (tc_smem_bytes(n_blk, ctas, op, f) <= smem_limit) { *op_stages = op; return f; }
   *op_stages = 0;
   return 0;

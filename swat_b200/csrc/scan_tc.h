@@ -18,13 +18,15 @@ struct TcArgs {
   int32_t n_ranges;       // unit plan: tile ranges R (0 = legacy launch)
   int32_t qb_base;        // legacy launch: covers the Q blocks [qb_base, qb_base + qb_count), block = qb_base + pair % qb_count
   int32_t qb_count;
+  uint32_t* progress;     // nullable [pairs of this launch]: tiles each pair has requested so far (lockstep of the pairs sharing a tile range)
+  int32_t lock_window;    // a pair requests tile i only when every pair of its range has requested tile i - lock_window
   const int32_t* blk_class;  // [n_qb+1] first class of each Q block
   const int32_t* blk_split;  // [n_qb] grouped reduces: column (multiple of 32) where the second epilogue warp set starts
 };
 
 size_t tc_smem_bytes(int n_blk, int ctas, int n_stages, int n_fstages);
 int tc_pick_stages(int n_blk, int ctas, size_t smem_limit);
-int tc_pick_fstages(int n_blk, int ctas, size_t smem_limit, int* op_stages);
+int tc_pick_fstages(int n_blk, int ctas, size_t smem_limit, int* op_stages, int prefer_op);
 // tm_bank / tm_q: CUtensorMap*; f32: tm_bank describes an fp32 bank (boxes of 128 rows x 32 k)
 cudaError_t launch_scan_tc(const void* tm_bank, const void* tm_q, const TcArgs& p, int ctas, int reduce,
                            bool partitioned, bool dense, bool f32, int grid, cudaStream_t stream);

@@ -142,16 +142,28 @@ __global__ void __launch_bounds__(256) final_tau_kernel(const JobState st, int n
 // survivor lists -> per-class candidate arrays, keeping only entries at or above the final class
 // threshold (about k_fetch plus one histogram bin per class)
 __global__ void __launch_bounds__(256) partition_kernel(const JobState st) {
+  // one CTA per (list, quarter); four entries per thread and round, all loaded before any is tested: the kernel is a
+  // chain of dependent global accesses (count -> entry -> threshold -> slot), so independent entries hide each other
   const uint32_t l = blockIdx.x;
   const uint32_t n = min(st.list_count[l], st.list_cap);
   const uint4* src = st.list + static_cast<size_t>(l) * st.list_cap;
-  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
-    const uint4 e = src[i];
-    const uint32_t cls = e.z;
-    if (e.y >= st.tau_enc[cls]) {
-      const uint32_t slot = atomicAdd(&st.count[cls], 1u);
-      if (slot < st.cap) st.cand[static_cast<size_t>(cls) * st.cap + slot] = (static_cast<uint64_t>(e.y) << 32) | e.x;
-      else atomicOr(st.flags, 1u);
+  constexpr uint32_t kUnroll = 4;
+  const uint32_t step = gridDim.y * blockDim.x * kUnroll;
+  for (uint32_t i0 = (blockIdx.y * blockDim.x + threadIdx.x) * kUnroll; i0 < n; i0 += step) {
+    uint4 e[kUnroll];
+    uint32_t tau[kUnroll];
+#pragma unroll
+    for (uint32_t j = 0; j < kUnroll; ++j) e[j] = (i0 + j < n) ? src[i0 + j] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (uint32_t j = 0; j < kUnroll; ++j) tau[j] = (i0 + j < n) ? st.tau_enc[e[j].z] : 0xffffffffu;
+#pragma unroll
+    for (uint32_t j = 0; j < kUnroll; ++j) {
+      if (i0 + j < n && e[j].y >= tau[j]) {
+        const uint32_t cls = e[j].z;
+        const uint32_t slot = atomicAdd(&st.count[cls], 1u);
+        if (slot < st.cap) st.cand[static_cast<size_t>(cls) * st.cap + slot] = (static_cast<uint64_t>(e[j].y) << 32) | e[j].x;
+        else atomicOr(st.flags, 1u);
+      }
     }
   }
 }
@@ -675,7 +687,7 @@ cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset,
   final_tau_kernel<<<(n_classes + 7) / 8, 256, 0, stream>>>(st, n_classes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  partition_kernel<<<dim3(st.n_lists, 4), 256, 0, stream>>>(st);
+  partition_kernel<<<dim3(st.n_lists, 2), 256, 0, stream>>>(st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated);

@@ -50,11 +50,6 @@ static __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// release at cluster scope: data this thread wrote (and fenced into the async proxy) is visible to whoever acquires
-// the barrier from another CTA of the pair
-static __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
-}
 static __device__ __forceinline__ uint64_t globaltimer_ns() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
@@ -72,22 +67,13 @@ static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) 
     }
   } while (!done);
 }
-// same, acquiring at cluster scope (the barrier is signalled by threads of both CTAs of a pair)
-static __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done, spins = 0;
-  uint64_t t0 = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && (++spins & 0xfffu) == 0u) {
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
-  } while (!done);
+static __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+static __device__ __forceinline__ void st_relaxed_gpu_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 static __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(tm)) : "memory");

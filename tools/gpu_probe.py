@@ -59,3 +59,15 @@ for zc in (1, 0, 1, 0):
     ctx.set_option("zero_copy", zc)
     t0 = time.perf_counter(); _lib.topk_host(ctx, qs, h_cap, 500, 0.0, t2i_bank=h_img); dt = time.perf_counter() - t0
     print(f"topk_host zero_copy={zc}: wall {dt*1e3:.1f} ms  {N/dt/1e6:.1f} M rows/s", json.dumps(ctx.last_timing()))
+# several Q blocks: pairs sharing a tile range with / without the lockstep window
+del h_cap, h_img
+for Q in (400, 1000):
+    qcq, qq, _ = synth.make_queries(Q, 1, seed=5, dtype=torch.bfloat16)
+    qsq = _lib.Queries(ctx, qq.float())
+    jq = _lib.Job(ctx, qsq, 576, -1e-4)
+    for lw in (0, 4, 0, 4, 2, 8):
+        ctx.set_option("lock_window", lw)
+        t = ev_time(lambda: (jq.reset(), jq.scan(cap)), reps=4)
+        print(f"Q={Q} lock_window={lw}: scan {t[len(t)//2]:.3f} ms  ({[round(x,3) for x in t]})", flush=True)
+    jq.close(); qsq.close()
+ctx.set_option("lock_window", 4)
