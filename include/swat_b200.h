@@ -84,6 +84,16 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
                             swat_queries** out);
 int32_t swat_queries_destroy(swat_queries* q);
 
+/* ---- feature-shard loader (torch.load(...) + .cuda(), sample_retrieval.py:1473-1476, :337, :399) -------------- */
+/* Rows [row_begin, row_end) of a flat shard file (raw row-major [n_rows,512] bf16 | f32: caption.bin / image.bin of
+ * swat_b200/shards.py, converted once from the reference's *_mined.pth) -> d_dst, caller-allocated
+ * [row_end-row_begin, 512] device memory: a rank of a sharded run loads its own row range.  Banks are plain device
+ * pointers in this ABI, so there is no separate "bank from device" call.  GPUDirect Storage (cuFileRead straight into
+ * d_dst) when libcufile loads and accepts the file, *used_gds = 1; otherwise pread() into two pinned staging buffers of
+ * chunk_rows rows (0 = 65536), the read of chunk i+1 overlapping the H2D copy of chunk i on `stream`.  Synchronises. */
+int32_t swat_bank_load(swat_ctx* ctx, const char* path, int32_t dtype, int64_t row_begin, int64_t row_end, void* d_dst,
+                       int64_t chunk_rows, int32_t* used_gds, void* stream);
+
 /* ---- streaming job: running per-class top-k_fetch over any number of bank views ------------- */
 /* Replaces, for all classes at once, the per-class  t2t_similarity -> sorted() -> walk  of
  * t2t_ranked_sampler (:752-758): state = per-class threshold, histogram and candidate buffer. */

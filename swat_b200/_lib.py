@@ -22,7 +22,7 @@ DIM = 512
 
 EXPORTS = [
     "swat_version", "swat_last_error", "swat_ctx_create", "swat_ctx_destroy", "swat_ctx_set_option",
-    "swat_ctx_launch_count", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
+    "swat_ctx_launch_count", "swat_bank_load", "swat_queries_create", "swat_queries_destroy", "swat_job_create", "swat_job_reset",
     "swat_job_set_class_depth", "swat_job_scan", "swat_job_select", "swat_job_export_flags", "swat_job_status", "swat_job_destroy", "swat_scan_eps", "swat_rescore_walk", "swat_merge_topk",
     "swat_scores_dense", "swat_score_rows", "swat_zeroshot_predict", "swat_near_duplicates", "swat_topk", "swat_topk_host", "swat_ctx_last_timing",
 ]
@@ -56,6 +56,7 @@ def load() -> C.CDLL:
         "swat_ctx_destroy": [vp],
         "swat_ctx_set_option": [vp, C.c_char_p, i64],
         "swat_ctx_last_timing": [vp, C.POINTER(C.c_double)],
+        "swat_bank_load": [vp, C.c_char_p, i32, i64, i64, vp, i64, C.POINTER(i32), vp],
         "swat_queries_create": [vp, vp, i32, vp, i32, i32, C.POINTER(vp)],
         "swat_queries_destroy": [vp],
         "swat_job_create": [vp, vp, i32, f32, C.POINTER(vp)],
@@ -279,6 +280,18 @@ class Job:
             self.close()
         except Exception:
             pass
+
+
+def bank_load(ctx: Context, path: str, dtype: torch.dtype, row_begin: int, row_end: int, chunk_rows: int = 0):
+    """Rows ``[row_begin, row_end)`` of a flat shard file -> a new ``[n,512]`` device tensor (``swat_bank_load``).
+    Returns ``(tensor, used_gds)``."""
+    dev = torch.device("cuda", ctx.device)
+    out = torch.empty(int(row_end) - int(row_begin), DIM, dtype=dtype, device=dev)
+    gds = C.c_int32(0)
+    with torch.cuda.device(dev):
+        _check(load().swat_bank_load(ctx._h, os.fsencode(path), _dtype_code(out), int(row_begin), int(row_end), _ptr(out), int(chunk_rows),
+                                     C.byref(gds), _stream(ctx.device)))
+    return out, bool(gds.value)
 
 
 def scores_dense(ctx: Context, queries: Queries, bank: torch.Tensor, engine="auto") -> torch.Tensor:

@@ -35,6 +35,23 @@ int32_t fail(int32_t code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+namespace swat {
+// error reporting / context access for the other translation units of the library (loader.cu)
+int32_t api_fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+}  // namespace swat
+
+namespace {
+
 #define CU_OK(expr)                                                                                     \
   do {                                                                                                  \
     cudaError_t e__ = (expr);                                                                           \
@@ -153,6 +170,10 @@ struct swat_job {
   std::vector<uint32_t> h_k_class;    // what swat_job_set_class_depth last uploaded there (empty = unknown)
   cudaStream_t last_stream = nullptr;
 };
+
+namespace swat {
+int api_ctx_device(const swat_ctx* ctx) { return ctx->device; }
+}  // namespace swat
 
 namespace {
 

@@ -18,7 +18,7 @@ PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libswat_b200.so")
 BUILD = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "scan_tc.cu", "scan_simt.cu", "select.cu"]
+SOURCES = ["api.cu", "scan_tc.cu", "scan_simt.cu", "select.cu", "loader.cu"]
 HEADERS = ["common.cuh", "epilogue.cuh", "scan_tc.h", "tc_ptx.cuh", os.path.join(REPO, "include", "swat_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -114,11 +114,25 @@ class FlatShard:
         return {"caption_features": self.caption(), "image_features": self.image(), "labels": self.labels(),
                 "filepath": self.paths()}
 
-    def to_device(self, device, rows: Optional[slice] = None, pinned_chunk_rows: int = 1 << 18):
-        """Rows -> HBM (a rank of a sharded run passes its own row range).  Two pinned staging buffers: the host copy
-        of chunk i+1 out of the page cache overlaps the asynchronous H2D copy of chunk i, which runs at full PCIe rate
-        because the source is page-locked."""
+    def to_device(self, device, rows: Optional[slice] = None, pinned_chunk_rows: int = 1 << 16, native: bool = True):
+        """Rows -> HBM (a rank of a sharded run passes its own row range).
+
+        ``native`` (default): the C-ABI loader ``swat_bank_load`` -- GPUDirect Storage when available, else ``pread`` into
+        two pinned staging buffers with the read of chunk i+1 overlapping the H2D copy of chunk i.  ``self.used_gds``
+        tells which.  ``native=False`` does the staged copy with torch tensors (kept as the loader's cross-check)."""
         rows = rows or slice(0, self.n_rows)
+        if native:
+            from . import _lib
+            from .retrieval import get_context
+            dev = torch.device(device)
+            ctx = get_context(dev.index if dev.index is not None else torch.cuda.current_device())
+            tdt = _TORCH[self.dtype]
+            out_c, g1 = _lib.bank_load(ctx, os.path.join(self.path, "caption.bin"), tdt, rows.start, rows.stop, pinned_chunk_rows)
+            out_i, g2 = (None, False)
+            if self._img is not None:
+                out_i, g2 = _lib.bank_load(ctx, os.path.join(self.path, "image.bin"), tdt, rows.start, rows.stop, pinned_chunk_rows)
+            self.used_gds = bool(g1 or g2)
+            return out_c, out_i
         n = rows.stop - rows.start
         tdt = _TORCH[self.dtype]
         out_c = torch.empty(n, DIM, dtype=tdt, device=device)

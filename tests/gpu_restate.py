@@ -113,14 +113,15 @@ def restate_topk_walk(t2t_bank: torch.Tensor, queries: torch.Tensor, k: int, thr
 
 
 def compare_walks(got, ref, tie_tol: float, boundary_tol: float = 1e-3, what: str = "", aux_thr: Optional[float] = None,
-                  flip_tol: float = 2e-6):
+                  flip_tol: float = 2e-6, thr: Optional[float] = None):
     """``got`` = (scores, rows, t2i | None, counts) from the product (device or host tensors), ``ref`` = (rows, scores,
     t2i | None, counts) from an oracle (numpy).  The north star's parity rule per class:
 
     * same counts, scores within 1e-3, each side descending;
     * rows on one side only are either at the k-th boundary (score within ``boundary_tol`` of the last accepted score)
-      or *predicate flips*: their T2I score sits within ``flip_tol`` of the threshold, so two fp32 summation orders
-      legitimately disagree on ``t2i >= 0.25`` (each flip also moves one row across the k-th boundary);
+      or *predicate flips*: their T2I score (or, with ``thr``, their T2T score) sits within ``flip_tol`` of the
+      threshold, so two fp32 summation orders legitimately disagree on ``t2i >= 0.25`` (each flip also moves one row
+      across the k-th boundary);
     * the rows both sides accepted appear in the same order up to swaps among scores that agree to ``tie_tol``.
 
     Returns (interior swaps, boundary differences, predicate flips, positions compared)."""
@@ -143,6 +144,8 @@ def compare_walks(got, ref, tie_tol: float, boundary_tol: float = 1e-3, what: st
         if aux_thr is not None and g_t is not None and r_t is not None:
             ta = dict(zip(a.tolist(), g_t[c, :n].tolist())); tb = dict(zip(b.tolist(), r_t[c, :m].tolist()))
             flipped = {r for r in only_a if abs(ta[r] - aux_thr) <= flip_tol} | {r for r in only_b if abs(tb[r] - aux_thr) <= flip_tol}
+        if thr is not None:            # same for the T2T threshold: a score within flip_tol of it may be accepted by one side only
+            flipped |= {r for r in only_a if abs(sa[r] - thr) <= flip_tol} | {r for r in only_b if abs(sb[r] - thr) <= flip_tol}
         assert abs(n - m) <= len(flipped), f"{what} class {c}: count {n} != {m}"
         last = min(float(g_s[c, n - 1]) if n else 1.0, float(r_s[c, m - 1]) if m else 1.0)
         for r in (only_a | only_b) - flipped:

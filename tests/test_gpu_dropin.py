@@ -300,10 +300,15 @@ def test_flat_shard_to_hbm_and_sampler(tmp_path, name, dt):
     fs = shards.FlatShard(str(tmp_path / "flat"))
     want_c = raw["caption_features"].to(torch.bfloat16 if dt == "bf16" else torch.float32)
     want_i = raw["image_features"].to(torch.bfloat16 if dt == "bf16" else torch.float32)
-    c, i = fs.to_device("cuda:0", pinned_chunk_rows=100)
-    assert torch.equal(c.cpu(), want_c) and torch.equal(i.cpu(), want_i)
-    c, i = fs.to_device("cuda:0", rows=slice(37, 411), pinned_chunk_rows=64)
-    assert torch.equal(c.cpu(), want_c[37:411]) and torch.equal(i.cpu(), want_i[37:411])
+    for native in (True, False):           # the C-ABI loader (swat_bank_load) and the torch staging path it replaces
+        c, i = fs.to_device("cuda:0", pinned_chunk_rows=100, native=native)
+        assert torch.equal(c.cpu(), want_c) and torch.equal(i.cpu(), want_i)
+        c, i = fs.to_device("cuda:0", rows=slice(37, 411), pinned_chunk_rows=64, native=native)
+        assert torch.equal(c.cpu(), want_c[37:411]) and torch.equal(i.cpu(), want_i[37:411])
+    print("GPUDirect Storage used:", fs.used_gds)
+    from swat_b200 import _lib
+    with pytest.raises(_lib.SwatError):
+        _lib.bank_load(retrieval.get_context(0), str(tmp_path / "flat" / "caption.bin"), want_c.dtype, 0, 10 ** 7)      # beyond the file
     feats = retrieval.transform_extracted_fea(fs.as_mined_dict())
     args = Namespace(dataset="synthetic", output_folder=str(tmp_path / "out"), prefix="T2T", bank_dtype=dt, caption_map_path="/nonexistent")
     ms, nd = retrieval.t2t_ranked_t2i_tshd_sampler(args, logging.getLogger("t"), prompts, int(z["k"]), 0.0, feats)

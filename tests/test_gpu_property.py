@@ -1,0 +1,74 @@
+"""Property test: random shapes and options through the whole pipeline against the CPU oracle.
+
+Hypothesis draws the bank size, class count, synonym-group sizes and reduce mode, k, both thresholds, the exclusion
+density, the layout (every class scans the bank / one class per row) and the bank dtype; ``swat_topk`` must equal
+``so.topk_walk`` under the parity rule (tests/gpu_restate.compare_walks) on every draw."""
+import numpy as np
+import pytest
+import torch
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import HealthCheck, given, settings, strategies as st      # noqa: E402
+
+from oracle import swat_oracle as so                                        # noqa: E402
+from tests.gpu_restate import compare_walks                                 # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from swat_b200 import _lib
+    ctx = _lib.Context(0)
+    yield _lib, ctx
+    ctx.close()
+
+
+def _bank(n, class_vecs, seed, rho=0.3):
+    g = torch.Generator().manual_seed(seed)
+    C = class_vecs.shape[0]
+    lab = torch.randint(0, C, (n,), generator=g)
+    rel = torch.rand(n, generator=g) < rho
+    a = torch.rand(n, generator=g) * 0.8 * rel
+    b = torch.rand(n, generator=g) * 0.6 * rel
+    unit = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    base = class_vecs[lab].float()
+    cap = unit(a[:, None] * base + torch.sqrt(1 - a * a)[:, None] * unit(torch.randn(n, 512, generator=g)))
+    img = unit(b[:, None] * base + torch.sqrt(1 - b * b)[:, None] * unit(torch.randn(n, 512, generator=g)))
+    if n > 8:                                    # exact duplicates: ties must break by row index
+        dst = torch.randint(1, n, (max(1, n // 50),), generator=g)
+        cap[dst] = cap[dst - 1]; img[dst] = img[dst - 1]; lab[dst] = lab[dst - 1]
+    return cap, img, lab
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(n=st.integers(1, 20_000), C=st.integers(1, 40), reduce=st.sampled_from(["none", "mean", "max", "min"]),
+       k=st.integers(1, 300), thr=st.sampled_from([-1.0, 0.0, 0.05]), t2i=st.sampled_from([None, 0.0, 0.1, 0.25]),
+       excl=st.sampled_from([0.0, 0.3, 1.0]), part=st.booleans(), f32=st.booleans(), seed=st.integers(0, 10_000))
+def test_pipeline_matches_oracle_on_random_draws(env, n, C, reduce, k, thr, t2i, excl, part, f32, seed):
+    lib, ctx = env
+    g = torch.Generator().manual_seed(seed)
+    sizes = [1] * C if reduce == "none" else torch.randint(1, 5, (C,), generator=g).tolist()
+    coq = np.repeat(np.arange(C), sizes).astype(np.int32)
+    unit = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    qc = unit(torch.randn(C, 512, generator=g))
+    q = unit(qc[torch.from_numpy(coq).long()] + 0.3 * unit(torch.randn(len(coq), 512, generator=g))) if reduce != "none" else qc
+    dt = torch.float32 if f32 else torch.bfloat16
+    q = q.to(torch.bfloat16).float() if not f32 else q             # bf16 banks are scored against bf16-rounded prompts
+    cap, img, lab = _bank(n, qc, seed + 1)
+    cap, img = cap.to(dt), img.to(dt)
+    ex = (torch.rand(n, generator=g) < excl).numpy() if excl > 0 else None
+    bits = None
+    if ex is not None:
+        b = np.packbits(ex, bitorder="little")
+        bits = torch.from_numpy(np.concatenate([b, np.zeros((-len(b)) % 4, np.uint8)]).view(np.int32).copy()).cuda()
+    rc = lab.to(torch.int32) if part else None
+    o = so.topk_walk(cap.float().numpy(), q.numpy(), k, thr, t2i_bank=None if t2i is None else img.float().numpy(),
+                     t2i_threshold=0.25 if t2i is None else t2i, class_of_query=coq, n_classes=C, reduce=reduce,
+                     row_labels=None if rc is None else rc.numpy(), exclude=ex)
+    qs = lib.Queries(ctx, q, coq, C, reduce)
+    got = lib.topk(ctx, qs, cap.cuda(), k, thr, t2i_bank=None if t2i is None else img.cuda(), t2i_threshold=0.25 if t2i is None else t2i,
+                   row_class=None if rc is None else rc.cuda(), exclude=bits)
+    qs.close()
+    compare_walks(got, o, 2e-6, what=f"n={n} C={C} {reduce} k={k} thr={thr} t2i={t2i} excl={excl} part={part} f32={f32} seed={seed}",
+                  aux_thr=t2i, thr=thr)

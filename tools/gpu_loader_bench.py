@@ -29,9 +29,14 @@ for rep in range(2):
     t0 = time.perf_counter()
     fs = shards.FlatShard(os.path.join(tmp, "flat"))
     t_open = time.perf_counter() - t0
-    c, i = fs.to_device("cuda:0")
+    c, i = fs.to_device("cuda:0")          # C-ABI loader: swat_bank_load (GDS or pread + pinned double buffer)
     t_flat = time.perf_counter() - t0
+    del c, i
+    t0 = time.perf_counter()
+    c, i = fs.to_device("cuda:0", native=False, pinned_chunk_rows=1 << 18)
+    t_torch = time.perf_counter() - t0
     gb = 2 * N * 1024 / 1e9
     print(f"run {rep}: torch.load + .cuda() {t_ref:.2f} s | torch.load(mmap) + .cuda() {t_mmap:.2f} s | "
-          f"FlatShard open {t_open * 1e3:.1f} ms, to HBM {t_flat:.2f} s ({gb / t_flat:.1f} GB/s for {gb:.1f} GB of bf16)")
+          f"FlatShard open {t_open * 1e3:.1f} ms, swat_bank_load to HBM {t_flat:.2f} s ({gb / t_flat:.1f} GB/s for {gb:.1f} GB of bf16, "
+          f"GDS={fs.used_gds}) | torch staging {t_torch:.2f} s")
     del c, i, fs
