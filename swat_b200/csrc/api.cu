@@ -981,7 +981,7 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     for (int c : bad) {
       const int64_t d = k_class.empty() ? k_fetch : static_cast<int64_t>(k_class[c]);
       const int64_t p = accepted[c];
-      const bool hopeless = p <= 0 || d * k / p > 2 * kMaxKFetch;   // factor 2: borderline classes still try the ladder
+      const bool hopeless = p <= 0 || 4 * d * k / p > 5 * kMaxKFetch;   // expected need 25 % beyond the widest over-fetch
       ((hopeless || !ladder_left) && can_swap ? few : deeper).push_back(c);
     }
     if (!few.empty()) {

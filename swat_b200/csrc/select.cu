@@ -65,10 +65,16 @@ __device__ uint32_t select_sorted(const KeyFn keys, uint32_t n, uint32_t n_valid
   // gather every real key >= prefix (on the decided digits)
   if (tid == 0) s_misc[3] = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < n; i += kSelThreads) {
-    const uint64_t key = keys(i);
-    if (key != 0ull && (key & mask) >= prefix) {
-      const uint32_t pos = atomicAdd(&s_misc[3], 1u);
+  for (uint32_t i0 = 0; i0 < n; i0 += kSelThreads) {       // warp-aggregated: one shared-memory atomic per warp and round
+    const uint32_t i = i0 + tid;
+    const uint64_t key = i < n ? keys(i) : 0ull;
+    const bool keep = key != 0ull && (key & mask) >= prefix;
+    const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+    uint32_t base = 0;
+    if ((tid & 31) == 0 && ball) base = atomicAdd(&s_misc[3], static_cast<uint32_t>(__popc(ball)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      const uint32_t pos = base + __popc(ball & ((1u << (tid & 31)) - 1u));
       if (pos < static_cast<uint32_t>(kSortCap)) s_keys[pos] = key;
     }
   }
@@ -142,26 +148,55 @@ __global__ void __launch_bounds__(256) final_tau_kernel(const JobState st, int n
 // survivor lists -> per-class candidate arrays, keeping only entries at or above the final class
 // threshold (about k_fetch plus one histogram bin per class)
 __global__ void __launch_bounds__(256) partition_kernel(const JobState st) {
-  // one CTA per (list, quarter); four entries per thread and round, all loaded before any is tested: the kernel is a
-  // chain of dependent global accesses (count -> entry -> threshold -> slot), so independent entries hide each other
+  // direct version (label sets too large for the shared-memory counters below): one global atomic per kept entry
   const uint32_t l = blockIdx.x;
   const uint32_t n = min(st.list_count[l], st.list_cap);
   const uint4* src = st.list + static_cast<size_t>(l) * st.list_cap;
-  constexpr uint32_t kUnroll = 4;
-  const uint32_t step = gridDim.y * blockDim.x * kUnroll;
-  for (uint32_t i0 = (blockIdx.y * blockDim.x + threadIdx.x) * kUnroll; i0 < n; i0 += step) {
-    uint4 e[kUnroll];
-    uint32_t tau[kUnroll];
-#pragma unroll
-    for (uint32_t j = 0; j < kUnroll; ++j) e[j] = (i0 + j < n) ? src[i0 + j] : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (uint32_t j = 0; j < kUnroll; ++j) tau[j] = (i0 + j < n) ? st.tau_enc[e[j].z] : 0xffffffffu;
-#pragma unroll
-    for (uint32_t j = 0; j < kUnroll; ++j) {
-      if (i0 + j < n && e[j].y >= tau[j]) {
-        const uint32_t cls = e[j].z;
-        const uint32_t slot = atomicAdd(&st.count[cls], 1u);
-        if (slot < st.cap) st.cand[static_cast<size_t>(cls) * st.cap + slot] = (static_cast<uint64_t>(e[j].y) << 32) | e[j].x;
+  for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+    const uint4 e = src[i];
+    const uint32_t cls = e.z;
+    if (e.y >= st.tau_enc[cls]) {
+      const uint32_t slot = atomicAdd(&st.count[cls], 1u);
+      if (slot < st.cap) st.cand[static_cast<size_t>(cls) * st.cap + slot] = (static_cast<uint64_t>(e.y) << 32) | e.x;
+      else atomicOr(st.flags, 1u);
+    }
+  }
+}
+
+// Block-aggregated version.  About k_fetch entries per class survive the final threshold, i.e. hundreds of thousands
+// of atomics on a few hundred hot counters: same-address atomics serialise in L2 and that, not the 40 MB of list
+// traffic, set the pace (67 us).  Each CTA owns a slice of the lists, counts its kept entries per class in shared
+// memory, reserves one range per class with ONE global atomic, and scatters on a second pass over its (L2-resident) slice.
+__global__ void __launch_bounds__(1024) partition_agg_kernel(const JobState st, int n_classes) {
+  extern __shared__ uint32_t s_part[];
+  uint32_t* s_cnt = s_part;                 // [n_classes] kept entries of this CTA, then running offsets
+  uint32_t* s_base = s_part + n_classes;    // [n_classes] first slot of this CTA's range
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) s_cnt[c] = 0;
+  __syncthreads();
+  for (uint32_t l = blockIdx.x; l < st.n_lists; l += gridDim.x) {
+    const uint32_t n = min(st.list_count[l], st.list_cap);
+    const uint4* src = st.list + static_cast<size_t>(l) * st.list_cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint4 e = src[i];
+      if (e.y >= st.tau_enc[e.z]) atomicAdd(&s_cnt[e.z], 1u);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) {
+    const uint32_t m = s_cnt[c];
+    s_base[c] = m ? atomicAdd(&st.count[c], m) : 0u;
+    s_cnt[c] = 0;
+  }
+  __syncthreads();
+  for (uint32_t l = blockIdx.x; l < st.n_lists; l += gridDim.x) {
+    const uint32_t n = min(st.list_count[l], st.list_cap);
+    const uint4* src = st.list + static_cast<size_t>(l) * st.list_cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint4 e = src[i];
+      const uint32_t cls = e.z;
+      if (e.y >= st.tau_enc[cls]) {
+        const uint32_t slot = s_base[cls] + atomicAdd(&s_cnt[cls], 1u);
+        if (slot < st.cap) st.cand[static_cast<size_t>(cls) * st.cap + slot] = (static_cast<uint64_t>(e.y) << 32) | e.x;
         else atomicOr(st.flags, 1u);
       }
     }
@@ -687,7 +722,21 @@ cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset,
   final_tau_kernel<<<(n_classes + 7) / 8, 256, 0, stream>>>(st, n_classes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  partition_kernel<<<dim3(st.n_lists, 2), 256, 0, stream>>>(st);
+  const size_t part_smem = static_cast<size_t>(n_classes) * 8;
+  if (part_smem <= 160 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(partition_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    partition_agg_kernel<<<sms, 1024, part_smem, stream>>>(st, n_classes);
+  } else {
+    partition_kernel<<<dim3(st.n_lists, 4), 256, 0, stream>>>(st);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated);

@@ -117,7 +117,7 @@ def test_config1_verbatim_port(cfg1):
                             aux_thr=0.25 if with_t2i else None)
         # the port (like the reference) scores each class with its own GEMV: bit-identical rows of the planted block of
         # 1000 ties come out 1 ulp apart depending on their position in the BLAS blocking, so their order is not index order
-        _report(f"cfg1 verbatim port, Zipf-partitioned, t2i={with_t2i}", res, swap_div=100)
+        _report(f"cfg1 verbatim port, Zipf-partitioned, t2i={with_t2i}", res, swap_div=50)
     # unpartitioned: classes 5 and 117
     cap, img, _ = w["banks"][False]
     capf, imgf = cap.cpu().numpy(), img.cpu().numpy()
