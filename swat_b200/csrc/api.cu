@@ -117,7 +117,7 @@ struct swat_ctx {
   DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
   DevBuf w_swap[10];                // bank-swap escalation pass: two re-score stages
   int lock_window = 0;              // several Q blocks: pairs sharing a tile range stay within this many tiles of each other (0 = off)
-  DevBuf w_progress;
+  DevBuf w_progress, w_bits, w_splice;
   int f32_op_stages = 3;            // fp32 banks: bf16 operand stages (the rest of the shared memory stages fp32 boxes); before swat_queries_create
   bool zero_copy = true;            // host pipeline: read candidates' rows from pinned host banks in place
   bool swap_pass = true;            // classes with fewer than k rows passing T2I: enumerate the passers from the image bank
@@ -238,9 +238,17 @@ float scan_eps(const swat_queries* q, int32_t dtype, int32_t engine) {
   return (engine == SWAT_ENGINE_TC && dtype == SWAT_F32) ? q->eps_conv : kEpsAccum;
 }
 
+// the two passes of the tensor-core in-pass predicate (ScanArgs::bits_out / pass_bits)
+struct ScanBits {
+  uint32_t* out = nullptr;          // pass A: write the predicate bitmap (dense mode, nothing is selected)
+  const uint32_t* pass = nullptr;   // pass B: keep a survivor only if its bit is set
+  int64_t words = 0;                // words per class
+  float thr = 0.0f;                 // pass A threshold
+};
+
 int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
                   float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, float* dense_out,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const ScanBits* bits = nullptr) {
   swat_ctx* ctx = job->ctx;
   const swat_queries* q = job->q;
   if (n_rows == 0) return SWAT_OK;
@@ -252,6 +260,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
   const bool f32 = dtype == SWAT_F32;
   // dense scores are the S1 primitives (t2t_similarity :397-416) and the zero-shot logits: exact fp32 arithmetic for fp32 banks
   if (engine == SWAT_ENGINE_AUTO) engine = (dense_out != nullptr && f32) ? SWAT_ENGINE_SIMT : resolve_engine(q, dtype, d_t2i_bank != nullptr);
+  const bool dense = dense_out != nullptr || (bits != nullptr && bits->out != nullptr);   // nothing is selected
   if (engine == SWAT_ENGINE_TC && d_t2i_bank != nullptr)
     return fail(SWAT_ERR_UNSUPPORTED, "the tcgen05 engine does not evaluate the in-pass T2I predicate");
   ScanArgs a;
@@ -268,6 +277,10 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
   a.dense_ld = q->C;
   a.dense_transposed = 0;
   a.n_classes = q->C;
+  a.bits_out = bits ? bits->out : nullptr;
+  a.pass_bits = bits ? bits->pass : nullptr;
+  a.bits_words = bits ? bits->words : 0;
+  a.bits_thr = bits ? bits->thr : 0.0f;
   job->last_stream = stream;
   if (engine == SWAT_ENGINE_TC) {
     if ((f32 ? q->n_fstages : q->n_stages) <= 0)
@@ -286,14 +299,15 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     int grid = ctx->sm_count;
     if (ctx->max_ctas > 0) grid = std::min(grid, ctx->max_ctas);
     grid = std::max(q->ctas, grid / q->ctas * q->ctas);
-    if (dense_out == nullptr && static_cast<uint32_t>(grid) * kTcEpiWarps > job->st.n_lists)
+    if (!dense && static_cast<uint32_t>(grid) * kTcEpiWarps > job->st.n_lists)
       return fail(SWAT_ERR_INVALID, "grid of %d CTAs needs %d survivor lists, job has %u", grid, grid * kTcEpiWarps, job->st.n_lists);
     const char* bank = static_cast<const char*>(d_bank);
     // ---- threshold bootstrap: a fresh job would append every non-negative score of its first waves
     // (thresholds start at the user threshold).  Dense-score a small prefix with the same kernel, take
     // its exact top-k_fetch per class, and start the real scan with selective thresholds.
     int64_t B = 0;
-    if (dense_out == nullptr && job->fresh && ctx->bootstrap_rows > 0 && d_row_class == nullptr && d_exclude == nullptr) {
+    // (not with a predicate bitmap: the prefix's best rows need not pass the predicate, their scores are no valid bound)
+    if (!dense && a.pass_bits == nullptr && job->fresh && ctx->bootstrap_rows > 0 && d_row_class == nullptr && d_exclude == nullptr) {
       B = std::min<int64_t>(ctx->bootstrap_rows, (512ll << 20) / (4ll * q->C)) / 256 * 256;
       if (B < 8192 || n_rows < 8 * B || static_cast<uint32_t>(grid) * kTcEpiWarps >= job->st.n_lists) B = 0;
     }
@@ -307,6 +321,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
       pd.s.dense_out = ctx->w_boot.as<float>();
       pd.s.dense_ld = B;
       pd.s.dense_transposed = 1;
+      pd.s.bits_out = nullptr;
       pd.bank_hint = 0x1000000000000000ull;
       for (int b0 = 0; b0 < q->n_qb; b0 += grid / q->ctas) {
         pd.qb_base = b0;
@@ -329,7 +344,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
     const int pairs = grid / q->ctas;
     const int64_t tiles = (a.n_rows + 128 * q->ctas - 1) / (128 * q->ctas);
     int launches = 1;
-    if (ctx->unit_plan && dense_out == nullptr && q->n_qb > 1 && pairs % q->n_qb != 0) {
+    if (ctx->unit_plan && !dense && q->n_qb > 1 && pairs % q->n_qb != 0) {
       const int g = std::gcd(q->n_qb, pairs);
       const int per_pair = q->n_qb / g, ranges = pairs / g;        // units per pair, tile ranges
       if (per_pair <= 64 && tiles >= 16ll * ranges) {              // units of >= 16 tiles, else one launch does
@@ -338,7 +353,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
       }
     }
     if (p.n_ranges == 0 && q->n_qb > pairs) launches = (q->n_qb + pairs - 1) / pairs;   // legacy plan: `pairs` Q blocks per launch
-    const bool lockstep = ctx->lock_window > 0 && q->n_qb > 1 && dense_out == nullptr;
+    const bool lockstep = ctx->lock_window > 0 && q->n_qb > 1 && !dense;
     if (lockstep) {
       SW_OK(ctx->w_progress.ensure(static_cast<size_t>(launches) * pairs * 4));
       CU_OK(cudaMemsetAsync(ctx->w_progress.p, 0, static_cast<size_t>(launches) * pairs * 4, stream));
@@ -352,15 +367,15 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
         p.qb_base = i * pairs;
         p.qb_count = std::min(pairs, q->n_qb - p.qb_base);
       }
-      CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense_out != nullptr, f32, grid, stream));
+      CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense, f32, grid, stream));
     }
     ctx->launches += launches - 1;
   } else {
     const void* qp = (dtype == SWAT_BF16) ? static_cast<const void*>(q->d_qp_bf16) : static_cast<const void*>(q->d_qp_f32);
-    CU_OK(launch_scan_simt(a, d_bank, d_t2i_bank, qp, dtype, q->reduce, d_row_class != nullptr, dense_out != nullptr, stream));
+    CU_OK(launch_scan_simt(a, d_bank, d_t2i_bank, qp, dtype, q->reduce, d_row_class != nullptr, dense, stream));
   }
   ctx->launches += 1;
-  if (dense_out == nullptr) job->fresh = false;
+  if (!dense) job->fresh = false;
   return SWAT_OK;
 }
 
@@ -485,7 +500,9 @@ const void* mapped_alias(const void* h) {
 }
 
 // one pass over the whole bank, folding every view into `job`
-int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, bool dual, float t2i_thr, cudaStream_t stream) {
+int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, const ScanBits* bits, cudaStream_t stream) {
+  const bool dual = false;         // the fp32-FMA in-pass predicate is reachable through swat_job_scan only
+  const float t2i_thr = 0.0f;
   if (!b.host) {
     const int64_t max_view = 0x40000000ll;   // TMA coordinates are int32
     for (int64_t r0 = 0; r0 < b.n_rows; r0 += max_view) {
@@ -494,7 +511,7 @@ int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, bool dual, floa
       SW_OK(scan_view(job, static_cast<const char*>(b.t2t) + off, b.dtype, n, r0,
                       dual ? static_cast<const char*>(b.t2i) + off : nullptr, t2i_thr,
                       b.row_class ? b.row_class + r0 : nullptr, b.exclude ? b.exclude + r0 / 32 : nullptr, SWAT_ENGINE_AUTO,
-                      nullptr, stream));
+                      nullptr, stream, bits));
     }
     return SWAT_OK;
   }
@@ -536,7 +553,7 @@ int32_t scan_all(swat_ctx* ctx, swat_job* job, const BankSrc& b, bool dual, floa
     CU_OK(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
     CU_OK(cudaStreamWaitEvent(stream, ctx->ev_copied[s], 0));
     SW_OK(scan_view(job, dst, b.dtype, n, r0, dst2, t2i_thr, b.row_class ? ctx->w_rc[s].as<int32_t>() : nullptr,
-                    b.exclude ? ctx->w_ex[s].as<uint32_t>() : nullptr, SWAT_ENGINE_AUTO, nullptr, stream));
+                    b.exclude ? ctx->w_ex[s].as<uint32_t>() : nullptr, SWAT_ENGINE_AUTO, nullptr, stream, bits));
     CU_OK(cudaEventRecord(ctx->ev_used[s], stream));
   }
   return SWAT_OK;
@@ -658,6 +675,23 @@ int32_t walk_candidates(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, 
   return SWAT_OK;
 }
 
+// splice result rows of some classes into the final arrays with one kernel (dst class ids / source indices uploaded once)
+int32_t splice_results(swat_ctx* ctx, const std::vector<int32_t>& dst_cls, const std::vector<int32_t>& src_idx, int32_t k,
+                       const float* s_scores, const int64_t* s_rows, const float* s_aux, const int32_t* s_counts, float* d_scores,
+                       int64_t* d_rows, float* d_aux, int32_t* d_counts, cudaStream_t stream) {
+  const size_t n = dst_cls.size();
+  if (n == 0) return SWAT_OK;
+  SW_OK(ctx->w_splice.ensure(2 * n * 4));
+  std::vector<int32_t> both(dst_cls);
+  both.insert(both.end(), src_idx.begin(), src_idx.end());
+  CU_OK(cudaMemcpyAsync(ctx->w_splice.p, both.data(), 2 * n * 4, cudaMemcpyHostToDevice, stream));
+  CU_OK(launch_splice(ctx->w_splice.as<int32_t>(), ctx->w_splice.as<int32_t>() + n, static_cast<int>(n), k, s_scores, s_rows, s_aux, s_counts,
+                      d_scores, d_rows, d_aux, d_counts, stream));
+  CU_OK(cudaStreamSynchronize(stream));        // `both` is pageable and dies at scope end
+  ctx->launches += 1;
+  return SWAT_OK;
+}
+
 // Bank-swap escalation pass.  A class whose T2T-ordered walk ran out of candidates has FEW rows passing the T2I
 // predicate (that is why k were not found among the best 4096 by T2T).  So enumerate the passers instead: scan the
 // IMAGE bank with the T2I threshold (minus the scan's error bound) as the row threshold; if fewer than 4096 rows of the
@@ -685,7 +719,7 @@ int32_t swap_pass(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_
     SW_OK(acquire_job(ctx, q, kf, t2i_thr - eps, cap, list_entries, &job));
     SW_OK(swat_job_reset(job, stream));
     CU_OK(cudaEventRecord(ctx->ev[0], stream));
-    SW_OK(scan_all(ctx, job, sb, false, 0.0f, stream));
+    SW_OK(scan_all(ctx, job, sb, nullptr, stream));
     CU_OK(cudaEventRecord(ctx->ev[1], stream));
     CU_OK(launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(),
                         ctx->w_trunc.as<int32_t>(), stream));
@@ -716,16 +750,14 @@ int32_t swap_pass(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int64_
   std::vector<char> want(C, only ? 0 : 1);
   if (only) for (int c : *only) want[c] = 1;
   unresolved->clear();
+  std::vector<int32_t> take;
   for (int c = 0; c < C; ++c) {
     if (!want[c]) continue;
-    if (ctx->h_status[1 + c] != 0) { unresolved->push_back(c); continue; }
-    const size_t o = static_cast<size_t>(c) * k;
-    CU_OK(cudaMemcpyAsync(d_out_scores + o, w[0].as<float>() + o, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream));
-    CU_OK(cudaMemcpyAsync(d_out_rows + o, w[1].as<int64_t>() + o, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, stream));
-    if (d_out_t2i) CU_OK(cudaMemcpyAsync(d_out_t2i + o, w[2].as<float>() + o, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream));
-    CU_OK(cudaMemcpyAsync(d_out_counts + c, w[3].as<int32_t>() + c, 4, cudaMemcpyDeviceToDevice, stream));
+    if (ctx->h_status[1 + c] != 0) unresolved->push_back(c);
+    else take.push_back(c);
   }
-  CU_OK(cudaStreamSynchronize(stream));
+  SW_OK(splice_results(ctx, take, take, k, w[0].as<float>(), w[1].as<int64_t>(), d_out_t2i ? w[2].as<float>() : nullptr, w[3].as<int32_t>(),
+                       d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream));
   return SWAT_OK;
 }
 
@@ -791,16 +823,12 @@ int32_t escalate_classes(swat_ctx* ctx, const swat_queries* q, const BankSrc& b,
   if (rc == SWAT_OK)
     rc = run_pipeline(ctx, sub, sb, row_offset, k, thr, t2i_thr, o_s.as<float>(), o_r.as<int64_t>(), d_out_t2i ? o_t.as<float>() : nullptr,
                       o_c.as<int32_t>(), stream, k_fetch_next, depth + 1);
-  cudaError_t e = cudaSuccess;
-  for (int i = 0; i < n && rc == SWAT_OK && e == cudaSuccess; ++i) {
-    const size_t c = classes[i];
-    e = cudaMemcpyAsync(d_out_scores + c * k, o_s.as<float>() + static_cast<size_t>(i) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_out_rows + c * k, o_r.as<int64_t>() + static_cast<size_t>(i) * k, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, stream);
-    if (e == cudaSuccess && d_out_t2i) e = cudaMemcpyAsync(d_out_t2i + c * k, o_t.as<float>() + static_cast<size_t>(i) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_out_counts + c, o_c.as<int32_t>() + i, 4, cudaMemcpyDeviceToDevice, stream);
+  if (rc == SWAT_OK) {
+    std::vector<int32_t> dst(classes.begin(), classes.end()), src(n);
+    for (int i = 0; i < n; ++i) src[i] = i;
+    rc = splice_results(ctx, dst, src, k, o_s.as<float>(), o_r.as<int64_t>(), d_out_t2i ? o_t.as<float>() : nullptr, o_c.as<int32_t>(),
+                        d_out_scores, d_out_rows, d_out_t2i, d_out_counts, stream);
   }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  if (rc == SWAT_OK && e != cudaSuccess) rc = fail(SWAT_ERR_CUDA, "splicing escalated classes failed: %s", cudaGetErrorString(e));
   q->last_k_fetch = sub->last_k_fetch;
   if (!cached) swat_queries_destroy(sub);
   return rc;
@@ -831,7 +859,7 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
   const int C = q->C;
   const bool want_t2i = b.t2i != nullptr;
   if (depth == 0) for (int i = 0; i < 8; ++i) ctx->timing[i] = 0;
-  const bool can_swap = want_t2i && ctx->swap_pass && !b.host;
+  const bool can_swap = want_t2i && ctx->swap_pass;
   const bool hinted_swap = k_fetch_init == 0 && depth == 0 && q->all_few_hint && ctx->overfetch == 0;
   if ((k_fetch_init == kSwapPass || hinted_swap) && can_swap) {
     // escalation beyond the widest over-fetch (or a query set whose classes all had too few T2I passers last time):
@@ -858,8 +886,10 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
       return SWAT_OK;
     }
   }
-  bool dual = want_t2i && k_fetch_init > kMaxKFetch;          // in-pass predicate (fp32-FMA kernel, both banks per row)
-  float eps = scan_eps(q, b.dtype, resolve_engine(q, b.dtype, dual));
+  // in-pass predicate: one tensor-core pass over the image bank writes the per-class bitmap of rows passing T2I, the
+  // caption scan then keeps only survivors whose bit is set -- the walk of :507-527 for ANY data, at two passes
+  bool dual = want_t2i && k_fetch_init > kMaxKFetch;
+  float eps = scan_eps(q, b.dtype, resolve_engine(q, b.dtype, false));
   // every candidate of the in-pass mode passed the (loosened) predicate: k plus slack for the frontier suffices
   int32_t k_fetch = dual ? default_k_fetch(ctx, k, false, b.host, eps)
                          : (k_fetch_init > 0 ? std::min(std::max(k_fetch_init, k), kMaxKFetch) : default_k_fetch(ctx, k, want_t2i, b.host, eps));
@@ -895,7 +925,22 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     }
     SW_OK(swat_job_reset(job, stream));
     CU_OK(cudaEventRecord(ctx->ev[0], stream));
-    SW_OK(scan_all(ctx, job, b, dual, t2i_thr - eps, stream));
+    if (dual) {
+      ScanBits pa, pb;
+      pa.words = pb.words = (b.n_rows + 31) / 32;
+      SW_OK(ctx->w_bits.ensure(static_cast<size_t>(C) * std::max<int64_t>(pa.words, 1) * 4));
+      pa.out = ctx->w_bits.as<uint32_t>();
+      pa.thr = t2i_thr - eps;
+      pb.pass = ctx->w_bits.as<uint32_t>();
+      BankSrc ib = b;              // pass A ranks nothing: class scores of the image rows against the threshold
+      ib.t2t = b.t2i; ib.t2i = nullptr; ib.t2t_mapped = b.t2i_mapped; ib.t2i_mapped = nullptr;
+      ib.row_class = nullptr; ib.exclude = nullptr;
+      SW_OK(scan_all(ctx, job, ib, &pa, stream));
+      SW_OK(scan_all(ctx, job, b, &pb, stream));
+      ctx->timing[4] += 1;
+    } else {
+      SW_OK(scan_all(ctx, job, b, nullptr, stream));
+    }
     CU_OK(cudaEventRecord(ctx->ev[1], stream));
     SW_OK(ctx->w_scores.ensure(static_cast<size_t>(C) * kf * 4));
     SW_OK(ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8));
@@ -1005,7 +1050,6 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
                                          "rows tie with the k-th score?)", (int)deeper.size(), kMaxKFetch);
       if (static_cast<int>(deeper.size()) == C) {
         dual = true;
-        eps = scan_eps(q, b.dtype, SWAT_ENGINE_SIMT);
         k_fetch = default_k_fetch(ctx, k, false, b.host, eps);
         k_class.clear();
         continue;
@@ -1096,7 +1140,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_exact, &ctx->w_aux, &ctx->w_incomplete, &ctx->w_keys,
                     &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
-                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot, &ctx->w_progress,
+                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot, &ctx->w_progress, &ctx->w_bits, &ctx->w_splice,
                     &ctx->w_swap[0], &ctx->w_swap[1], &ctx->w_swap[2], &ctx->w_swap[3], &ctx->w_swap[4], &ctx->w_swap[5], &ctx->w_swap[6],
                     &ctx->w_swap[7], &ctx->w_swap[8], &ctx->w_swap[9]};
   for (DevBuf* b : bufs) b->release();

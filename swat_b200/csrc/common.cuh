@@ -76,6 +76,13 @@ struct ScanArgs {
   int64_t dense_ld;           // leading dimension of dense_out
   int32_t dense_transposed;   // 0: dense_out[row*ld + class], 1: dense_out[class*ld + row] (coalesced)
   int32_t n_classes;
+  // In-pass predicate on the tensor cores, two passes.  Pass A (dense mode over the predicate bank): bit (class, row)
+  // of bits_out = class score >= bits_thr.  Pass B (selecting scan of the ranking bank): a survivor is kept only if
+  // its bit in pass_bits is set.  Both are [n_classes][bits_words] words over shard rows (row_base + view row).
+  uint32_t* bits_out;
+  const uint32_t* pass_bits;
+  int64_t bits_words;
+  float bits_thr;
 };
 
 __device__ __forceinline__ uint32_t class_k(const JobState& st, int cls) { return st.k_class ? st.k_class[cls] : st.k_fetch; }

@@ -38,6 +38,8 @@ struct SlowCtx {
   uint32_t list_cap;
   uint32_t row_base;
   float hist_lo, hist_scale;
+  const uint32_t* pass_bits;  // nullable: per-class bitmap of rows that pass the predicate (see ScanArgs)
+  int64_t bits_words;
 };
 __device__ __forceinline__ SlowCtx make_slow_ctx(const ScanArgs& a, uint32_t list_id) {
   SlowCtx s;
@@ -49,6 +51,8 @@ __device__ __forceinline__ SlowCtx make_slow_ctx(const ScanArgs& a, uint32_t lis
   s.row_base = a.row_base;
   s.hist_lo = a.st.hist_lo;
   s.hist_scale = a.st.hist_scale;
+  s.pass_bits = a.pass_bits;
+  s.bits_words = a.bits_words;
   return s;
 }
 
@@ -126,20 +130,33 @@ __device__ __forceinline__ void drain_survivors(const SlowCtx& sc, EpiCtx& cx, c
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t ballot = __ballot_sync(0xffffffffu, mask != 0u);
   while (ballot != 0u) {
-    const uint32_t n = __popc(ballot);
-    uint32_t base = cx.list_pos;
-    if (ATOMIC_LIST) {
-      if (lane == 0) base = atomicAdd(sc.list_count, n);
-      base = __shfl_sync(0xffffffffu, base, 0);
-    } else {
-      cx.list_pos += n;
-    }
-    if (mask != 0u) {
-      const int j = __ffs(mask) - 1;
+    // every lane with work takes its lowest remaining survivor; with a predicate bitmap the survivor must also have
+    // its (class, row) bit set -- tested here, on the rare path, so the fast path never sees the bitmap
+    int j = 0, cls = 0;
+    bool keep = mask != 0u;
+    if (keep) {
+      j = __ffs(mask) - 1;
       mask &= mask - 1u;
-      const int cls = cx.cls_col[col0 + j];
+      cls = cx.cls_col[col0 + j];
+      if (sc.pass_bits != nullptr) {
+        const uint32_t r = sc.row_base + cx.row;
+        keep = ((sc.pass_bits[static_cast<size_t>(cls) * sc.bits_words + (r >> 5)] >> (r & 31u)) & 1u) != 0u;
+      }
+    }
+    const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+    const uint32_t n = __popc(kept);
+    uint32_t base = cx.list_pos;
+    if (n != 0u) {
+      if (ATOMIC_LIST) {
+        if (lane == static_cast<uint32_t>(__ffs(kept) - 1)) base = atomicAdd(sc.list_count, n);
+        base = __shfl_sync(0xffffffffu, base, __ffs(kept) - 1);
+      } else {
+        cx.list_pos += n;
+      }
+    }
+    if (keep) {
       const float s = red_fin<RED>(pick_column<NC>(v, j), cx.cnt_col[col0 + j]) + 0.0f;   // -0.0 -> +0.0: Python compares them equal, the key must too
-      const uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
+      const uint32_t slot = base + __popc(kept & ((1u << lane) - 1u));
       if (slot < sc.list_cap) {
         const uint64_t key = make_key(s, sc.row_base + cx.row);
         sc.list_base[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(cls), 0u);
@@ -185,9 +202,16 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& a, const SlowCtx& 
     for (int j = 0; j < NC; ++j) {
       cx.acc = (RED == RED_NONE) ? v[j] : red_op<RED>(cx.acc, v[j]);
       if ((endmask >> j) & 1u) {  // warp-uniform
-        if (cx.row_valid)
+        if (a.bits_out != nullptr) {
+          // a warp owns 32 consecutive rows starting at a multiple of 32: one word per (class, warp)
+          const uint32_t word = __ballot_sync(0xffffffffu, cx.row_valid && red_fin<RED>(cx.acc, cnt[j]) >= a.bits_thr);
+          const uint32_t r = a.row_base + cx.row;
+          if ((threadIdx.x & 31) == 0 && static_cast<int64_t>(r >> 5) < a.bits_words)
+            a.bits_out[static_cast<size_t>(cls[j]) * a.bits_words + (r >> 5)] = word;
+        } else if (cx.row_valid) {
           a.dense_out[a.dense_transposed ? static_cast<size_t>(cls[j]) * a.dense_ld + cx.row : static_cast<size_t>(cx.row) * a.dense_ld + cls[j]] =
               red_fin<RED>(cx.acc, cnt[j]);
+        }
         cx.acc = red_init<RED>();
       }
     }

@@ -77,6 +77,10 @@ constexpr int kWalkLaunches = 2;
 // out[i] = canonical score of bank row i against the queries of class row_class[i] (-inf where row_class[i] < 0)
 cudaError_t launch_score_rows(const void* bank, int dtype, const int32_t* row_class, int64_t n_rows, const void* queries,
                               const int32_t* class_begin, int n_classes, int reduce, float* out, cudaStream_t stream);
+// result rows of n classes: dst[d_dst_cls[i]] <- src[d_src_idx[i]] ([.,k] scores / rows / aux, [.] counts)
+cudaError_t launch_splice(const int32_t* d_dst_cls, const int32_t* d_src_idx, int n, int k, const float* s_scores, const int64_t* s_rows,
+                          const float* s_aux, const int32_t* s_counts, float* d_scores, int64_t* d_rows, float* d_aux, int32_t* d_counts,
+                          cudaStream_t stream);
 // row_class of a sub-query run: out[i] = map[in[i]] (map: original class -> sub class or -1), -1 stays -1
 cudaError_t launch_remap_classes(const int32_t* in, const int32_t* map, int n_map, int64_t n, int32_t* out, cudaStream_t stream);
 

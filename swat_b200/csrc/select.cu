@@ -782,6 +782,29 @@ cudaError_t launch_score_rows(const void* bank, int dtype, const int32_t* row_cl
   return cudaGetLastError();
 }
 
+// out[dst_cls[i]] <- src[src_idx[i]] for the [.,k] result arrays of n classes (splicing escalated classes into the result)
+__global__ void __launch_bounds__(256) splice_kernel(const int32_t* __restrict__ dst_cls, const int32_t* __restrict__ src_idx, int k,
+                                                     const float* __restrict__ s_scores, const int64_t* __restrict__ s_rows,
+                                                     const float* __restrict__ s_aux, const int32_t* __restrict__ s_counts,
+                                                     float* __restrict__ d_scores, int64_t* __restrict__ d_rows, float* __restrict__ d_aux,
+                                                     int32_t* __restrict__ d_counts) {
+  const size_t d = static_cast<size_t>(dst_cls[blockIdx.x]) * k, s = static_cast<size_t>(src_idx[blockIdx.x]) * k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    d_scores[d + j] = s_scores[s + j];
+    d_rows[d + j] = s_rows[s + j];
+    if (d_aux && s_aux) d_aux[d + j] = s_aux[s + j];
+  }
+  if (threadIdx.x == 0) d_counts[dst_cls[blockIdx.x]] = s_counts[src_idx[blockIdx.x]];
+}
+
+cudaError_t launch_splice(const int32_t* d_dst_cls, const int32_t* d_src_idx, int n, int k, const float* s_scores, const int64_t* s_rows,
+                          const float* s_aux, const int32_t* s_counts, float* d_scores, int64_t* d_rows, float* d_aux, int32_t* d_counts,
+                          cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  splice_kernel<<<n, 256, 0, stream>>>(d_dst_cls, d_src_idx, k, s_scores, s_rows, s_aux, s_counts, d_scores, d_rows, d_aux, d_counts);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_remap_classes(const int32_t* in, const int32_t* map, int n_map, int64_t n, int32_t* out, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   remap_classes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, map, n_map, n, out);
