@@ -88,9 +88,10 @@ int32_t swat_queries_destroy(swat_queries* q);
 /* Rows [row_begin, row_end) of a flat shard file (raw row-major [n_rows,512] bf16 | f32: caption.bin / image.bin of
  * swat_b200/shards.py, converted once from the reference's *_mined.pth) -> d_dst, caller-allocated
  * [row_end-row_begin, 512] device memory: a rank of a sharded run loads its own row range.  Banks are plain device
- * pointers in this ABI, so there is no separate "bank from device" call.  GPUDirect Storage (cuFileRead straight into
- * d_dst) when libcufile loads and accepts the file, *used_gds = 1; otherwise pread() into two pinned staging buffers of
- * chunk_rows rows (0 = 65536), the read of chunk i+1 overlapping the H2D copy of chunk i on `stream`.  Synchronises. */
+ * pointers in this ABI, so there is no separate "bank from device" call.  pread() into two pinned staging buffers of
+ * chunk_rows rows (0 = 65536), the read of chunk i+1 overlapping the H2D copy of chunk i on `stream`; with SWAT_GDS=1 in
+ * the environment and a libcufile that accepts the file, GPUDirect Storage instead (cuFileRead straight into d_dst,
+ * *used_gds = 1).  Synchronises. */
 int32_t swat_bank_load(swat_ctx* ctx, const char* path, int32_t dtype, int64_t row_begin, int64_t row_end, void* d_dst,
                        int64_t chunk_rows, int32_t* used_gds, void* stream);
 

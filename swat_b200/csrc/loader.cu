@@ -4,8 +4,9 @@
 // /root/reference/retrieval/sample_retrieval.py:1473-1476, :337, :399 (a pickled dict that is read, unpickled and
 // copied row block by row block through pageable memory).  The flat shard (swat_b200/shards.py: raw row-major
 // [n_rows,512] bf16 | f32 files) is read straight into the bank's place in HBM:
-//   * GPUDirect Storage when libcufile loads and accepts the file (cuFileRead into device memory, no host staging);
-//   * otherwise pread() into two pinned staging buffers, the read of chunk i+1 overlapping the H2D copy of chunk i.
+//   * pread() into two pinned staging buffers, the read of chunk i+1 overlapping the H2D copy of chunk i (default);
+//   * GPUDirect Storage when SWAT_GDS=1 is set and libcufile loads and accepts the file (cuFileRead into device
+//     memory, no host staging).
 #include <cuda_runtime.h>
 #include <cufile.h>
 #include <dlfcn.h>
@@ -41,7 +42,10 @@ CuFileApi& cufile() {
   static CuFileApi api;
   if (api.tried) return api;
   api.tried = true;
-  if (getenv("SWAT_NO_GDS")) return api;
+  // Opt-in: on hosts without the nvidia-fs kernel module cuFileDriverOpen / cuFileRead can block for minutes in their
+  // compatibility mode, so GPUDirect Storage is used only when the operator asks for it (SWAT_GDS=1).
+  const char* want = getenv("SWAT_GDS");
+  if (!want || want[0] == '0') return api;
   api.lib = dlopen("libcufile.so.0", RTLD_NOW | RTLD_LOCAL);
   if (!api.lib) return api;
   api.driver_open = reinterpret_cast<decltype(api.driver_open)>(dlsym(api.lib, "cuFileDriverOpen"));

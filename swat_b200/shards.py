@@ -117,9 +117,9 @@ class FlatShard:
     def to_device(self, device, rows: Optional[slice] = None, pinned_chunk_rows: int = 1 << 16, native: bool = True):
         """Rows -> HBM (a rank of a sharded run passes its own row range).
 
-        ``native`` (default): the C-ABI loader ``swat_bank_load`` -- GPUDirect Storage when available, else ``pread`` into
-        two pinned staging buffers with the read of chunk i+1 overlapping the H2D copy of chunk i.  ``self.used_gds``
-        tells which.  ``native=False`` does the staged copy with torch tensors (kept as the loader's cross-check)."""
+        ``native`` (default): the C-ABI loader ``swat_bank_load`` -- ``pread`` into two pinned staging buffers with the read
+        of chunk i+1 overlapping the H2D copy of chunk i, or GPUDirect Storage with ``SWAT_GDS=1``; ``self.used_gds`` tells
+        which.  ``native=False`` does the staged copy with torch tensors (kept as the loader's cross-check)."""
         rows = rows or slice(0, self.n_rows)
         if native:
             from . import _lib

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 hypothesis = pytest.importorskip("hypothesis")
-from hypothesis import HealthCheck, given, settings, strategies as st      # noqa: E402
+from hypothesis import HealthCheck, Phase, given, settings, strategies as st      # noqa: E402
 
 from oracle import swat_oracle as so                                        # noqa: E402
 from tests.gpu_restate import compare_walks                                 # noqa: E402
@@ -41,7 +41,9 @@ def _bank(n, class_vecs, seed, rho=0.3):
     return cap, img, lab
 
 
-@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+# no shrinking: a failing draw is reported as drawn (its parameters are in the assertion message); GPU minutes are scarce
+@settings(max_examples=30, deadline=None, database=None, phases=[Phase.explicit, Phase.generate],
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(n=st.integers(1, 20_000), C=st.integers(1, 40), reduce=st.sampled_from(["none", "mean", "max", "min"]),
        k=st.integers(1, 300), thr=st.sampled_from([-1.0, 0.0, 0.05]), t2i=st.sampled_from([None, 0.0, 0.1, 0.25]),
        excl=st.sampled_from([0.0, 0.3, 1.0]), part=st.booleans(), f32=st.booleans(), seed=st.integers(0, 10_000))
