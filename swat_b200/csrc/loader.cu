@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/swat_b200.h"
 #include "common.cuh"
@@ -127,12 +129,27 @@ extern "C" int32_t swat_bank_load(swat_ctx* ctx, const char* path, int32_t dtype
   for (size_t o = 0; o < bytes && rc == SWAT_OK; o += chunk, b ^= 1) {
     const size_t n = std::min(chunk, bytes - o);
     if (busy[b] && cudaEventSynchronize(ev[b]) != cudaSuccess) { rc = api_fail(SWAT_ERR_CUDA, "event sync failed"); break; }
-    size_t got = 0;
-    while (got < n) {
-      const ssize_t r = pread(fd, stage[b] + got, n - got, static_cast<off_t>(off + o + got));
-      if (r <= 0) { rc = api_fail(SWAT_ERR_INVALID, "read of %s failed at offset %zu: %s", path, off + o + got, r == 0 ? "unexpected end of file" : strerror(errno)); break; }
-      got += static_cast<size_t>(r);
+    // the page cache -> pinned copy is a memcpy in the kernel: a few reader threads per chunk reach the memory bandwidth
+    const unsigned nt = n >= (size_t(8) << 20) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+    const size_t seg = (n / nt + 4095) / 4096 * 4096;
+    std::vector<int> err(nt, 0);
+    auto reader = [&](unsigned t) {
+      const size_t lo = std::min(n, static_cast<size_t>(t) * seg), hi = (t + 1 == nt) ? n : std::min(n, lo + seg);
+      size_t got = lo;
+      while (got < hi) {
+        const ssize_t r = pread(fd, stage[b] + got, hi - got, static_cast<off_t>(off + o + got));
+        if (r <= 0) { err[t] = r == 0 ? -1 : errno; return; }
+        got += static_cast<size_t>(r);
+      }
+    };
+    if (nt == 1) reader(0);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(reader, t);
+      for (auto& x : th) x.join();
     }
+    for (unsigned t = 0; t < nt && rc == SWAT_OK; ++t)
+      if (err[t] != 0) rc = api_fail(SWAT_ERR_INVALID, "read of %s failed near offset %zu: %s", path, off + o, err[t] < 0 ? "unexpected end of file" : strerror(err[t]));
     if (rc != SWAT_OK) break;
     if (cudaMemcpyAsync(static_cast<char*>(d_dst) + o, stage[b], n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
         cudaEventRecord(ev[b], stream) != cudaSuccess)
