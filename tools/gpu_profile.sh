@@ -1,13 +1,10 @@
 #!/bin/bash
-# round profile artifacts: bench line, ncu launch list of the same command, full captures of the scan kernel
+# round-2 profile artifacts: full captures of the scan kernel (bf16 bench workload, fp32 banks), DRAM traffic with several Q blocks
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo "bench exit $?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
-# steady state: 3 launches per step (dense prefix, main scan); skip the warm-up steps
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_tc -s 8 -c 2 -f -o gpurun_out/r01_scan_tc \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
-# Q = 1000 (imagenet shape, 4 Q blocks): does the bank still stream from HBM once?
-timeout 900 ncu --set full --clock-control none -k regex:scan_tc -s 6 -c 3 -f -o gpurun_out/r01_scan_tc_q1000 \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --classes 1000 --t2t-only > gpurun_out/ncu_q1000.log 2>&1; echo "ncu q1000 exit $?"
-tail -c 700 gpurun_out/bench_r01.json
+# bench workload: launches per step = dense prefix + main scan; skip the warm-up steps, capture one main scan
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_tc -s 7 -c 1 -f -o gpurun_out/r02_scan_tc \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-extras > gpurun_out/r02_ncu_full.log 2>&1; echo "ncu full exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_tc_kernel -s 3 -c 1 -f -o gpurun_out/r02_scan_f32_fixed \
+    python tools/gpu_f32_probe.py 4000000 > gpurun_out/r02_ncu_f32.log 2>&1; echo "ncu f32 exit $?"
+timeout 600 ncu --metrics dram__bytes_read.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
+    --clock-control none -k regex:scan_tc --csv --log-file gpurun_out/r02_l2share.csv python tools/gpu_l2share.py 10000000 200,400,1000 > gpurun_out/r02_l2share.log 2>&1; echo "l2share exit $?"
