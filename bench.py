@@ -362,7 +362,21 @@ def run_ours(a, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        # pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated: the e2e leg streams
+        # 10 GB per rank out of host memory and should not cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = f"rank pinned to {len(cpus)} CPUs local to GPU {local_rank}"
+        except Exception as e:          # affinity is an optimisation only
+            numa = f"affinity not set: {type(e).__name__}"
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local_rank)
     if a.overfetch:
@@ -490,6 +504,7 @@ def run_ours(a, rank, world, local_rank):
                "last_step_device_ms": {"caption_stream_and_scan": e2e_tm["scan_ms"], "select": e2e_tm["select_ms"],
                                        "rescore_and_walk": e2e_tm["t2i_ms"], "total": e2e_tm["total_ms"],
                                        "escalations": e2e_tm["escalations"]},
+               "numa": numa,
                "api": "swat_topk_host (C-ABI, pinned host banks)" if world == 1 else
                       "swat_topk_host per rank on its pinned host shard + one NCCL all-gather + swat_merge_topk"}
         del h_cap, h_img
