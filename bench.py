@@ -249,6 +249,9 @@ def run_extras(a, rank, world, dev, main):
         for _ in range(warm):
             step()
         scans = ctx.__dict__["_time_scans"] = []
+        sampler = ClockSampler(dev.index) if rank == 0 else None
+        if sampler:
+            sampler.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kern = []
@@ -260,6 +263,7 @@ def run_extras(a, rank, world, dev, main):
                 kern.append(tm["scan_ms"] / max(tm["scan_launches"], 1.0))      # one pass over the bank (all of its launches)
         e1.record()
         barrier()
+        clocks = sampler.stop() if sampler else None
         ctx.__dict__["_time_scans"] = None
         ms = max_over_ranks(e0.elapsed_time(e1) / reps)
         if world > 1:
@@ -268,7 +272,7 @@ def run_extras(a, rank, world, dev, main):
         kms = max_over_ranks(kern[len(kern) // 2]) if kern else None
         roof, bound = roof_rows_per_s(q_cols, bytes_per_row, hbm, tf)
         return {"rows_per_gpu": n_local, "Q": q_cols, "ms_per_step": ms, "scan_kernel_ms": kms,
-                "rows_per_s": n_local * world / (ms * 1e-3),
+                "rows_per_s": n_local * world / (ms * 1e-3), "clocks": clocks,
                 "roofline": {"bound": bound, "roof_rows_per_s_per_gpu": roof, "step_frac": n_local / (ms * 1e-3) / roof,
                              "kernel_frac": None if not kms else n_local / (kms * 1e-3) / roof}}
 

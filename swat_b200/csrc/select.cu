@@ -27,6 +27,15 @@ struct ScoreKeys {
   }
 };
 
+// keys below a lower bound of the k-th best are absent (merge: most of G*k entries cannot be in the result)
+struct FloorKeys {
+  const uint64_t* keys; uint64_t floor;
+  __device__ __forceinline__ uint64_t operator()(uint32_t i) const {
+    const uint64_t k = keys[i];
+    return k >= floor ? k : 0ull;
+  }
+};
+
 template <typename KeyFn>
 __device__ uint32_t select_sorted(const KeyFn keys, uint32_t n, uint32_t n_valid, uint32_t K, uint64_t* s_keys,
                                   uint32_t* s_hist, uint32_t* s_misc) {
@@ -622,17 +631,32 @@ merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ scores
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_misc[4];
   __shared__ uint32_t s_valid;
+  __shared__ unsigned long long s_floor;
   const int c = blockIdx.x, tid = threadIdx.x;
   const uint32_t n = static_cast<uint32_t>(G) * k;
   const uint64_t* kc = keys + static_cast<size_t>(c) * n;
-  if (tid == 0) s_valid = 0;
+  if (tid == 0) { s_valid = 0; s_floor = ~0ull; }
   __syncthreads();
+  // Lower bound of the k_out-th best key: the first ceil(k_out/G) entries of all shard lists together are at least
+  // k_out keys, so the result cannot reach below the smallest of them (for sorted lists that is the weakest shard's
+  // ceil(k_out/G)-th row).  An absent or predicate-failing entry among them (key 0) voids the bound.  Typically ~k_out
+  // of the G*k keys stay and the block sort shrinks accordingly.
+  const uint32_t per = (static_cast<uint32_t>(k_out) + G - 1) / G;
+  if (per <= static_cast<uint32_t>(k)) {
+    unsigned long long lo = ~0ull;
+    for (uint32_t i = tid; i < static_cast<uint32_t>(G) * per; i += kSelThreads) lo = min(lo, static_cast<unsigned long long>(kc[static_cast<size_t>(i / per) * k + i % per]));
+    if (lo != ~0ull) atomicMin(&s_floor, lo);
+  } else if (tid == 0) {
+    s_floor = 0ull;
+  }
+  __syncthreads();
+  const FloorKeys fk{kc, s_floor != 0ull ? static_cast<uint64_t>(s_floor) : 1ull};
   uint32_t v = 0;
-  for (uint32_t i = tid; i < n; i += kSelThreads) v += kc[i] != 0ull ? 1u : 0u;
+  for (uint32_t i = tid; i < n; i += kSelThreads) v += fk(i) != 0ull ? 1u : 0u;
   if (v) atomicAdd(&s_valid, v);
   __syncthreads();
   const uint32_t valid = s_valid;
-  const uint32_t total = select_sorted(GlobalKeys{kc}, n, valid, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
+  const uint32_t total = select_sorted(fk, n, valid, static_cast<uint32_t>(k_out), s_keys, s_hist, s_misc);
   const uint32_t cnt = min(static_cast<uint32_t>(k_out), total);
   for (uint32_t i = tid; i < static_cast<uint32_t>(k_out); i += kSelThreads) {
     const bool ok = i < cnt;
