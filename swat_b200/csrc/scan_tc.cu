@@ -153,7 +153,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         if (lane == 0) st_relaxed_gpu_u32(p.progress + pair_id, it);
         if (it < static_cast<uint32_t>(p.lock_window) || (it & 1u)) return;
         const uint32_t need = it - static_cast<uint32_t>(p.lock_window);
-        for (int spin = 0; spin < 256; ++spin) {
+        for (int spin = 0; spin < 48; ++spin) {      // bounded (~5 us): the window is a hint, never a dependency
           const uint32_t mine = lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu;
           if (__reduce_min_sync(0xffffffffu, mine) >= need) break;
           __nanosleep(100);
