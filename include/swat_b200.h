@@ -53,7 +53,7 @@ typedef enum { SWAT_REDUCE_NONE = 0, SWAT_REDUCE_MEAN = 1, SWAT_REDUCE_MAX = 2, 
 
 /* which scan kernel: AUTO = the tcgen05 kernel (bf16 banks natively; fp32 banks are converted to bf16 on the fly by
  * converter warps and every candidate is re-scored exactly in fp32 afterwards); SIMT = the fp32-FMA kernel (any
- * dtype, the in-pass T2I predicate, and the on-device checker). */
+ * dtype; exact dense scores of fp32 banks, the single-pass two-bank predicate of swat_job_scan, the on-device checker). */
 typedef enum { SWAT_ENGINE_AUTO = 0, SWAT_ENGINE_TC = 1, SWAT_ENGINE_SIMT = 2 } swat_engine;
 
 typedef struct swat_ctx swat_ctx;
@@ -108,7 +108,8 @@ int32_t swat_job_set_class_depth(swat_job* job, const int32_t* h_depth, void* st
 /* Score one bank view (rows [row_base, row_base+n_rows) of the shard) against every query and fold
  * it into the job.  d_bank: [n_rows,512] row-major, 16-byte aligned, dtype bf16|f32.
  * d_t2i_bank (nullable): same rows of the image bank; when given, the predicate
- * t2i >= t2i_threshold is evaluated in-pass for every row (exact for any data, 2x the bytes).
+ * t2i >= t2i_threshold is evaluated in the same pass for every row on the fp32-FMA kernel (2x the bytes; the
+ * whole-pipeline calls use two tensor-core passes with a per-class bitmap instead).
  * d_row_class (nullable): [n_rows] dense class index of each row, -1 = none: the reference's
  * partitioned case, a row is eligible only for its own class (transform_extracted_fea :1387-1415).
  * d_exclude (nullable): bitmap over the view's rows, bit set = never accept
@@ -201,12 +202,14 @@ int32_t swat_near_duplicates(swat_ctx* ctx, const void* d_bank, int32_t dtype, i
 /* t2t_ranked_sampler (:724-771) when d_t2i_bank == NULL, t2t_ranked_t2i_tshd_sampler (:774-825)
  * otherwise, for all classes at once.  Outputs [C,k] (d_out_t2i nullable), rows are
  * row_offset + local row (row_offset + n_rows < 2^32 - 1).  Scores are canonical (see swat_rescore_walk): identical
- * whichever engine, shard count or escalation path produced them.  Handles candidate-buffer overflow and over-fetch escalation
- * internally: deeper over-fetch for the classes that need it, then a pass over the image bank that
- * enumerates the rows able to pass T2I (classes with few of them), finally the exact in-pass
- * predicate.  Bank rows and queries are cosine features, L2-normalised as extract_mined_feature.py:121,181
- * and utils/features.py:30-31 produce them (the image-bank pass allows 1e-4 between tensor-core and exact
- * scores).  Synchronises. */
+ * whichever engine, shard count or escalation path produced them.  Handles candidate-buffer overflow and over-fetch
+ * escalation internally: deeper over-fetch for the classes that need it, then a pass over the image bank that
+ * enumerates the rows able to pass T2I (classes with few of them), finally the two-pass in-pass predicate (an
+ * image-bank pass writes a per-class bitmap of passing rows, the caption scan keeps only survivors whose bit is set).
+ * A class that cannot be proven exact at the widest over-fetch (more than ~3500 rows tying with its k-th score)
+ * fails the call with SWAT_ERR_INCOMPLETE -- never a silently wrong row.  fp32 banks: rows are assumed L2-normalised
+ * (extract_mined_feature.py:121,181; utils/features.py:30-31), which is what bounds the error of their bf16-rounded
+ * scan.  k <= 4096.  Synchronises. */
 int32_t swat_topk(swat_ctx* ctx, const swat_queries* q, const void* d_t2t_bank, const void* d_t2i_bank,
                   int32_t dtype, int64_t n_rows, int64_t row_offset, int32_t k, float t2t_threshold,
                   float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude,

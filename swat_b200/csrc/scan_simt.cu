@@ -1,10 +1,10 @@
 // SIMT fp32-FMA scan kernel: the exact-arithmetic path.
 //
-// Used (a) for fp32 banks (the reference's own dtype, utils/extras.py:163 model.float()), where
-// scores are accumulated in fp32 in ascending-k order like a plain dot product, (b) as the in-pass
-// T2I predicate fallback: with a second bank the full reference predicate
-// `t2t >= thr and t2i >= t2i_thr` (sample_retrieval.py:511-514) is evaluated for every row, which is
-// exact for any data, and (c) as the on-device checker the tcgen05 kernel is tested against.
+// Used (a) for the DENSE scores of fp32 banks (the S1 primitives t2t_similarity / cal_t2i_similarity and the zero-shot
+// logits; the reference's own dtype, utils/extras.py:163 model.float()), accumulated in fp32 in ascending-k order like a
+// plain dot product, (b) for swat_job_scan with a second bank: the full reference predicate
+// `t2t >= thr and t2i >= t2i_thr` (sample_retrieval.py:511-514) evaluated for every row in one pass, and (c) as the
+// on-device checker the tcgen05 kernel is tested against.  The whole-pipeline calls never select with it.
 // Same selection epilogue as the tensor-core kernel (epilogue.cuh): thread = bank row.
 #include "common.cuh"
 #include "epilogue.cuh"

@@ -165,3 +165,38 @@ def test_random_sampler_threshold0_is_host_only(tmp_path):
         assert [row[p] for fl in ms["file_list"] for p in fl] == ref["rows"] and nd == ref["counts"]
         assert hashlib.sha256(open(f"{args.output_folder}/RND_sampled_list.txt", "rb").read()).hexdigest() == ref["sampled_sha"]
         assert hashlib.sha256(open(f"{args.output_folder}/RND_filtered_list.txt", "rb").read()).hexdigest() == ref["filtered_sha"]
+
+
+def test_filtered_list_walk_reproduces_reference_rows():
+    """``filtered_list.txt`` (sample_retrieval.py:463-469, :521-527) is host logic over per-row scores: with the oracle's
+    fp32 scores standing in for ``swat_score_rows`` it must list exactly the rows the reference rejected, in walk order."""
+    import inspect
+    import torch
+    from oracle import swat_oracle as so
+    from swat_b200 import retrieval
+    from tests.golden_util import load_bank_case, make_paths
+    assert list(inspect.signature(retrieval.sampling).parameters)[:6] == ["args", "logger", "model", "preprocess", "metrics", "dataset_root"]
+    for name in ("bank_bf16", "bank_f32"):
+        z, meta, cap, img, q = load_bank_case(name)
+        class_ids, labels, k = z["class_ids"], z["labels"], int(z["k"])
+        paths, _ = make_paths(labels, class_ids)
+        classes = [str(c) for c in sorted(class_ids.tolist())]
+        row_class = torch.from_numpy(labels.astype(np.int32))
+        S, I = so.score_matrix(cap, q), so.score_matrix(img, q)
+        own = lambda M: torch.from_numpy(M[np.arange(len(labels)), labels].astype(np.float32))
+        row = {p: i for i, p in enumerate(paths)}
+        for m, t2t_all, pred_all in (("t2t", own(S), None), ("t2t_t2i", own(S), own(I)), ("t2i", own(I), None)):
+            lines = retrieval._filtered_lines(classes, row_class, paths, t2t_all, pred_all, None, k, 0.0, 0.25, None)
+            got = [row[l.split(", ")[-2]] for l in lines]
+            ref = z[f"part_{m}_filtered_rows"].tolist()
+            assert len(got) == len(ref) == meta["diag"]["part"][m]["n_filtered"], (name, m)
+            assert sorted(got) == sorted(ref) and sum(a != b for a, b in zip(got, ref)) <= 4, (name, m)
+
+
+def test_unpartitioned_exclusion_runs_deeper_and_filters_on_the_host():
+    from swat_b200 import retrieval
+    sets = retrieval._exclusion_sets({"3": {"a", "b"}, 4: set()}, {"3": {"c"}, "5": {"d"}})
+    assert sets == {"3": {"a", "b", "c"}, "5": {"d"}}
+    bits, ex = retrieval._exclusion_bitmap(["p0", "a", "d", "c"], ["3", "5"], np.array([0, 0, 1, 1], np.int32), sets)
+    assert ex.tolist() == [False, True, True, False]          # "c" is excluded for class 3 only, the row belongs to class 5
+    assert int(bits[0]) == 0b0110
