@@ -269,6 +269,43 @@ def test_bank_swap_escalation(lib):
     qs.close(); ctx.close()
 
 
+def test_partitioned_escalation_mix(lib):
+    """Partitioned data (a row is eligible for its own class only) where the classes need DIFFERENT escalation paths in
+    one call: class 0 fills in the first pass, class 1 has ~50 T2I passers (bank-swap pass on a sub-query set with
+    renumbered row classes), class 2 has 6000 passers whose captions rank low (more than the swap pass can enumerate:
+    two-pass in-pass predicate), class 3 has none.  Round 1 spliced rows of the wrong class here (sub-query sets kept the
+    original row_class array)."""
+    n_per, C = 20_000, 4
+    lab = np.repeat(np.arange(C), n_per).astype(np.int32)
+    q = _rand_unit(C, 83, torch.bfloat16)
+    bank = _rand_unit(C * n_per, 81, torch.bfloat16)
+    img = _rand_unit(C * n_per, 82, torch.bfloat16)
+    unit = lambda x: torch.nn.functional.normalize(x.float(), dim=-1).to(torch.bfloat16)
+    img[0:n_per:2] = q[0]                                              # class 0: every second row passes, plenty in its T2T head
+    img[n_per:2 * n_per:400] = q[1]                                    # class 1: 50 passers
+    rows2 = torch.arange(2 * n_per, 3 * n_per, 3)[:6000]               # class 2: 6000 passers ...
+    img[rows2] = q[2]
+    bank[rows2] = unit(-0.05 * q[2].float()[None, :] + bank[rows2].float())  # ... whose captions rank BELOW most of the class: < 300 of them in its T2T top-4096
+    bf, imf, qf = bank.float().numpy(), img.float().numpy(), q.float().numpy()
+    o = so.topk_walk(bf, qf, 300, 0.0, t2i_bank=imf, t2i_threshold=0.25, row_labels=lab)
+    assert int(o[3][0]) == 300 and 0 < int(o[3][1]) < 300 and int(o[3][2]) == 300 and int(o[3][3]) == 0
+    rank2 = np.argsort(np.argsort(-so.score_matrix(bf[2 * n_per:3 * n_per], qf)[:, 2]))     # T2T rank inside class 2
+    assert rank2[o[0][2][299] - 2 * n_per] > 4096                       # its walk really ends beyond the widest over-fetch
+    S = so.score_matrix(bf, qf)
+    for swap in (1, 0):
+        ctx = lib.Context(0, swap_pass=swap)
+        qs = lib.Queries(ctx, q.float())
+        for rep in range(2):
+            g = lib.topk(ctx, qs, bank.cuda(), 300, 0.0, t2i_bank=img.cuda(), t2i_threshold=0.25, row_class=torch.from_numpy(lab).cuda())
+            check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=f"partitioned mix swap={swap} rep={rep}")
+            rows = g[1].cpu().numpy()
+            for c in range(C):
+                r = rows[c][rows[c] >= 0]
+                assert np.all(lab[r] == c), f"class {c} received rows of another class"
+        assert ctx.last_timing()["scan_launches"] >= 2
+        qs.close(); ctx.close()
+
+
 def test_host_pipeline_equals_resident(lib, ctx2):
     """Scores are canonical (one fixed-order fp32 dot per returned row), so the resident pipeline, the host pipeline
     with pinned banks (candidates' rows read in place over PCIe) and the host pipeline with pageable banks (host-side
