@@ -146,18 +146,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           tma_load_2d<kCtas>(smem_u32(sB + kc * b_chunk_bytes), &tm_q, q_bar_lead, kc * 64, qb * NB + static_cast<int>(rank) * NBC,
                              0x14F0000000000000ull /* evict_last: every CTA re-reads the query block */);
       }
-      // lockstep: before requesting tile `it`, wait (bounded) until every pair of the group has requested tile it - window
+      // lockstep: before requesting tile `it`, every pair of the group should have requested tile it - window.  The
+      // peers' progress words are fetched one check AHEAD (the load issued at tile it is consumed at tile it + 2), so the
+      // L2 round trip never sits in the producer's critical path -- a blocking read here cost 5-25 % of the scan; only a
+      // pair that really runs ahead of its group spins (bounded: the window is a hint, never a dependency).
       const bool lockstep = p.progress != nullptr && grp_size > 1 && rank == 0;
+      uint32_t peers_seen = 0xffffffffu;           // min over the group, as of the previous check
       auto keep_in_step = [&](uint32_t it) {
         if (!lockstep) return;
         if (lane == 0) st_relaxed_gpu_u32(p.progress + pair_id, it);
-        if (it < static_cast<uint32_t>(p.lock_window) || (it & 1u)) return;
-        const uint32_t need = it - static_cast<uint32_t>(p.lock_window);
-        for (int spin = 0; spin < 48; ++spin) {      // bounded (~5 us): the window is a hint, never a dependency
-          const uint32_t mine = lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu;
-          if (__reduce_min_sync(0xffffffffu, mine) >= need) break;
-          __nanosleep(100);
+        if (it & 1u) return;
+        if (it >= static_cast<uint32_t>(p.lock_window) + 2u) {
+          const uint32_t need = it - static_cast<uint32_t>(p.lock_window) - 2u;     // the snapshot is two tiles old
+          uint32_t seen = __reduce_min_sync(0xffffffffu, peers_seen);
+          for (int spin = 0; seen < need && spin < 48; ++spin) {
+            __nanosleep(100);
+            seen = __reduce_min_sync(0xffffffffu, lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu);
+          }
         }
+        peers_seen = lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu;   // for the next check
       };
       uint32_t tile_it = 0;
       if (F32) {
@@ -361,6 +368,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       const int first = kInterleave ? 32 * half : (half == 0 ? 0 : split);
       const int last = kInterleave ? NB : (half == 0 ? split : NB);
       constexpr int kStep = kInterleave ? 64 : 32;
+      // Grouped reduces on 4 epilogue warps (fp32 banks): one warp walks the whole block, and the zero-query padding
+      // columns the host inserts in front of `blk_split` (so that no class straddles it) would leak a 0 into the next
+      // class's max / min: restart the running reduce where the second half begins.
+      const int restart = (kEpiWarps == 4 && RED != RED_NONE) ? p.blk_split[qb] : -1;
       if (first < last) {
         tmem_ld32_issue(taddr + first, ra);
         tmem_wait(ra);
@@ -368,6 +379,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           const bool has_b = c0 + kStep < last, has_next = c0 + 2 * kStep < last;
           if (has_b) tmem_ld32_issue(taddr + c0 + kStep, rb); else release_tmem();
           to_f32x32(ra, v);
+          if (c0 == restart) cx.acc = red_init<RED>();
           if (NB - c0 == 16) {   // trailing half chunk: columns the MMA never wrote must not look like scores
 #pragma unroll
             for (int j = 16; j < 32; ++j) v[j] = 0.0f;
@@ -377,6 +389,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
             tmem_wait(rb);
             if (has_next) tmem_ld32_issue(taddr + c0 + 2 * kStep, ra); else release_tmem();
             to_f32x32(rb, v);
+            if (c0 + kStep == restart) cx.acc = red_init<RED>();
             if (NB - (c0 + kStep) == 16) {
 #pragma unroll
               for (int j = 16; j < 32; ++j) v[j] = 0.0f;

@@ -42,8 +42,9 @@ def _bank(n, class_vecs, seed, rho=0.3):
 
 
 # no shrinking: a failing draw is reported as drawn (its parameters are in the assertion message); GPU minutes are scarce
-@settings(max_examples=30, deadline=None, database=None, phases=[Phase.explicit, Phase.generate],
+@settings(max_examples=40, deadline=None, database=None, derandomize=True, phases=[Phase.explicit, Phase.generate],
           suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@hypothesis.example(n=13839, C=24, reduce="min", k=2, thr=0.0, t2i=0.1, excl=0.0, part=False, f32=True, seed=2861)   # padding columns leaked into a min (fp32 banks)
 @given(n=st.integers(1, 20_000), C=st.integers(1, 40), reduce=st.sampled_from(["none", "mean", "max", "min"]),
        k=st.integers(1, 300), thr=st.sampled_from([-1.0, 0.0, 0.05]), t2i=st.sampled_from([None, 0.0, 0.1, 0.25]),
        excl=st.sampled_from([0.0, 0.3, 1.0]), part=st.booleans(), f32=st.booleans(), seed=st.integers(0, 10_000))
