@@ -116,7 +116,7 @@ struct swat_ctx {
   DevBuf w_scores, w_rows, w_counts, w_trunc, w_exact, w_aux, w_incomplete, w_keys, w_stage[3], w_rc[3], w_ex[3], w_img, w_idx;
   DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
   DevBuf w_swap[10];                // bank-swap escalation pass: two re-score stages
-  int lock_window = 4;              // several Q blocks: pairs sharing a tile range stay within this many tiles of each other (0 = off)
+  int lock_window = 0;              // several Q blocks: pairs sharing a tile range stay within this many tiles of each other (0 = off, the default: see DESIGN.md 3.1)
   DevBuf w_progress, w_bits, w_splice;
   int f32_op_stages = 3;            // fp32 banks: bf16 operand stages (the rest of the shared memory stages fp32 boxes); before swat_queries_create
   bool zero_copy = true;            // host pipeline: read candidates' rows from pinned host banks in place
