@@ -21,7 +21,8 @@ One step = one pass of the whole pipeline (scan + select + T2I walk [+ gather + 
            scan-kernel ms, rows/s and both roofline fractions): at every N the config-4 shape (imagenet C = Q = 1000,
            T2T top-500, 50 M rows per GPU, NCCL merge), the strong-scaling point of config 5 (100 M rows split over
            the N GPUs, Q = 200) and `cold_call_ms` (first call on a fresh context, allocation and escalation included);
-           at N = 1 also the query-count sweep Q in {64, 200, 400, 1000} over 50 M rows and config 1 (fp32 banks).
+           at N = 1 also the query-count sweep Q in {64, 200, 400, 1000} over 50 M rows, the nine-dataset sweep of config 3
+           over the same bank (class-mean prompts and synonym groups with MAX) and config 1 (fp32 banks).
 """
 import argparse
 import json
@@ -313,6 +314,35 @@ def run_extras(a, rank, world, dev, main):
     qc, q1000, _ = synth.make_queries(1000, 1, seed=a.seed + 1, dtype=torch.bfloat16)
     capx, _, _ = synth.make_bank(n_x, qc, seed=a.seed + 1, device=dev, dtype=torch.bfloat16, chunk=1 << 20, with_images=False,
                                  row_offset=rank * n_x)
+    if world == 1:
+        # ---- config 3: the nine datasets of the paper over this one bank, class-mean prompts (Q = C) and synonym groups
+        # with a per-class MAX (Q = S); (C, S) from SURVEY.md 8a
+        out["cfg3_sweep9"] = []
+        for name, C3, S3 in (("flowers102", 102, 343), ("fgvc-aircraft", 100, 271), ("eurosat", 10, 51), ("dtd", 47, 75), ("food101", 101, 413),
+                             ("oxford_pets", 37, 114), ("stanford_cars", 196, 1221), ("semi-aves", 200, 400), ("imagenet", 1000, 5191)):
+            for mode in ("class-mean", "synonyms-max"):
+                if mode == "class-mean":
+                    qs = _lib.Queries(ctx, qc[:C3].float())
+                    Q3 = C3
+                else:
+                    sizes = [1] * C3                                  # S3 synonyms over C3 classes, deterministic and uneven
+                    left, i = S3 - C3, 0
+                    while left > 0:
+                        add = min(left, 1 + (i * 7) % max(1, 2 * (S3 // C3)))
+                        sizes[(i * 37) % C3] += add
+                        left -= add
+                        i += 1
+                    g = torch.Generator().manual_seed(C3 * 1000 + S3)
+                    coq = torch.repeat_interleave(torch.arange(C3, dtype=torch.int32), torch.tensor(sizes))
+                    u = torch.nn.functional.normalize(torch.randn(coq.numel(), 512, generator=g), dim=-1)
+                    q3 = torch.nn.functional.normalize(qc[:C3][coq.long()].float() + 0.3 * u, dim=-1).to(torch.bfloat16).float()
+                    qs = _lib.Queries(ctx, q3, coq, C3, "max")
+                    Q3 = S3
+                e = timed(ctx, t2t_step(ctx, qs, capx, 0), n_x, Q3, 1024.0, warm=1, reps=2)
+                e.pop("clocks", None)
+                e["workload"] = f"{name}: C = {C3}, Q = {Q3} ({mode}), T2T top-{a.k}, {n_x} x 512 bf16 rows"
+                out["cfg3_sweep9"].append(e)
+                qs.close()
     sweep = (64, 200, 400, 1000) if world == 1 else (1000,)
     out["cfg5_qsweep"] = []
     for Q in sweep:

@@ -21,7 +21,7 @@ d=json.loads(open("gpurun_out/${TAG}_bench.json").read().strip().split("\n")[-1]
 print("ms/step", d["ms_per_step"], "value", d["value"], "roof", d["roofline"]["frac"], "step_frac", d["stats"]["step_frac_of_roofline"], "e2e", d["e2e"]["value"], "launches", d["gpu_launches"])
 c=d["configs"]
 print("cold", c["cold_call_ms"], c.get("cold_call_breakdown_ms")); print("e2e", d["e2e"].get("ms_per_step"), d["e2e"].get("last_step_device_ms"))
-for e in c["cfg5_qsweep"]+[c["cfg5_strong_scaling"]]+c.get("cfg1_fp32",[]):
+for e in c.get("cfg3_sweep9",[])+c["cfg5_qsweep"]+[c["cfg5_strong_scaling"]]+c.get("cfg1_fp32",[]):
     print(e["workload"][:70], "| ms", round(e["ms_per_step"],3), "kern", e["scan_kernel_ms"] and round(e["scan_kernel_ms"],3), "step_frac", round(e["roofline"]["step_frac"],3), "kern_frac", e["roofline"]["kernel_frac"] and round(e["roofline"]["kernel_frac"],3), e.get("escalations_per_step"))
 PY
 tail -14 gpurun_out/${TAG}_probe.log
