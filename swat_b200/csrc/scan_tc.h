@@ -70,6 +70,8 @@ struct WalkArgs {
   float* out_scores; int64_t* out_rows; float* out_aux; int32_t* out_counts;   // [C,k] / [C]
   float* out_limit;             // nullable [C]: -inf = proven exact, else rows scoring <= limit may be missing
   int32_t* incomplete;          // nullable [C]: 1 = fewer than k accepted and the list cannot vouch for that
+  int32_t* eps_violation;       // nullable [1]: set when some candidate's exact score is further than eps from the score
+                                // the scan ranked it by -- the error bound does not hold (rows not L2-normalised?)
 };
 cudaError_t launch_rescore_walk(const WalkArgs& a, cudaStream_t stream);
 constexpr int kWalkLaunches = 2;

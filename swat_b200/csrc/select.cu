@@ -444,6 +444,8 @@ __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
     if (lane == 0) {
       a.exact_scratch[base + j0 + i] = t2t;
       if (a.aux_bank) a.aux_scratch[base + j0 + i] = ax;
+      // the frontier proof rests on |approximate - exact| <= eps: check it on every row we look at anyway
+      if (a.eps_violation && !a.all_or_nothing && r[i] >= 0 && fabsf(t2t - a.cand_scores[base + j0 + i]) > a.eps) *a.eps_violation = 1;
     }
   }
 }

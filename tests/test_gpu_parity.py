@@ -450,6 +450,13 @@ def test_bad_arguments_raise(lib, ctx2):
         lib.topk(ctx2, qs, _rand_unit(64, 2).cuda(), 100000)                   # k beyond the supported maximum
     with pytest.raises((ValueError, TypeError)):
         lib.topk(ctx2, qs, torch.zeros(64, 256).cuda(), 10)
+    # fp32 banks are scanned as bf16-rounded rows under an error bound that assumes L2-normalised rows: un-normalised
+    # features must fail loudly (the re-score checks the bound on every candidate), never return unproven rows
+    big = (_rand_unit(4096, 5) * 40.0).cuda()
+    with pytest.raises(lib.SwatError, match="L2-normalised"):
+        lib.topk(ctx2, qs, big, 10)
+    ok = lib.topk(ctx2, qs, _rand_unit(4096, 5).cuda(), 10)
+    assert int(ok[3].min()) == 10
 
 
 @pytest.mark.parametrize("reduce", ["none", "max"])
