@@ -594,7 +594,8 @@ struct CandLists {
 int32_t walk_candidates(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, bool use_aux, int64_t row_offset, const CandLists& cl,
                         int32_t k, float thr, float aux_thr, float eps, bool all_or_nothing, float* o_scores, int64_t* o_rows,
                         float* o_aux, int32_t* o_counts, float* o_limit, int32_t* o_incomplete, cudaStream_t stream,
-                        const swat_queries* q_aux = nullptr, int32_t* d_eps_violation = nullptr) {
+                        const swat_queries* q_aux = nullptr, int32_t* d_eps_violation = nullptr, int32_t* d_status = nullptr,
+                        const uint32_t* d_job_flags = nullptr) {
   const int C = q->C;
   const size_t n_slots = static_cast<size_t>(C) * cl.stride;
   SW_OK(ctx->w_exact.ensure(n_slots * 4));
@@ -615,6 +616,7 @@ int32_t walk_candidates(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, 
   w.exact_scratch = ctx->w_exact.as<float>(); w.aux_scratch = ctx->w_aux.as<float>();
   w.out_scores = o_scores; w.out_rows = o_rows; w.out_aux = o_aux; w.out_counts = o_counts; w.out_limit = o_limit; w.incomplete = o_incomplete;
   w.eps_violation = d_eps_violation;
+  w.status = d_status; w.job_flags = d_job_flags;
   w.key_row_base = row_offset;
   const bool mapped = b.host && b.t2t_mapped && (!use_aux || b.t2i_mapped);
   if (!b.host || mapped) {
@@ -947,12 +949,16 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     SW_OK(ctx->w_rows.ensure(static_cast<size_t>(C) * kf * 8));
     SW_OK(ctx->w_counts.ensure(static_cast<size_t>(C) * 4));
     SW_OK(ctx->w_trunc.ensure(static_cast<size_t>(C) * 4));
-    SW_OK(ctx->w_incomplete.ensure((static_cast<size_t>(C) + 1) * 4));
-    int32_t* d_violation = ctx->w_incomplete.as<int32_t>() + C;      // [C] incomplete flags + 1 word: error bound violated
-    CU_OK(cudaMemsetAsync(d_violation, 0, 4, stream));
+    // everything the host reads back after the step, one block (WalkArgs::status): [0] overflow word, [1..C] incomplete
+    // flags, [1+C..2C] accepted counts, [1+2C] error bound violated (cleared by the select)
+    SW_OK(ctx->w_incomplete.ensure((2 * static_cast<size_t>(C) + 2) * 4));
+    int32_t* d_status = ctx->w_incomplete.as<int32_t>();
+    int32_t* d_violation = d_status + 1 + 2 * C;
     // resident banks: rows leave the select as global ids (row_offset + shard-local row)
+    // without a predicate the walk needs the k best rows only: candidates more than 2 eps below the k-th approximate
+    // score cannot be among them and are not re-scored (select_kernel)
     CU_OK(launch_select(job->st, C, row_offset, ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(),
-                        ctx->w_trunc.as<int32_t>(), stream));
+                        ctx->w_trunc.as<int32_t>(), stream, want_t2i ? 0u : static_cast<uint32_t>(k), 2.0f * eps + 1.0e-6f, d_violation));
     job->last_stream = stream;
     ctx->launches += kSelectLaunches;
     CU_OK(cudaEventRecord(ctx->ev[2], stream));
@@ -983,14 +989,10 @@ int32_t run_pipeline(swat_ctx* ctx, const swat_queries* q, const BankSrc& b, int
     CU_OK(cudaEventRecord(ctx->ev[3], stream));
     CandLists cl{ctx->w_scores.as<float>(), ctx->w_rows.as<int64_t>(), ctx->w_counts.as<int32_t>(), ctx->w_trunc.as<int32_t>(), kf};
     SW_OK(walk_candidates(ctx, q, b, want_t2i, row_offset, cl, k, thr, t2i_thr, eps, false, d_out_scores, d_out_rows, d_out_t2i,
-                          d_out_counts, nullptr, ctx->w_incomplete.as<int32_t>(), stream, nullptr, d_violation));
+                          d_out_counts, nullptr, nullptr, stream, nullptr, d_violation, d_status, job->st.flags));
     CU_OK(cudaEventRecord(ctx->ev[4], stream));
     SW_OK(ensure_status(ctx, 2 * static_cast<size_t>(C) + 2));
-    ctx->h_status[0] = 0;
-    if (late_check) CU_OK(cudaMemcpyAsync(ctx->h_status, job->st.flags, 4, cudaMemcpyDeviceToHost, stream));
-    CU_OK(cudaMemcpyAsync(ctx->h_status + 1, ctx->w_incomplete.p, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
-    CU_OK(cudaMemcpyAsync(ctx->h_status + 1 + C, d_out_counts, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToHost, stream));
-    CU_OK(cudaMemcpyAsync(ctx->h_status + 1 + 2 * C, d_violation, 4, cudaMemcpyDeviceToHost, stream));
+    CU_OK(cudaMemcpyAsync(ctx->h_status, d_status, (2 * static_cast<size_t>(C) + 2) * 4, cudaMemcpyDeviceToHost, stream));
     CU_OK(cudaStreamSynchronize(stream));
     if (ctx->h_status[1 + 2 * C] != 0)
       return fail(SWAT_ERR_INVALID, "a candidate's exact score differs from the score the scan ranked it by by more than the error bound "

@@ -38,8 +38,11 @@ cudaError_t launch_scan_simt(const ScanArgs& a, const void* bank, const void* ba
 // final per-class select of the k_fetch best candidates
 // final per-class select: final thresholds from the histograms, partition of the survivor lists by
 // class, radix-select + sort of the k_fetch best candidates (3 launches)
+// band_k > 0: cut every list behind the first candidate scoring below (band_k-th best score - band); see select_kernel
+// zero_word (nullable): one int32 the select clears on the way (the walk's eps_violation word)
 cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
-                          int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream);
+                          int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream, uint32_t band_k = 0, float band = 0.0f,
+                          int32_t* zero_word = nullptr);
 constexpr int kSelectLaunches = 3;
 
 // Exact re-score + accept walk over per-class candidate lists (select.cu).
@@ -72,6 +75,9 @@ struct WalkArgs {
   int32_t* incomplete;          // nullable [C]: 1 = fewer than k accepted and the list cannot vouch for that
   int32_t* eps_violation;       // nullable [1]: set when some candidate's exact score is further than eps from the score
                                 // the scan ranked it by -- the error bound does not hold (rows not L2-normalised?)
+  // nullable [2C+2]: everything the host reads back after a step, in one block: [0] the job's overflow word
+  // (*job_flags), [1..C] incomplete flags, [1+C..2C] accepted counts ([1+2C] is the eps_violation word)
+  int32_t* status; const uint32_t* job_flags;
 };
 cudaError_t launch_rescore_walk(const WalkArgs& a, cudaStream_t stream);
 constexpr int kWalkLaunches = 2;

@@ -36,6 +36,98 @@ struct FloorKeys {
   }
 };
 
+// Descending bitonic sort of s_keys[0..P) by the whole block (P a power of two <= kSortCap; optional 16-bit payload
+// moved with the keys).  Called after a __syncthreads(); ends with one.  A thread owns E = P / 1024 consecutive
+// positions: every compare-exchange at distance j < 32 E stays inside a warp (registers and xor-shuffles, no barrier),
+// only the steps at distance >= 32 E go through shared memory with a block barrier each -- 20 barriers instead of 55
+// at P = 1024, 27 instead of 78 at P = 4096.
+template <int E, bool IDX>
+__device__ __forceinline__ void sort_warp_steps(uint64_t (&x)[E], uint32_t (&xi)[E], uint32_t pos0, uint32_t k, uint32_t j_from) {
+  for (uint32_t j = j_from; j >= static_cast<uint32_t>(E); j >>= 1) {       // partner = same slot of lane ^ (j / E)
+    const int lane_mask = static_cast<int>(j / E);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint32_t i = pos0 + e;
+      const uint64_t y = __shfl_xor_sync(0xffffffffu, x[e], lane_mask);
+      const uint32_t yi = IDX ? __shfl_xor_sync(0xffffffffu, xi[e], lane_mask) : 0u;
+      const bool keep_max = ((i & j) == 0) == ((i & k) == 0);                 // lower position of a descending pair, or upper of an ascending one
+      const bool take = keep_max ? (y > x[e]) : (y < x[e]);
+      if (take) { x[e] = y; xi[e] = yi; }
+    }
+  }
+#pragma unroll
+  for (int jj = E / 2; jj > 0; jj >>= 1) {                                    // partner inside the thread
+    if (j_from >= static_cast<uint32_t>(jj)) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & jj) == 0) {
+          const bool desc = ((pos0 + e) & k) == 0;
+          if ((x[e] < x[e | jj]) == desc) {
+            const uint64_t t = x[e]; x[e] = x[e | jj]; x[e | jj] = t;
+            const uint32_t ti = xi[e]; xi[e] = xi[e | jj]; xi[e | jj] = ti;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int E, bool IDX>
+__device__ void block_sort_desc_e(uint64_t* s_keys, uint16_t* s_idx, uint32_t P) {
+  const uint32_t tid = threadIdx.x, pos0 = tid * E;
+  const bool active = pos0 < P;
+  constexpr uint32_t W = 32u * E;               // positions per warp
+  uint64_t x[E];
+  uint32_t xi[E];
+  auto load = [&]() {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      x[e] = active ? s_keys[pos0 + e] : 0ull;
+      xi[e] = (IDX && active) ? s_idx[pos0 + e] : 0u;
+    }
+  };
+  auto store = [&]() {
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        s_keys[pos0 + e] = x[e];
+        if (IDX) s_idx[pos0 + e] = static_cast<uint16_t>(xi[e]);
+      }
+    }
+  };
+  load();
+  for (uint32_t k = 2; k <= min(W, P); k <<= 1) sort_warp_steps<E, IDX>(x, xi, pos0, k, k >> 1);
+  store();
+  __syncthreads();
+  for (uint32_t k = 2 * W; k <= P; k <<= 1) {
+    for (uint32_t j = k >> 1; j >= W; j >>= 1) {
+      for (uint32_t i = tid; i < P; i += kSelThreads) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = s_keys[i], b = s_keys[ixj];
+          const bool desc = (i & k) == 0;
+          if ((a < b) == desc) {
+            s_keys[i] = b; s_keys[ixj] = a;
+            if (IDX) { const uint16_t t = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = t; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    load();
+    sort_warp_steps<E, IDX>(x, xi, pos0, k, W >> 1);
+    store();
+    __syncthreads();
+  }
+}
+
+template <bool IDX>
+__device__ void block_sort_desc(uint64_t* s_keys, uint16_t* s_idx, uint32_t P) {
+  if (P >= 4u * kSelThreads) block_sort_desc_e<4, IDX>(s_keys, s_idx, P);
+  else if (P >= 2u * kSelThreads) block_sort_desc_e<2, IDX>(s_keys, s_idx, P);
+  else block_sort_desc_e<1, IDX>(s_keys, s_idx, P);
+}
+
 template <typename KeyFn>
 __device__ uint32_t select_sorted(const KeyFn keys, uint32_t n, uint32_t n_valid, uint32_t K, uint64_t* s_keys,
                                   uint32_t* s_hist, uint32_t* s_misc) {
@@ -93,25 +185,18 @@ __device__ uint32_t select_sorted(const KeyFn keys, uint32_t n, uint32_t n_valid
   while (P < total) P <<= 1;
   for (uint32_t i = total + tid; i < P; i += kSelThreads) s_keys[i] = 0ull;   // real keys are never 0
   __syncthreads();
-  for (uint32_t k = 2; k <= P; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < P; i += kSelThreads) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = s_keys[i], y = s_keys[ixj];
-          const bool desc = (i & k) == 0;
-          if ((x < y) == desc) { s_keys[i] = y; s_keys[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
+  block_sort_desc<false>(s_keys, nullptr, P);
   return total;
 }
 
+// band_k > 0 (walks without a predicate): the k-th best APPROXIMATE score a_k bounds what the walk can use.  The k best
+// approximate rows score at least a_k - eps exactly, so a row ranked below a_k - 2 eps (= `band`, plus a rounding margin)
+// can never be among the k best exact rows: the list is cut behind the first such candidate, which stays as the
+// frontier marker (frontier = its score + eps < a_k - eps, so every possible top-k row is still vouched for).  The
+// re-score then reads k + (rows within the band) rows per class instead of the whole over-fetch.
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
-              int32_t* __restrict__ out_counts, int32_t* __restrict__ out_trunc) {
+              int32_t* __restrict__ out_counts, int32_t* __restrict__ out_trunc, uint32_t band_k, float band, int32_t* zero_word) {
   __shared__ uint64_t s_keys[kSortCap];
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_misc[4];
@@ -121,7 +206,17 @@ select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_sco
   const uint32_t K = class_k(st, c);          // this class's depth
   const uint32_t stride = st.k_fetch;         // output row pitch = the deepest class
   const uint32_t total = select_sorted(GlobalKeys{st.cand + static_cast<size_t>(c) * st.cap}, n, n, K, s_keys, s_hist, s_misc);
-  const uint32_t cnt = min(K, total);
+  uint32_t cnt = min(K, total);
+  bool cut = false;
+  if (band_k > 0 && cnt > band_k) {
+    const float floor_score = key_score(s_keys[band_k - 1]) - band;
+    uint32_t lo = band_k, hi = cnt;           // first position whose score is below the band (scores descend)
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (key_score(s_keys[mid]) >= floor_score) lo = mid + 1; else hi = mid;
+    }
+    if (lo + 1 < cnt) { cnt = lo + 1; cut = true; }
+  }
   for (uint32_t i = threadIdx.x; i < stride; i += kSelThreads) {
     const bool ok = i < cnt;
     const uint64_t key = ok ? s_keys[i] : 0ull;
@@ -129,10 +224,11 @@ select_kernel(const JobState st, int64_t row_offset, float* __restrict__ out_sco
     out_rows[static_cast<size_t>(c) * stride + i] = ok ? static_cast<int64_t>(key_row(key)) + row_offset : -1;
   }
   if (threadIdx.x == 0) {
+    if (zero_word && c == 0) *zero_word = 0;
     out_counts[c] = static_cast<int32_t>(cnt);
     // more eligible rows than k_fetch exist iff more than k_fetch candidates survived, or the
     // threshold ever rose above the user threshold (rows below it were dropped)
-    if (out_trunc) out_trunc[c] = (appended > K || st.tau_enc[c] > f32_enc(st.thr)) ? 1 : 0;
+    if (out_trunc) out_trunc[c] = (cut || appended > K || st.tau_enc[c] > f32_enc(st.thr)) ? 1 : 0;
   }
 }
 
@@ -365,8 +461,10 @@ template <> struct Raw16<__nv_bfloat16> {
 };
 
 // Exact scores of the candidates: one warp per NC consecutive candidates of a class.  All of their rows (ranking bank
-// and, with a predicate bank, the aux rows) are requested before any is consumed -- the kernel is bound by the latency
-// of those scattered 1-2 KB reads, not by bandwidth.
+// and, with a predicate bank, the aux rows) are requested before any is consumed.  The kernel moves 2.6-3.2 TB/s of
+// scattered 1-2 KB rows, which is what HBM gives this access pattern: staging the rows through shared memory
+// (cp.async.bulk per row, then 16-byte cp.async, 96 KB in flight per CTA, ids and class tables prefetched a chunk
+// ahead) was measured SLOWER on the B200 (193-294 us against 129 us for 200 x 1024 candidates of both banks).
 template <typename T, int NC>
 __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
   const int lane = threadIdx.x & 31;
@@ -477,22 +575,7 @@ __global__ void __launch_bounds__(kSelThreads) walk_kernel(const WalkArgs a) {
     s_idx[i] = static_cast<uint16_t>(i);
   }
   __syncthreads();
-  for (uint32_t kk = 2; kk <= P; kk <<= 1) {
-    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < P; i += kSelThreads) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = s_keys[i], y = s_keys[ixj];
-          const bool desc = (i & kk) == 0;
-          if ((x < y) == desc) {
-            s_keys[i] = y; s_keys[ixj] = x;
-            const uint16_t t = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = t;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
+  block_sort_desc<true>(s_keys, s_idx, P);
   constexpr int kPer = kSortCap / kSelThreads;   // 4 consecutive sorted positions per thread
   bool pass[kPer];
   uint32_t mine = 0;
@@ -557,6 +640,11 @@ __global__ void __launch_bounds__(kSelThreads) walk_kernel(const WalkArgs a) {
     const bool complete = !trunc || total >= static_cast<uint32_t>(a.k);
     if (a.out_limit) a.out_limit[c] = complete ? -INFINITY : frontier;
     if (a.incomplete) a.incomplete[c] = complete ? 0 : 1;
+    if (a.status) {
+      a.status[1 + c] = complete ? 0 : 1;
+      a.status[1 + a.n_classes + c] = static_cast<int32_t>(cnt);
+      if (c == 0) a.status[0] = a.job_flags ? static_cast<int32_t>(*a.job_flags) : 0;
+    }
   }
 }
 
@@ -743,7 +831,7 @@ cudaError_t launch_near_dup(const void* bank, int dtype, const int64_t* d_order,
 }
 
 cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset, float* d_scores, int64_t* d_rows,
-                          int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream) {
+                          int32_t* d_counts, int32_t* d_truncated, cudaStream_t stream, uint32_t band_k, float band, int32_t* zero_word) {
   if (n_classes <= 0) return cudaSuccess;
   final_tau_kernel<<<(n_classes + 7) / 8, 256, 0, stream>>>(st, n_classes);
   cudaError_t e = cudaGetLastError();
@@ -765,7 +853,7 @@ cudaError_t launch_select(const JobState& st, int n_classes, int64_t row_offset,
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated);
+  select_kernel<<<n_classes, kSelThreads, 0, stream>>>(st, row_offset, d_scores, d_rows, d_counts, d_truncated, d_truncated ? band_k : 0u, band, zero_word);
   return cudaGetLastError();
 }
 
