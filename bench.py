@@ -428,9 +428,14 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # the caller owns the result tensors: one set, reused by every step (what a loop over shards does)
+    out = (torch.empty(a.classes, k, dtype=torch.float32, device=dev), torch.empty(a.classes, k, dtype=torch.int64, device=dev),
+           None if img is None else torch.empty(a.classes, k, dtype=torch.float32, device=dev),
+           torch.empty(a.classes, dtype=torch.int32, device=dev))
+
     def step():
         if world == 1:
-            return _lib.topk(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset)
+            return _lib.topk(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset, out=out)
         return sdist.topk_sharded(ctx, qs, cap, k, 0.0, t2i_bank=img, t2i_threshold=0.25, row_offset=row_offset, world=world)
 
     for _ in range(max(a.warmup, 3)):

@@ -117,7 +117,8 @@ struct swat_ctx {
   DevBuf w_out_scores, w_out_rows, w_out_t2i, w_out_counts, w_boot;
   DevBuf w_swap[10];                // bank-swap escalation pass: two re-score stages
   int lock_window = 0;              // several Q blocks: pairs sharing a tile range stay within this many tiles of each other (0 = off, the default: see DESIGN.md 3.1)
-  DevBuf w_progress, w_bits, w_splice;
+  DevBuf w_progress, w_bits, w_splice, w_tiles;
+  bool dyn_tiles = true;            // one Q block: dynamic tile scheduling (pairs finish 3-5 % apart under a static split)
   int f32_op_stages = 3;            // fp32 banks: bf16 operand stages (the rest of the shared memory stages fp32 boxes); before swat_queries_create
   bool zero_copy = true;            // host pipeline: read candidates' rows from pinned host banks in place
   bool swap_pass = true;            // classes with fewer than k rows passing T2I: enumerate the passers from the image bank
@@ -353,6 +354,13 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
       }
     }
     if (p.n_ranges == 0 && q->n_qb > pairs) launches = (q->n_qb + pairs - 1) / pairs;   // legacy plan: `pairs` Q blocks per launch
+    // one Q block: pairs take tiles from a global counter instead of a fixed stride (TcArgs::tile_sched)
+    if (ctx->dyn_tiles && !dense && q->n_qb == 1 && p.n_ranges == 0 && launches == 1 && tiles > 4ll * pairs) {
+      const size_t bytes = (2 + static_cast<size_t>(pairs) * kTileRing) * 8;
+      SW_OK(ctx->w_tiles.ensure(bytes));
+      CU_OK(cudaMemsetAsync(ctx->w_tiles.p, 0, bytes, stream));
+      p.tile_sched = ctx->w_tiles.as<unsigned long long>();
+    }
     const bool lockstep = ctx->lock_window > 0 && q->n_qb > 1 && !dense;
     if (lockstep) {
       SW_OK(ctx->w_progress.ensure(static_cast<size_t>(launches) * pairs * 4));
@@ -367,7 +375,33 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
         p.qb_base = i * pairs;
         p.qb_count = std::min(pairs, q->n_qb - p.qb_base);
       }
+      static const bool tracing = getenv("SWAT_SCAN_TRACE") != nullptr;
+      static unsigned long long* d_trace = nullptr;
+      if (tracing) {
+        if (!d_trace) CU_OK(cudaMalloc(&d_trace, 1024 * 8 * 8));
+        CU_OK(cudaMemsetAsync(d_trace, 0, 1024 * 8 * 8, stream));
+        p.trace = d_trace;
+      }
+      cudaEvent_t t0 = nullptr, t1 = nullptr;
+      if (tracing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, stream); }
       CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense, f32, grid, stream));
+      if (tracing) {
+        cudaEventRecord(t1, stream);
+        std::vector<unsigned long long> h(static_cast<size_t>(grid) * 8);
+        CU_OK(cudaMemcpyAsync(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost, stream));
+        CU_OK(cudaStreamSynchronize(stream));
+        float ms = 0; cudaEventElapsedTime(&ms, t0, t1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+        unsigned long long first = ~0ull, last = 0;
+        for (int b = 0; b < grid; ++b) { first = std::min(first, h[b * 8]); last = std::max(last, h[b * 8 + 7]); }
+        double mx[8] = {0}, mn[8];
+        for (int i = 0; i < 8; ++i) mn[i] = 1e30;
+        for (int b = 0; b < grid; ++b)
+          for (int i = 0; i < 8; ++i) if (h[b * 8 + i]) { const double v = (h[b * 8 + i] - first) * 1e-3; mx[i] = std::max(mx[i], v); mn[i] = std::min(mn[i], v); }
+        fprintf(stderr, "[swat trace] scan rows=%lld event %.1f us, first entry -> last exit %.1f us | us since first entry (min/max over CTAs): "
+                        "entry %.1f/%.1f prologue %.1f/%.1f queries %.1f/%.1f mma1 %.1f/%.1f mmaN %.1f/%.1f epi1 %.1f/%.1f epiN %.1f/%.1f exit %.1f/%.1f\n",
+                (long long)a.n_rows, ms * 1e3, (last - first) * 1e-3, mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3], mn[4], mx[4], mn[5], mx[5],
+                mn[6], mx[6], mn[7], mx[7]);
+      }
     }
     ctx->launches += launches - 1;
   } else {
@@ -1149,7 +1183,7 @@ int32_t swat_ctx_destroy(swat_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->w_scores, &ctx->w_rows, &ctx->w_counts, &ctx->w_trunc, &ctx->w_exact, &ctx->w_aux, &ctx->w_incomplete, &ctx->w_keys,
                     &ctx->w_stage[0], &ctx->w_stage[1], &ctx->w_stage[2], &ctx->w_rc[0], &ctx->w_rc[1], &ctx->w_rc[2],
                     &ctx->w_ex[0], &ctx->w_ex[1], &ctx->w_ex[2], &ctx->w_img, &ctx->w_idx,
-                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot, &ctx->w_progress, &ctx->w_bits, &ctx->w_splice,
+                    &ctx->w_out_scores, &ctx->w_out_rows, &ctx->w_out_t2i, &ctx->w_out_counts, &ctx->w_boot, &ctx->w_progress, &ctx->w_bits, &ctx->w_splice, &ctx->w_tiles,
                     &ctx->w_swap[0], &ctx->w_swap[1], &ctx->w_swap[2], &ctx->w_swap[3], &ctx->w_swap[4], &ctx->w_swap[5], &ctx->w_swap[6],
                     &ctx->w_swap[7], &ctx->w_swap[8], &ctx->w_swap[9]};
   for (DevBuf* b : bufs) b->release();
@@ -1181,6 +1215,7 @@ int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value) {
   else if (n == "zero_copy") ctx->zero_copy = value != 0;
   else if (n == "f32_op_stages") { if (value < 2 || value > 4) return fail(SWAT_ERR_INVALID, "f32_op_stages must be 2..4"); ctx->f32_op_stages = static_cast<int>(value); }
   else if (n == "lock_window") ctx->lock_window = static_cast<int>(std::max<int64_t>(0, value));
+  else if (n == "dyn_tiles") ctx->dyn_tiles = value != 0;
   else if (n == "bootstrap_rows") ctx->bootstrap_rows = std::max<int64_t>(0, value);
   else return fail(SWAT_ERR_INVALID, "unknown option '%s'", name);
   return SWAT_OK;

@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constant__ CUtensorMap tm_q, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned long long* trace = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();                      // CTA entry
 
   constexpr int kEpiWarps = F32 ? 4 : 8;   // bf16: two per TMEM lane quadrant on interleaved 32-column chunks
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,6 +60,31 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   constexpr int kTileRows = 128 * kCtas;
   const int64_t n_tiles = (p.s.n_rows + kTileRows - 1) / kTileRows;
   const int64_t t_first = (pair_in_qb < pairs_qb) ? pair_in_qb : n_tiles;
+  // Tile of this pair's iteration `it` (n_tiles = no more).  Static plan: t_first + it * pairs_qb.  Dynamic plan
+  // (p.tile_sched; one Q block): the pairs finish 3-5 % apart under a static split (SM position, survivor bursts), so
+  // after its first tile a pair takes the next unclaimed tile from a global counter.  The leader CTA's producer claims
+  // three iterations ahead and publishes (iteration, tile) in a small ring in global memory; every other warp of the
+  // pair peeks at the entry of iteration it + 1 while it works on iteration it, so nobody waits on the L2 round trip.
+  const bool dyn = !DENSE && p.tile_sched != nullptr;
+  unsigned long long* tile_ring = dyn ? p.tile_sched + 2 + static_cast<size_t>(pair_id) * kTileRing : nullptr;
+  auto tile_peek = [&](uint32_t it) -> unsigned long long {
+    return (dyn && it > 0) ? ld_relaxed_gpu_u64(tile_ring + (it & (kTileRing - 1))) : 0ull;
+  };
+  auto tile_get = [&](uint32_t it, unsigned long long peeked) -> int64_t {      // warp-uniform
+    if (!dyn) {
+      const int64_t t = t_first + static_cast<int64_t>(it) * pairs_qb;
+      return t < n_tiles ? t : n_tiles;
+    }
+    if (it == 0) return t_first;
+    uint32_t spins = 0;
+    while (static_cast<uint32_t>(peeked >> 32) != it + 1u) {
+      if (++spins > 40000000u) __trap();            // a hang becomes a launch failure
+      __nanosleep(40);
+      peeked = ld_relaxed_gpu_u64(tile_ring + (it & (kTileRing - 1)));
+    }
+    const int64_t t = static_cast<int64_t>(static_cast<uint32_t>(peeked));
+    return t < n_tiles ? t : n_tiles;
+  };
   // CTAs serving this Q block in this launch (the refresher warps split the block's classes among them)
   int qb_peers = pairs_qb, qb_rank = pair_in_qb;
   if (p.n_ranges > 0) {
@@ -133,6 +160,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();                      // prologue done (tables, TMEM, cluster sync)
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -167,12 +195,51 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         peers_seen = lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu;   // for the next check
       };
       uint32_t tile_it = 0;
+      // Dynamic plan, leader CTA: the tiles of iterations it + 1 and it + 2 sit in registers, the claim for it + 3 is in
+      // flight (its value is first touched one iteration later, when it is published).  Other CTA: reads the ring.
+      const bool claimer = dyn && rank == 0;
+      uint32_t tq1 = 0xffffffffu, tq2 = 0xffffffffu, tq3 = 0xffffffffu;     // tiles of it + 1, it + 2, it + 3 (0xffffffff = none)
+      unsigned int* tile_counter = reinterpret_cast<unsigned int*>(p.tile_sched);
+      auto claim = [&]() -> uint32_t {                                       // every lane gets the same tile
+        uint32_t v = 0;
+        if (lane == 0) v = atomicAdd(tile_counter, 1u);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        const uint64_t t = static_cast<uint64_t>(v) + static_cast<uint64_t>(n_pairs);   // the first n_pairs tiles are static
+        return t < static_cast<uint64_t>(n_tiles) ? static_cast<uint32_t>(t) : 0xffffffffu;
+      };
+      auto publish = [&](uint32_t it, uint32_t tile) {
+        if (lane == 0) st_relaxed_gpu_u64(tile_ring + (it & (kTileRing - 1)), (static_cast<unsigned long long>(it + 1u) << 32) | tile);
+      };
+      unsigned long long peeked = 0;
+      auto first_tile = [&]() -> int64_t {
+        if (claimer) {
+          tq1 = claim(); tq2 = claim();
+          publish(1, tq1); publish(2, tq2);
+          tq3 = claim();
+        } else {
+          peeked = tile_peek(1);
+        }
+        return t_first;
+      };
+      auto next_tile = [&](uint32_t it) -> int64_t {                          // it = the iteration that starts now (>= 1)
+        if (!dyn) return tile_get(it, 0ull);
+        if (claimer) {
+          const uint32_t cur = tq1;
+          publish(it + 2u, tq3);                                            // entries up to it + 2 are now visible
+          tq1 = tq2; tq2 = tq3;
+          tq3 = (cur != 0xffffffffu) ? claim() : 0xffffffffu;               // for it + 3
+          return cur != 0xffffffffu ? static_cast<int64_t>(cur) : n_tiles;
+        }
+        const int64_t t = tile_get(it, peeked);
+        peeked = tile_peek(it + 1u);
+        return t;
+      };
       if (F32) {
         // fp32 boxes of 128 rows x 32 k (16 KB) into this CTA's own ring; the converter warps free a stage as soon as
         // its contents sit in their registers
         const uint32_t sF_a = smem_u32(sF), ffull_a = smem_u32(ffull_bar), fempty_a = smem_u32(fempty_bar);
         uint32_t stage = 0, phase = 0;
-        for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++tile_it) {
+        for (int64_t t = first_tile(); t < n_tiles; t = next_tile(++tile_it)) {
           keep_in_step(tile_it);
           const int row0 = static_cast<int>(t * kTileRows + rank * 128);
 #pragma unroll 1
@@ -189,7 +256,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         const uint32_t sA_a = smem_u32(sA), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
         const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
         uint32_t stage = 0, phase = 0;
-        for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++tile_it) {
+        for (int64_t t = first_tile(); t < n_tiles; t = next_tile(++tile_it)) {
           keep_in_step(tile_it);
           const int row0 = static_cast<int>(t * kTileRows + rank * 128);
 #pragma unroll 1
@@ -214,12 +281,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       const uint32_t idesc = make_idesc_bf16(128 * kCtas, NB);
       mbar_wait(smem_u32(q_bar), 0);
       tc_fence_after();
+      if (trace && lane == 0) trace[2] = globaltimer_ns();                         // query block resident
       const uint64_t a_base = make_smem_desc(smem_u32(sA)), b_base = make_smem_desc(smem_u32(sB));
       const uint32_t a_step = static_cast<uint32_t>(kStageBytes) >> 4, b_step = b_chunk_bytes >> 4;   // start-address field units
       const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
       const uint32_t tfull_a = smem_u32(tfull_bar), tempty_a = smem_u32(tempty_bar);
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++it) {
+      unsigned long long peeked = tile_peek(1);
+      for (int64_t t = t_first; t < n_tiles; ++it, t = tile_get(it, peeked), peeked = tile_peek(it + 1u)) {
         const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
         mbar_wait(tempty_a + buf * 8u, bphase ^ 1u);
         tc_fence_after();
@@ -239,7 +308,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
           if (++stage == static_cast<uint32_t>(p.n_stages)) { stage = 0; phase ^= 1u; }
         }
         if (elect_one()) umma_commit<kCtas>(tfull_a + buf * 8u);
+        if (trace && it == 0 && lane == 0) trace[3] = globaltimer_ns();            // first tile's MMAs issued
       }
+      if (trace && lane == 0) trace[4] = globaltimer_ns();                         // last tile's MMAs issued
     }
   } else if (warp == 3) {
     // ================================================================== threshold refresher
@@ -269,8 +340,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     const uint32_t ffull_a = smem_u32(ffull_bar), fempty_a = smem_u32(fempty_bar);
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     const uint32_t full_lead = (kCtas == 2) ? mapa_rank0(full_a) : full_a;
-    uint32_t fstage = 0, fphase = 0, stage = 0, phase = 0;
-    for (int64_t t = t_first; t < n_tiles; t += pairs_qb) {
+    uint32_t fstage = 0, fphase = 0, stage = 0, phase = 0, cit = 0;
+    unsigned long long peeked = tile_peek(1);
+    for (int64_t t = t_first; t < n_tiles; ++cit, t = tile_get(cit, peeked), peeked = tile_peek(cit + 1u)) {
 #pragma unroll 1
       for (int kc = 0; kc < 16; ++kc) {
         mbar_wait(ffull_a + fstage * 8u, fphase);
@@ -328,8 +400,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       tnext[i] = col_live[i] ? ld_cg_u32(tau_src[i]) : 0u;
     }
     uint32_t it = 0;
-    for (int64_t t = t_first; t < n_tiles; t += pairs_qb, ++it) {
+    unsigned long long peeked = 0;
+    for (int64_t t = t_first; t < n_tiles; ++it, t = tile_get(it, peeked)) {
       const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+      peeked = tile_peek(it + 1u);              // consumed after this tile: the load is in flight while the tile is processed
 #pragma unroll
       for (int i = 0; i < kColsPer; ++i) {
         if (col_live[i]) {
@@ -401,7 +475,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       } else {
         release_tmem();   // nothing to read for this warp in this tile
       }
+      if (trace && it == 0 && ew == 0 && lane == 0) trace[5] = globaltimer_ns();   // first tile through the epilogue
     }
+    if (trace && ew == 0 && lane == 0) trace[6] = globaltimer_ns();                // last tile through the epilogue
     if (lane == 0) {
       if (!DENSE) p.s.st.list_count[list_id] = cx.list_pos;
       atomicAdd(s_done, 1u);
@@ -411,6 +487,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   tc_fence_before();
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc<kCtas>(tmem_base, 512);
+  if (trace && threadIdx.x == 0) trace[7] = globaltimer_ns();                      // teardown
 }
 
 template <int kCtas, int RED, bool PART, bool DENSE, bool F32>

@@ -22,7 +22,13 @@ struct TcArgs {
   int32_t lock_window;    // a pair requests tile i only when every pair of its range has requested tile i - lock_window
   const int32_t* blk_class;  // [n_qb+1] first class of each Q block
   const int32_t* blk_split;  // [n_qb] grouped reduces: column (multiple of 32) where the second epilogue warp set starts
+  unsigned long long* trace; // nullable [grid][8]: globaltimer stamps of each CTA's phases (SWAT_SCAN_TRACE diagnostics)
+  // nullable: dynamic tile scheduling (one Q block, selecting scan).  [0] = tile counter, then per pair a ring of
+  // kTileRing entries ((iteration + 1) << 32 | tile): the leader CTA's producer claims tiles three iterations ahead
+  // and publishes them here for the other warps of the pair.  Zeroed before every launch.
+  unsigned long long* tile_sched;
 };
+constexpr int kTileRing = 16;
 
 size_t tc_smem_bytes(int n_blk, int ctas, int n_stages, int n_fstages);
 int tc_pick_stages(int n_blk, int ctas, size_t smem_limit);

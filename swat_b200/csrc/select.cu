@@ -322,12 +322,28 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   __shared__ uint32_t s_cut, s_total, s_base, s_fill;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const float* sc = scores_t + static_cast<size_t>(c) * B;
+  // A thread's scores live in registers across both passes: kPer independent loads up front instead of two dependent
+  // load -> atomic chains of B / 1024 steps (the kernel was bound by exactly that latency: 34 us for 32 K rows)
+  constexpr int kPer = 32;
+  const bool cached = B <= static_cast<uint32_t>(kPer) * kSelThreads;
+  float mine_s[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const uint32_t r = static_cast<uint32_t>(i) * kSelThreads + tid;
+    mine_s[i] = (cached && r < B) ? sc[r] + 0.0f : -INFINITY;
+  }
   for (int i = tid; i < kHistBins; i += kSelThreads) s_h[i] = 0;
   if (tid == 0) s_fill = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < B; i += kSelThreads) {
-    const float s = sc[i] + 0.0f;
-    if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPer; ++i)
+      if (mine_s[i] >= st.thr) atomicAdd(&s_h[hist_bin(st, mine_s[i])], 1u);
+  } else {
+    for (uint32_t i = tid; i < B; i += kSelThreads) {
+      const float s = sc[i] + 0.0f;
+      if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
+    }
   }
   __syncthreads();
   if (tid < 32) {   // warp 0: lane l owns bins 32l .. 32l+31; suffix-scan from the top
@@ -369,14 +385,19 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   const int cut = static_cast<int>(s_cut);
   const uint32_t list_id = first_spare_list + static_cast<uint32_t>(c) % (st.n_lists - first_spare_list);
   uint4* dst = st.list + static_cast<size_t>(list_id) * st.list_cap;
-  for (uint32_t i = tid; i < B; i += kSelThreads) {
-    const float s = sc[i] + 0.0f;
+  auto append = [&](float s, uint32_t i) {
     if (s >= st.thr && hist_bin(st, s) >= cut) {
       const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
       const uint64_t key = make_key(s, row_base + i);
       if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
       else atomicOr(st.flags, 2u);
     }
+  };
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) append(mine_s[i], static_cast<uint32_t>(i) * kSelThreads + tid);
+  } else {
+    for (uint32_t i = tid; i < B; i += kSelThreads) append(sc[i] + 0.0f, i);
   }
   for (int b = cut + tid; b < kHistBins; b += kSelThreads)
     if (s_h[b]) atomicAdd(&st.hist[static_cast<size_t>(c) * kHistBins + b], s_h[b]);
@@ -472,18 +493,25 @@ __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
   const int64_t w = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (w >= static_cast<int64_t>(a.n_classes) * groups) return;
   const int c = static_cast<int>(w / groups), j0 = static_cast<int>(w % groups) * NC;
-  const int n = min(a.cand_counts[c], a.stride);
-  if (j0 >= n) return;
   const size_t base = static_cast<size_t>(c) * a.stride;
+  // everything the warp needs to know is requested at once (candidate count, row ids, approximate scores, query
+  // ranges): one L2 round trip ahead of the row reads instead of a chain of three
+  const int n_raw = a.cand_counts[c];
   int64_t r[NC];
+  float approx[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    r[i] = -1;
-    if (j0 + i < n) r[i] = a.gather_index ? a.gather_index[base + j0 + i] : a.cand_rows[base + j0 + i] - a.bank_row_base;
-    if (r[i] >= a.bank_rows) r[i] = -1;
+    const bool in = j0 + i < a.stride;          // slots beyond the class's count hold stale ids: masked below
+    r[i] = in ? (a.gather_index ? a.gather_index[base + j0 + i] : a.cand_rows[base + j0 + i] - a.bank_row_base) : -1;
+    approx[i] = (in && a.eps_violation) ? a.cand_scores[base + j0 + i] : 0.0f;
   }
-  Raw16<T> x[NC], y[NC];
   const int q0 = a.class_begin[c], q1 = a.class_begin[c + 1];
+  const int n = min(n_raw, a.stride);
+  if (j0 >= n) return;
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+    if (j0 + i >= n || r[i] >= a.bank_rows || r[i] < 0) r[i] = -1;
+  Raw16<T> x[NC], y[NC];
   float aux[NC];
   if (a.lazy_t2t && a.aux_bank) {
     // rows are expensive to fetch (pinned host memory over PCIe): predicate rows first, ranking rows only for the
@@ -543,7 +571,7 @@ __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
       a.exact_scratch[base + j0 + i] = t2t;
       if (a.aux_bank) a.aux_scratch[base + j0 + i] = ax;
       // the frontier proof rests on |approximate - exact| <= eps: check it on every row we look at anyway
-      if (a.eps_violation && !a.all_or_nothing && r[i] >= 0 && fabsf(t2t - a.cand_scores[base + j0 + i]) > a.eps) *a.eps_violation = 1;
+      if (a.eps_violation && !a.all_or_nothing && r[i] >= 0 && fabsf(t2t - approx[i]) > a.eps) *a.eps_violation = 1;
     }
   }
 }
