@@ -1252,33 +1252,39 @@ int32_t swat_queries_create(swat_ctx* ctx, const float* h_queries, int32_t n_que
   swat_queries* q = new swat_queries();
   q->ctx = ctx; q->Q = n_queries; q->C = n_classes; q->reduce = reduce; q->class_begin = cb; q->ctas = ctx->cta_group;
   q->h_q.assign(h_queries, h_queries + static_cast<size_t>(n_queries) * kDim);
-  int max_cols = (q->ctas == 2) ? 256 : 144;
+  const int hard_cols = (q->ctas == 2) ? 256 : 144;
   int max_group = 1;
   for (int c = 0; c < n_classes; ++c) max_group = std::max(max_group, cb[c + 1] - cb[c]);
-  // grouped reduces: a class may not straddle the column where the second epilogue warp set starts,
-  // which can cost up to max_group-1 padding columns per block
-  if (reduce != SWAT_REDUCE_NONE) max_cols -= (max_group - 1);
+  // column layout of every block.  Grouped reduces: a class may not straddle the column where the second epilogue
+  // warp set starts, which can cost up to max_group-1 padding columns per block -- first try the full width (the
+  // padding is often not needed: Q = 256 in groups of 2 is one block), then plan with that slack held back.
   std::vector<int> first;
-  if (max_cols < max_group || !plan_blocks(cb, max_cols, q->n_qb, q->n_blk, first)) {
+  std::vector<std::vector<std::pair<int, int>>> place;   // per block: (class, first column)
+  std::vector<int32_t> split;
+  int widest = 0;
+  auto layout = [&](int max_cols) -> bool {
+    if (max_cols < max_group || !plan_blocks(cb, max_cols, q->n_qb, q->n_blk, first)) return false;
+    place.assign(q->n_qb, {});
+    split.assign(q->n_qb, 0);
+    widest = 0;
+    for (int b = 0; b < q->n_qb; ++b) {
+      const int cols = cb[first[b + 1]] - cb[first[b]];
+      const int H = (reduce == SWAT_REDUCE_NONE) ? (1 << 30) : ((cols + 1) / 2 + 31) / 32 * 32;
+      int col = 0;
+      for (int c = first[b]; c < first[b + 1]; ++c) {
+        const int R = cb[c + 1] - cb[c];
+        if (col < H && col + R > H) col = H;          // never straddle the split
+        place[b].push_back({c, col});
+        col += R;
+      }
+      split[b] = H;
+      widest = std::max(widest, col);
+    }
+    return widest <= hard_cols;
+  };
+  if (!layout(hard_cols) && (reduce == SWAT_REDUCE_NONE || !layout(hard_cols - (max_group - 1)))) {
     delete q;
     return fail(SWAT_ERR_UNSUPPORTED, "a class has %d queries; cannot keep it resident", max_group);
-  }
-  // column layout of every block
-  std::vector<std::vector<std::pair<int, int>>> place(q->n_qb);   // per block: (class, first column)
-  std::vector<int32_t> split(q->n_qb, 0);
-  int widest = 0;
-  for (int b = 0; b < q->n_qb; ++b) {
-    const int cols = cb[first[b + 1]] - cb[first[b]];
-    const int H = (reduce == SWAT_REDUCE_NONE) ? (1 << 30) : ((cols + 1) / 2 + 31) / 32 * 32;
-    int col = 0;
-    for (int c = first[b]; c < first[b + 1]; ++c) {
-      const int R = cb[c + 1] - cb[c];
-      if (col < H && col + R > H) col = H;          // never straddle the split
-      place[b].push_back({c, col});
-      col += R;
-    }
-    split[b] = H;
-    widest = std::max(widest, col);
   }
   q->n_blk = std::max(16, (widest + 15) / 16 * 16);
   for (int b = 0; b < q->n_qb; ++b) split[b] = std::min(split[b], q->n_blk);

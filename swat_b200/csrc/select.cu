@@ -322,28 +322,12 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   __shared__ uint32_t s_cut, s_total, s_base, s_fill;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const float* sc = scores_t + static_cast<size_t>(c) * B;
-  // A thread's scores live in registers across both passes: kPer independent loads up front instead of two dependent
-  // load -> atomic chains of B / 1024 steps (the kernel was bound by exactly that latency: 34 us for 32 K rows)
-  constexpr int kPer = 32;
-  const bool cached = B <= static_cast<uint32_t>(kPer) * kSelThreads;
-  float mine_s[kPer];
-#pragma unroll
-  for (int i = 0; i < kPer; ++i) {
-    const uint32_t r = static_cast<uint32_t>(i) * kSelThreads + tid;
-    mine_s[i] = (cached && r < B) ? sc[r] + 0.0f : -INFINITY;
-  }
   for (int i = tid; i < kHistBins; i += kSelThreads) s_h[i] = 0;
   if (tid == 0) s_fill = 0;
   __syncthreads();
-  if (cached) {
-#pragma unroll
-    for (int i = 0; i < kPer; ++i)
-      if (mine_s[i] >= st.thr) atomicAdd(&s_h[hist_bin(st, mine_s[i])], 1u);
-  } else {
-    for (uint32_t i = tid; i < B; i += kSelThreads) {
-      const float s = sc[i] + 0.0f;
-      if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
-    }
+  for (uint32_t i = tid; i < B; i += kSelThreads) {
+    const float s = sc[i] + 0.0f;
+    if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
   }
   __syncthreads();
   if (tid < 32) {   // warp 0: lane l owns bins 32l .. 32l+31; suffix-scan from the top
@@ -385,19 +369,14 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   const int cut = static_cast<int>(s_cut);
   const uint32_t list_id = first_spare_list + static_cast<uint32_t>(c) % (st.n_lists - first_spare_list);
   uint4* dst = st.list + static_cast<size_t>(list_id) * st.list_cap;
-  auto append = [&](float s, uint32_t i) {
+  for (uint32_t i = tid; i < B; i += kSelThreads) {
+    const float s = sc[i] + 0.0f;
     if (s >= st.thr && hist_bin(st, s) >= cut) {
       const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
       const uint64_t key = make_key(s, row_base + i);
       if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
       else atomicOr(st.flags, 2u);
     }
-  };
-  if (cached) {
-#pragma unroll
-    for (int i = 0; i < kPer; ++i) append(mine_s[i], static_cast<uint32_t>(i) * kSelThreads + tid);
-  } else {
-    for (uint32_t i = tid; i < B; i += kSelThreads) append(sc[i] + 0.0f, i);
   }
   for (int b = cut + tid; b < kHistBins; b += kSelThreads)
     if (s_h[b]) atomicAdd(&st.hist[static_cast<size_t>(c) * kHistBins + b], s_h[b]);

@@ -163,6 +163,47 @@ def test_topk_synonym_groups(lib, ctx, reduce, dtype):
     np.testing.assert_allclose(dense, S, atol=1e-5 if dtype == torch.bfloat16 else 2e-2)
 
 
+@pytest.mark.parametrize("reduce", ["max", "mean"])
+def test_full_width_grouped_block(lib, ctx2, reduce):
+    """128 classes x 2 synonyms = 256 query columns: the class boundary at column 128 is where the second epilogue
+    warp set starts, no padding is needed and the whole set is ONE resident block (it used to be planned as two)."""
+    from swat_b200 import synth
+    sizes = [2] * 128
+    qc, queries, coq = synth.make_queries(len(sizes), sizes, seed=13, dtype=torch.bfloat16)
+    cap, _, _ = synth.make_bank(120_000, qc, seed=13, dtype=torch.bfloat16, rho=0.3, tie_block=100, chunk=1 << 15, with_images=False)
+    capf, qf, coq_np = cap.float().numpy(), queries.float().numpy(), coq.numpy()
+    qs = lib.Queries(ctx2, queries.float(), coq, len(sizes), reduce)
+    g = lib.topk(ctx2, qs, cap.cuda(), 150, 0.0)
+    S = so.score_matrix(capf, qf, coq_np, len(sizes), reduce)
+    o = so.topk_walk(capf, qf, 150, 0.0, class_of_query=coq_np, n_classes=len(sizes), reduce=reduce)
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], S, TIE_TOL, what=f"full-width {reduce}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_dynamic_tile_plan_equals_static(lib, ctx2, dtype):
+    """One Q block: pairs claim tiles from a global counter (dyn_tiles, the default) instead of a fixed stride.  Which
+    pair scores a tile cannot matter: results are bit-identical to the static plan, on a bank whose tile count is
+    not a multiple of the pair count and ends in a ragged tile."""
+    from swat_b200 import synth
+    qc, queries, _ = synth.make_queries(48, 1, seed=17, dtype=torch.bfloat16)
+    cap, img, _ = synth.make_bank(74 * 256 * 9 + 12_345, qc, seed=17, dtype=dtype, rho=0.2, tie_block=200, chunk=1 << 16)
+    qs = lib.Queries(ctx2, queries.float())
+    capd, imgd = cap.cuda(), img.cuda()
+    out = {}
+    try:
+        for dyn in (1, 0):
+            ctx2.set_option("dyn_tiles", dyn)
+            out[dyn] = [lib.topk(ctx2, qs, capd, 300, 0.0), lib.topk(ctx2, qs, capd, 300, 0.0, t2i_bank=imgd, t2i_threshold=0.25)]
+    finally:
+        ctx2.set_option("dyn_tiles", 1)
+    for a, b in zip(out[1], out[0]):
+        assert torch.equal(a[3], b[3]) and torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+    capf, qf = cap.float().numpy(), queries.float().numpy()
+    o = so.topk_walk(capf, qf, 300, 0.0)
+    g = out[1][0]
+    check_result(g[0], g[1], g[3], o[0], o[1], o[3], capf @ qf.T, TIE_TOL, what=f"dynamic tiles {dtype}")
+
+
 @pytest.mark.parametrize("n_cls,syn", [(700, False), (230, True)])
 def test_unit_plan_many_query_blocks(lib, ctx, n_cls, syn):
     """More queries than one resident block holds, block count not dividing the CTA pairs: the scan runs as

@@ -9,6 +9,11 @@ if len(sys.argv) > 1:
     _lib.LIB_PATH = os.path.abspath(sys.argv[1])
     dev = torch.device("cuda", 0)
     ctx = _lib.Context(0)
+    for opt in sys.argv[2:]:                     # e.g. dyn_tiles=0 (options the old build does not know are skipped)
+        try:
+            ctx.set_option(opt.split("=")[0], int(opt.split("=")[1]))
+        except Exception as e:
+            print("option skipped:", opt, e)
     def run(name, cap, img, q, reps=30):
         qs = _lib.Queries(ctx, q.float())
         kw = {"t2i_bank": img, "t2i_threshold": 0.25} if img is not None else {}
@@ -22,7 +27,7 @@ if len(sys.argv) > 1:
             _lib.topk(ctx, qs, cap, 500, 0.0, **kw)
             t = ctx.last_timing(); scan += t["scan_ms"]; tail += t["select_ms"] + t["t2i_ms"]
         e1.record(); torch.cuda.synchronize()
-        print(f"{os.path.basename(sys.argv[1])} {name}: {e0.elapsed_time(e1)/reps:.4f} ms/step  scan {scan/reps:.4f}  select+walk {tail/reps:.4f}", flush=True)
+        print(f"{os.path.basename(sys.argv[1])} {' '.join(sys.argv[2:])} {name}: {e0.elapsed_time(e1)/reps:.4f} ms/step  scan {scan/reps:.4f}  select+walk {tail/reps:.4f}", flush=True)
         qs.close()
     qc, q, _ = synth.make_queries(200, 1, seed=0, dtype=torch.bfloat16)
     cap, img, _ = synth.make_bank(10_000_000, qc, seed=0, device=dev, dtype=torch.bfloat16, chunk=1 << 20)
