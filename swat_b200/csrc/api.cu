@@ -247,6 +247,38 @@ struct ScanBits {
   float thr = 0.0f;                 // pass A threshold
 };
 
+// launch_scan_tc, with the CTA phase stamps printed when SWAT_SCAN_TRACE is set (diagnostics: synchronises)
+int32_t launch_scan_traced(const CUtensorMap* tm_bank, const swat_queries* q, TcArgs p, bool part, bool dense, bool f32, int grid, cudaStream_t stream) {
+  static const bool tracing = getenv("SWAT_SCAN_TRACE") != nullptr;
+  if (!tracing) {
+    CU_OK(launch_scan_tc(tm_bank, &q->tm_q, p, q->ctas, q->reduce, part, dense, f32, grid, stream));
+    return SWAT_OK;
+  }
+  static unsigned long long* d_trace = nullptr;
+  if (!d_trace) CU_OK(cudaMalloc(&d_trace, 1024 * 8 * 8));
+  CU_OK(cudaMemsetAsync(d_trace, 0, 1024 * 8 * 8, stream));
+  p.trace = d_trace;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, stream);
+  CU_OK(launch_scan_tc(tm_bank, &q->tm_q, p, q->ctas, q->reduce, part, dense, f32, grid, stream));
+  cudaEventRecord(t1, stream);
+  std::vector<unsigned long long> h(static_cast<size_t>(grid) * 8);
+  CU_OK(cudaMemcpyAsync(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost, stream));
+  CU_OK(cudaStreamSynchronize(stream));
+  float ms = 0; cudaEventElapsedTime(&ms, t0, t1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+  unsigned long long first = ~0ull, last = 0;
+  for (int b = 0; b < grid; ++b) { first = std::min(first, h[b * 8]); last = std::max(last, h[b * 8 + 7]); }
+  double mx[8] = {0}, mn[8];
+  for (int i = 0; i < 8; ++i) mn[i] = 1e30;
+  for (int b = 0; b < grid; ++b)
+    for (int i = 0; i < 8; ++i) if (h[b * 8 + i]) { const double v = (h[b * 8 + i] - first) * 1e-3; mx[i] = std::max(mx[i], v); mn[i] = std::min(mn[i], v); }
+  fprintf(stderr, "[swat trace] scan rows=%lld%s event %.1f us, first entry -> last exit %.1f us | us since first entry (min/max over CTAs): "
+                  "entry %.1f/%.1f prologue %.1f/%.1f queries %.1f/%.1f mma1 %.1f/%.1f mmaN %.1f/%.1f epi1 %.1f/%.1f epiN %.1f/%.1f exit %.1f/%.1f\n",
+          (long long)p.s.n_rows, dense ? " dense" : "", ms * 1e3, (last - first) * 1e-3, mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3], mn[4], mx[4],
+          mn[5], mx[5], mn[6], mx[6], mn[7], mx[7]);
+  return SWAT_OK;
+}
+
 int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_rows, int64_t row_base, const void* d_t2i_bank,
                   float t2i_threshold, const int32_t* d_row_class, const uint32_t* d_exclude, int32_t engine, float* dense_out,
                   cudaStream_t stream, const ScanBits* bits = nullptr) {
@@ -327,7 +359,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
       for (int b0 = 0; b0 < q->n_qb; b0 += grid / q->ctas) {
         pd.qb_base = b0;
         pd.qb_count = std::min(grid / q->ctas, q->n_qb - b0);
-        CU_OK(launch_scan_tc(&tm_pre, &q->tm_q, pd, q->ctas, q->reduce, false, true, f32, grid, stream));
+        SW_OK(launch_scan_traced(&tm_pre, q, pd, false, true, f32, grid, stream));
       }
       CU_OK(launch_bootstrap(job->st, q->C, ctx->w_boot.as<float>(), static_cast<uint32_t>(B), a.row_base,
                              static_cast<uint32_t>(grid) * kTcEpiWarps, stream));
@@ -375,33 +407,7 @@ int32_t scan_view(swat_job* job, const void* d_bank, int32_t dtype, int64_t n_ro
         p.qb_base = i * pairs;
         p.qb_count = std::min(pairs, q->n_qb - p.qb_base);
       }
-      static const bool tracing = getenv("SWAT_SCAN_TRACE") != nullptr;
-      static unsigned long long* d_trace = nullptr;
-      if (tracing) {
-        if (!d_trace) CU_OK(cudaMalloc(&d_trace, 1024 * 8 * 8));
-        CU_OK(cudaMemsetAsync(d_trace, 0, 1024 * 8 * 8, stream));
-        p.trace = d_trace;
-      }
-      cudaEvent_t t0 = nullptr, t1 = nullptr;
-      if (tracing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, stream); }
-      CU_OK(launch_scan_tc(&tm_bank, &q->tm_q, p, q->ctas, q->reduce, d_row_class != nullptr, dense, f32, grid, stream));
-      if (tracing) {
-        cudaEventRecord(t1, stream);
-        std::vector<unsigned long long> h(static_cast<size_t>(grid) * 8);
-        CU_OK(cudaMemcpyAsync(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost, stream));
-        CU_OK(cudaStreamSynchronize(stream));
-        float ms = 0; cudaEventElapsedTime(&ms, t0, t1); cudaEventDestroy(t0); cudaEventDestroy(t1);
-        unsigned long long first = ~0ull, last = 0;
-        for (int b = 0; b < grid; ++b) { first = std::min(first, h[b * 8]); last = std::max(last, h[b * 8 + 7]); }
-        double mx[8] = {0}, mn[8];
-        for (int i = 0; i < 8; ++i) mn[i] = 1e30;
-        for (int b = 0; b < grid; ++b)
-          for (int i = 0; i < 8; ++i) if (h[b * 8 + i]) { const double v = (h[b * 8 + i] - first) * 1e-3; mx[i] = std::max(mx[i], v); mn[i] = std::min(mn[i], v); }
-        fprintf(stderr, "[swat trace] scan rows=%lld event %.1f us, first entry -> last exit %.1f us | us since first entry (min/max over CTAs): "
-                        "entry %.1f/%.1f prologue %.1f/%.1f queries %.1f/%.1f mma1 %.1f/%.1f mmaN %.1f/%.1f epi1 %.1f/%.1f epiN %.1f/%.1f exit %.1f/%.1f\n",
-                (long long)a.n_rows, ms * 1e3, (last - first) * 1e-3, mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3], mn[4], mx[4], mn[5], mx[5],
-                mn[6], mx[6], mn[7], mx[7]);
-      }
+      SW_OK(launch_scan_traced(&tm_bank, q, p, d_row_class != nullptr, dense, f32, grid, stream));
     }
     ctx->launches += launches - 1;
   } else {

@@ -325,9 +325,19 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   for (int i = tid; i < kHistBins; i += kSelThreads) s_h[i] = 0;
   if (tid == 0) s_fill = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < B; i += kSelThreads) {
-    const float s = sc[i] + 0.0f;
-    if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
+  // 16 independent loads, then their atomics: a plain load -> atomic loop pays one L2 round trip per element (the
+  // compiler keeps the loads behind the atomics), 64 of them over both passes for the usual 32 K-row prefix
+  constexpr int kBatch = 16;
+  for (uint32_t i0 = tid; i0 < B; i0 += kBatch * kSelThreads) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const uint32_t i = i0 + static_cast<uint32_t>(u) * kSelThreads;
+      v[u] = i < B ? sc[i] + 0.0f : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (i0 + static_cast<uint32_t>(u) * kSelThreads < B && v[u] >= st.thr) atomicAdd(&s_h[hist_bin(st, v[u])], 1u);
   }
   __syncthreads();
   if (tid < 32) {   // warp 0: lane l owns bins 32l .. 32l+31; suffix-scan from the top
@@ -369,13 +379,23 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   const int cut = static_cast<int>(s_cut);
   const uint32_t list_id = first_spare_list + static_cast<uint32_t>(c) % (st.n_lists - first_spare_list);
   uint4* dst = st.list + static_cast<size_t>(list_id) * st.list_cap;
-  for (uint32_t i = tid; i < B; i += kSelThreads) {
-    const float s = sc[i] + 0.0f;
-    if (s >= st.thr && hist_bin(st, s) >= cut) {
-      const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
-      const uint64_t key = make_key(s, row_base + i);
-      if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
-      else atomicOr(st.flags, 2u);
+  for (uint32_t i0 = tid; i0 < B; i0 += kBatch * kSelThreads) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const uint32_t i = i0 + static_cast<uint32_t>(u) * kSelThreads;
+      v[u] = i < B ? sc[i] + 0.0f : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const uint32_t i = i0 + static_cast<uint32_t>(u) * kSelThreads;
+      const float s = v[u];
+      if (i < B && s >= st.thr && hist_bin(st, s) >= cut) {
+        const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
+        const uint64_t key = make_key(s, row_base + i);
+        if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
+        else atomicOr(st.flags, 2u);
+      }
     }
   }
   for (int b = cut + tid; b < kHistBins; b += kSelThreads)
