@@ -246,7 +246,7 @@ def run_extras(a, rank, world, dev, main):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(ctx, step, n_local, q_cols, bytes_per_row, warm=2, reps=3):
+    def timed(ctx, step, n_local, q_cols, bytes_per_row, warm=3, reps=3):
         for _ in range(warm):
             step()
         scans = ctx.__dict__["_time_scans"] = []
@@ -338,7 +338,7 @@ def run_extras(a, rank, world, dev, main):
                     q3 = torch.nn.functional.normalize(qc[:C3][coq.long()].float() + 0.3 * u, dim=-1).to(torch.bfloat16).float()
                     qs = _lib.Queries(ctx, q3, coq, C3, "max")
                     Q3 = S3
-                e = timed(ctx, t2t_step(ctx, qs, capx, 0), n_x, Q3, 1024.0, warm=1, reps=2)
+                e = timed(ctx, t2t_step(ctx, qs, capx, 0), n_x, Q3, 1024.0, warm=3, reps=2)
                 e.pop("clocks", None)
                 e["workload"] = f"{name}: C = {C3}, Q = {Q3} ({mode}), T2T top-{a.k}, {n_x} x 512 bf16 rows"
                 out["cfg3_sweep9"].append(e)
