@@ -69,7 +69,11 @@ int32_t swat_ctx_destroy(swat_ctx* ctx);
 /* tuning knobs (all optional): "cta_group" (1|2, before swat_queries_create), "max_ctas", "cand_cap"
  * (per-class candidates kept after the final threshold), "list_entries" (total survivor-list entries),
  * "overfetch" (first k_fetch of the T2I walk), "host_chunk_rows"; 0 = automatic.  Switches (default 1): "unit_plan",
- * "swap_pass", "zero_copy" (host pipeline reads candidates' rows from pinned banks in place), "bootstrap_rows" */
+ * "swap_pass", "zero_copy" (host pipeline reads candidates' rows from pinned banks in place), "dyn_tiles" (one query
+ * block: CTA pairs claim bank tiles from a global counter instead of a fixed stride); "bootstrap_rows" (dense prefix
+ * that seeds the thresholds, default 32768, 0 = off), "lock_window" (several query blocks: pairs sharing a tile range
+ * stay within this many tiles of each other, default 0 = off), "f32_op_stages".  Environment: SWAT_DEBUG=1 logs
+ * allocations, SWAT_SCAN_TRACE=1 prints per-launch phase stamps of the scan kernel (diagnostics: synchronises). */
 int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value);
 /* counters since ctx creation: kernels launched by this library (bench.py's gpu_launches claim) */
 int64_t swat_ctx_launch_count(const swat_ctx* ctx);
