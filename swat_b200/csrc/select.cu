@@ -485,7 +485,8 @@ template <> struct Raw16<__nv_bfloat16> {
 // scattered 1-2 KB rows, which is what HBM gives this access pattern: staging the rows through shared memory
 // (cp.async.bulk per row, then 16-byte cp.async, 96 KB in flight per CTA, ids and class tables prefetched a chunk
 // ahead) was measured SLOWER on the B200 (193-294 us against 129 us for 200 x 1024 candidates of both banks).
-template <typename T, int NC>
+// AUX = a predicate bank is read as well; without one a warp keeps twice as many ranking rows in flight.
+template <typename T, int NC, bool AUX>
 __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
   const int lane = threadIdx.x & 31;
   const int groups = (a.stride + NC - 1) / NC;
@@ -510,38 +511,38 @@ __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
 #pragma unroll
   for (int i = 0; i < NC; ++i)
     if (j0 + i >= n || r[i] >= a.bank_rows || r[i] < 0) r[i] = -1;
-  Raw16<T> x[NC], y[NC];
-  float aux[NC];
-  if (a.lazy_t2t && a.aux_bank) {
+  Raw16<T> x[NC], y[AUX ? NC : 1];
+  float aux[AUX ? NC : 1];
+  if (AUX && a.lazy_t2t) {
     // rows are expensive to fetch (pinned host memory over PCIe): predicate rows first, ranking rows only for the
     // candidates that pass it -- the others can never be accepted and need no exact score
 #pragma unroll
     for (int i = 0; i < NC; ++i)
-      if (r[i] >= 0) y[i].load(static_cast<const T*>(a.aux_bank) + r[i] * kDim + lane * 16);
+      if (r[i] >= 0) y[AUX ? i : 0].load(static_cast<const T*>(a.aux_bank) + r[i] * kDim + lane * 16);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-      aux[i] = -INFINITY;
+      aux[AUX ? i : 0] = -INFINITY;
       if (r[i] >= 0) {
         float f[16];
-        y[i].unpack(f);
-        aux[i] = canonical_score<T>(f, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
+        y[AUX ? i : 0].unpack(f);
+        aux[AUX ? i : 0] = canonical_score<T>(f, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
       }
     }
 #pragma unroll
     for (int i = 0; i < NC; ++i)
-      if (r[i] >= 0 && aux[i] >= a.aux_thr) x[i].load(static_cast<const T*>(a.t2t_bank) + r[i] * kDim + lane * 16);
+      if (r[i] >= 0 && aux[AUX ? i : 0] >= a.aux_thr) x[i].load(static_cast<const T*>(a.t2t_bank) + r[i] * kDim + lane * 16);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       if (j0 + i >= n) break;                    // warp-uniform
       float t2t = -INFINITY;
-      if (r[i] >= 0 && aux[i] >= a.aux_thr) {
+      if (r[i] >= 0 && aux[AUX ? i : 0] >= a.aux_thr) {
         float f[16];
         x[i].unpack(f);
         t2t = canonical_score<T>(f, static_cast<const T*>(a.queries), q0, q1, a.reduce, lane);
       }
       if (lane == 0) {
         a.exact_scratch[base + j0 + i] = t2t;
-        a.aux_scratch[base + j0 + i] = aux[i];
+        a.aux_scratch[base + j0 + i] = aux[AUX ? i : 0];
       }
     }
     return;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
   for (int i = 0; i < NC; ++i) {
     if (r[i] >= 0) {
       x[i].load(static_cast<const T*>(a.t2t_bank) + r[i] * kDim + lane * 16);
-      if (a.aux_bank) y[i].load(static_cast<const T*>(a.aux_bank) + r[i] * kDim + lane * 16);
+      if (AUX) y[AUX ? i : 0].load(static_cast<const T*>(a.aux_bank) + r[i] * kDim + lane * 16);
     }
   }
 #pragma unroll
@@ -561,14 +562,14 @@ __global__ void __launch_bounds__(256, 2) rescore_kernel(const WalkArgs a) {
       float f[16];
       x[i].unpack(f);
       t2t = canonical_score<T>(f, static_cast<const T*>(a.queries), q0, q1, a.reduce, lane);
-      if (a.aux_bank) {
-        y[i].unpack(f);
+      if (AUX) {
+        y[AUX ? i : 0].unpack(f);
         ax = canonical_score<T>(f, static_cast<const T*>(a.aux_queries), a.aux_class_begin[c], a.aux_class_begin[c + 1], a.aux_reduce, lane);
       }
     }
     if (lane == 0) {
       a.exact_scratch[base + j0 + i] = t2t;
-      if (a.aux_bank) a.aux_scratch[base + j0 + i] = ax;
+      if (AUX) a.aux_scratch[base + j0 + i] = ax;
       // the frontier proof rests on |approximate - exact| <= eps: check it on every row we look at anyway
       if (a.eps_violation && !a.all_or_nothing && r[i] >= 0 && fabsf(t2t - approx[i]) > a.eps) *a.eps_violation = 1;
     }
@@ -897,13 +898,19 @@ cudaError_t launch_job_reset(const JobState& st, int n_classes, cudaStream_t str
 }
 
 cudaError_t launch_rescore_walk(const WalkArgs& a, cudaStream_t stream) {
-  constexpr int kBf16Cands = 4, kF32Cands = 2;          // candidates per warp
-  const int per = a.dtype == 0 ? kBf16Cands : kF32Cands;
+  constexpr int kBf16Cands = 4, kF32Cands = 2;          // candidates per warp with a predicate bank; twice that without
+  const bool aux = a.aux_bank != nullptr;
+  const int per = (a.dtype == 0 ? kBf16Cands : kF32Cands) * (aux ? 1 : 2);
   const int64_t n = static_cast<int64_t>(a.n_classes) * ((a.stride + per - 1) / per);
   if (n <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((n + 7) / 8);
-  if (a.dtype == 0) rescore_kernel<__nv_bfloat16, kBf16Cands><<<grid, 256, 0, stream>>>(a);
-  else rescore_kernel<float, kF32Cands><<<grid, 256, 0, stream>>>(a);
+  if (a.dtype == 0) {
+    if (aux) rescore_kernel<__nv_bfloat16, kBf16Cands, true><<<grid, 256, 0, stream>>>(a);
+    else rescore_kernel<__nv_bfloat16, 2 * kBf16Cands, false><<<grid, 256, 0, stream>>>(a);
+  } else {
+    if (aux) rescore_kernel<float, kF32Cands, true><<<grid, 256, 0, stream>>>(a);
+    else rescore_kernel<float, 2 * kF32Cands, false><<<grid, 256, 0, stream>>>(a);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   walk_kernel<<<a.n_classes, kSelThreads, 0, stream>>>(a);
