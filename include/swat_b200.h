@@ -72,7 +72,8 @@ int32_t swat_ctx_destroy(swat_ctx* ctx);
  * "swap_pass", "zero_copy" (host pipeline reads candidates' rows from pinned banks in place), "dyn_tiles" (one query
  * block: CTA pairs claim bank tiles from a global counter instead of a fixed stride); "bootstrap_rows" (dense prefix
  * that seeds the thresholds, default 32768, 0 = off), "lock_window" (several query blocks: pairs sharing a tile range
- * stay within this many tiles of each other, default 0 = off), "f32_op_stages".  Environment: SWAT_DEBUG=1 logs
+ * stay within this many tiles of each other; 0 = off, default -1 = automatic: 4 for 4-8 query blocks while the scan
+ * observes a power-capped SM clock), "f32_op_stages".  Environment: SWAT_DEBUG=1 logs
  * allocations, SWAT_SCAN_TRACE=1 prints per-launch phase stamps of the scan kernel (diagnostics: synchronises). */
 int32_t swat_ctx_set_option(swat_ctx* ctx, const char* name, int64_t value);
 /* counters since ctx creation: kernels launched by this library (bench.py's gpu_launches claim) */

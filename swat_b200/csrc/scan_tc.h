@@ -27,6 +27,9 @@ struct TcArgs {
   // kTileRing entries ((iteration + 1) << 32 | tile): the leader CTA's producer claims tiles three iterations ahead
   // and publishes them here for the other warps of the pair.  Zeroed before every launch.
   unsigned long long* tile_sched;
+  // nullable: CTA 0 writes the SM clock it observed over the launch (MHz = clock64 ticks / globaltimer time) here; the
+  // host uses it to tell a power-capped GPU (automatic lockstep window, api.cu)
+  unsigned long long* clock_probe;
 };
 constexpr int kTileRing = 16;
 

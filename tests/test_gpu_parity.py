@@ -204,6 +204,28 @@ def test_dynamic_tile_plan_equals_static(lib, ctx2, dtype):
     check_result(g[0], g[1], g[3], o[0], o[1], o[3], capf @ qf.T, TIE_TOL, what=f"dynamic tiles {dtype}")
 
 
+def test_lockstep_window_is_result_neutral(lib, ctx2):
+    """Four Q blocks: held in step (lock_window > 0, what the automatic mode switches on for a power-capped GPU) the
+    pairs of a tile range read the bank once; which pair is ahead cannot matter to the result."""
+    from swat_b200 import synth
+    qc, queries, _ = synth.make_queries(1000, 1, seed=23, dtype=torch.bfloat16)
+    cap, _, _ = synth.make_bank(400_000, qc, seed=23, dtype=torch.bfloat16, rho=0.3, tie_block=300, chunk=1 << 16, with_images=False)
+    qs = lib.Queries(ctx2, queries.float())
+    capd = cap.cuda()
+    out = {}
+    try:
+        for lw in (0, 4, -1):
+            ctx2.set_option("lock_window", lw)
+            out[lw] = lib.topk(ctx2, qs, capd, 100, 0.0)
+    finally:
+        ctx2.set_option("lock_window", -1)
+    for lw in (4, -1):
+        assert torch.equal(out[lw][1], out[0][1]) and torch.equal(out[lw][0], out[0][0]) and torch.equal(out[lw][3], out[0][3])
+    capf, qf = cap.float().numpy(), queries.float().numpy()
+    o = so.topk_walk(capf, qf, 100, 0.0)
+    check_result(out[4][0], out[4][1], out[4][3], o[0], o[1], o[3], capf @ qf.T, TIE_TOL, what="lockstep")
+
+
 @pytest.mark.parametrize("n_cls,syn", [(700, False), (230, True)])
 def test_unit_plan_many_query_blocks(lib, ctx, n_cls, syn):
     """More queries than one resident block holds, block count not dividing the CTA pairs: the scan runs as
