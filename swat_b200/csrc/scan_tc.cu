@@ -66,8 +66,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
   const int64_t t_first = (pair_in_qb < pairs_qb) ? pair_in_qb : n_tiles;
   // Tile of this pair's iteration `it` (n_tiles = no more).  Static plan: t_first + it * pairs_qb.  Dynamic plan
   // (p.tile_sched; one Q block): the pairs finish 3-5 % apart under a static split (SM position, survivor bursts), so
-  // after its first tile a pair takes the next unclaimed tile from a global counter.  The leader CTA's producer claims
-  // three iterations ahead and publishes (iteration, tile) in a small ring in global memory; every other warp of the
+  // after its first three tiles a pair takes the next unclaimed tile from a global counter.  The leader CTA's producer
+  // claims ahead and publishes (iteration, tile) in a small ring in global memory two iterations early; every other warp of the
   // pair peeks at the entry of iteration it + 1 while it works on iteration it, so nobody waits on the L2 round trip.
   const bool dyn = !DENSE && p.tile_sched != nullptr;
   unsigned long long* tile_ring = dyn ? p.tile_sched + 2 + static_cast<size_t>(pair_id) * kTileRing : nullptr;
@@ -82,7 +82,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
     if (it == 0) return t_first;
     uint32_t spins = 0;
     while (static_cast<uint32_t>(peeked >> 32) != it + 1u) {
-      if (++spins > 40000000u) __trap();            // a hang becomes a launch failure
+      if (++spins > 4000000u) __trap();             // a hang becomes a launch failure after a few seconds
       __nanosleep(40);
       peeked = ld_relaxed_gpu_u64(tile_ring + (it & (kTileRing - 1)));
     }
@@ -199,16 +199,28 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         peers_seen = lane < grp_size ? ld_relaxed_gpu_u32(p.progress + grp_first + lane) : 0xffffffffu;   // for the next check
       };
       uint32_t tile_it = 0;
-      // Dynamic plan, leader CTA: the tiles of iterations it + 1 and it + 2 sit in registers, the claim for it + 3 is in
-      // flight (its value is first touched one iteration later, when it is published).  Other CTA: reads the ring.
+      // Dynamic plan, leader CTA: the pair's first three tiles are static (pair, pair + P, pair + 2P); from then on the
+      // tiles of iterations it and it + 1 sit in registers and the claim for it + 2 is in flight -- its value is first
+      // touched one iteration after the atomic was issued, so the producer never waits on the L2 round trip.  Other
+      // CTA: reads the ring.
       const bool claimer = dyn && rank == 0;
-      uint32_t tq1 = 0xffffffffu, tq2 = 0xffffffffu, tq3 = 0xffffffffu;     // tiles of it + 1, it + 2, it + 3 (0xffffffff = none)
+      uint32_t tq1 = 0xffffffffu, tq2 = 0xffffffffu;       // tiles of it + 1, it + 2 relative to the running iteration (0xffffffff = none)
+      uint32_t raw_claim = 0;                               // lane 0: result of the pending atomic
+      bool claim_pending = false;
       unsigned int* tile_counter = reinterpret_cast<unsigned int*>(p.tile_sched);
-      auto claim = [&]() -> uint32_t {                                       // every lane gets the same tile
-        uint32_t v = 0;
-        if (lane == 0) v = atomicAdd(tile_counter, 1u);
-        v = __shfl_sync(0xffffffffu, v, 0);
-        const uint64_t t = static_cast<uint64_t>(v) + static_cast<uint64_t>(n_pairs);   // the first n_pairs tiles are static
+      auto static_tile = [&](int j) -> uint32_t {
+        const int64_t t = t_first + static_cast<int64_t>(j) * n_pairs;
+        return t < n_tiles ? static_cast<uint32_t>(t) : 0xffffffffu;
+      };
+      auto claim_issue = [&]() {
+        if (lane == 0) raw_claim = atomicAdd(tile_counter, 1u);
+        claim_pending = true;
+      };
+      auto claim_take = [&]() -> uint32_t {                                  // every lane gets the same tile
+        if (!claim_pending) return 0xffffffffu;
+        claim_pending = false;
+        const uint32_t v = __shfl_sync(0xffffffffu, raw_claim, 0);
+        const uint64_t t = static_cast<uint64_t>(v) + 3ull * static_cast<uint64_t>(n_pairs);
         return t < static_cast<uint64_t>(n_tiles) ? static_cast<uint32_t>(t) : 0xffffffffu;
       };
       auto publish = [&](uint32_t it, uint32_t tile) {
@@ -217,9 +229,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
       unsigned long long peeked = 0;
       auto first_tile = [&]() -> int64_t {
         if (claimer) {
-          tq1 = claim(); tq2 = claim();
+          tq1 = static_tile(1); tq2 = static_tile(2);
           publish(1, tq1); publish(2, tq2);
-          tq3 = claim();
+          if (tq2 != 0xffffffffu) claim_issue();                             // for iteration 3
         } else {
           peeked = tile_peek(1);
         }
@@ -229,9 +241,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_bank, const __grid_constan
         if (!dyn) return tile_get(it, 0ull);
         if (claimer) {
           const uint32_t cur = tq1;
-          publish(it + 2u, tq3);                                            // entries up to it + 2 are now visible
-          tq1 = tq2; tq2 = tq3;
-          tq3 = (cur != 0xffffffffu) ? claim() : 0xffffffffu;               // for it + 3
+          const uint32_t nxt = claim_take();                                // tile of it + 2, claimed one iteration ago
+          publish(it + 2u, nxt);                                            // entries up to it + 2 are now visible
+          tq1 = tq2; tq2 = nxt;
+          if (nxt != 0xffffffffu) claim_issue();                             // for it + 3
           return cur != 0xffffffffu ? static_cast<int64_t>(cur) : n_tiles;
         }
         const int64_t t = tile_get(it, peeked);
