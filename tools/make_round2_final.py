@@ -1,7 +1,9 @@
 """Round-2 final evidence: gpurun_out/r02f_* (tools/gpu_final.sh) -> tracked summaries under profiles/.  Runs here (needs ncu)."""
 import csv, io, json, shutil, subprocess, sys
 SRC, OUT = "gpurun_out", "profiles"
-d = json.loads(open(f"{SRC}/r02f_bench.json").read().strip().split("\n")[-1])
+import os
+BENCH = next(f for f in (f"{SRC}/r02n_bench.json", f"{SRC}/r02f_bench.json") if os.path.exists(f))   # r02n: tools/gpu_full.sh with the final code
+d = json.loads(open(BENCH).read().strip().split("\n")[-1])
 json.dump(d, open(f"{OUT}/r02_bench_n1.json", "w"))
 try:
     d2 = json.loads(open(f"{SRC}/r02_bench_n2.json").read().strip().split("\n")[-1])
@@ -45,7 +47,7 @@ md += ["", "All captured launches:", "", "| kernel | launches | mean us |", "|--
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     md.append(f"| `{k}` | {n} | {t / n:.1f} |")
 scan = [v for k, v in step if k == "scan_tc_kernel"][-1]
-md += ["", f"Same command without ncu (`profiles/r02_bench_n1.json`): {d['ms_per_step']:.3f} ms per step, scan kernel {d['roofline']['kernel_ms']:.3f} ms "
+md += ["", f"The bench line of the final code (`profiles/r02_bench_n1.json`, no profiler, another box of the pool): {d['ms_per_step']:.3f} ms per step, scan kernel {d['roofline']['kernel_ms']:.3f} ms "
        f"({d['roofline']['frac']:.3f} of the measured HBM peak) = {d['roofline']['kernel_ms'] / d['ms_per_step']:.2f} of the step; under ncu the scan's share is {scan / tot:.2f}.",
        "", "Old and new build on ONE box, alternating processes (`tools/gpu_ab_step.py`, `profiles/r02_ab_start_vs_end.txt`; `old` = the library at the",
        "start of this round's second half, commit 2faf7cb): T2T500+T2I0.25 2.17 -> 2.11 ms per step, T2T-500 2.10 -> 2.02 ms, config 1 (1 M fp32 rows)",
