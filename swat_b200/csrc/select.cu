@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(1024) partition_agg_kernel(const JobState st, 
 // with at least k_fetch scores at or above it; pass 2 appends exactly the rows at or above that edge
 // (k_fetch plus about one bin: a superset of the prefix's top k_fetch, which is all the job needs) to
 // a spare survivor list, adds those bins to the global histogram and raises the class threshold to
-// the edge.  The main scan then begins with selective thresholds instead of appending every
+// the edge.  (34 us for 200 classes x 32 K rows; loads batched 16 at a time measured the same, register-cached scores
+// with warp-aggregated atomics 71 us: the plain loops stay.)  The main scan then begins with selective thresholds instead of appending every
 // non-negative score of its first waves.
 __global__ void __launch_bounds__(kSelThreads)
 bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t B, uint32_t row_base, uint32_t first_spare_list) {
@@ -325,19 +326,9 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   for (int i = tid; i < kHistBins; i += kSelThreads) s_h[i] = 0;
   if (tid == 0) s_fill = 0;
   __syncthreads();
-  // 16 independent loads, then their atomics: a plain load -> atomic loop pays one L2 round trip per element (the
-  // compiler keeps the loads behind the atomics), 64 of them over both passes for the usual 32 K-row prefix
-  constexpr int kBatch = 16;
-  for (uint32_t i0 = tid; i0 < B; i0 += kBatch * kSelThreads) {
-    float v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const uint32_t i = i0 + static_cast<uint32_t>(u) * kSelThreads;
-      v[u] = i < B ? sc[i] + 0.0f : -INFINITY;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      if (i0 + static_cast<uint32_t>(u) * kSelThreads < B && v[u] >= st.thr) atomicAdd(&s_h[hist_bin(st, v[u])], 1u);
+  for (uint32_t i = tid; i < B; i += kSelThreads) {
+    const float s = sc[i] + 0.0f;
+    if (s >= st.thr) atomicAdd(&s_h[hist_bin(st, s)], 1u);
   }
   __syncthreads();
   if (tid < 32) {   // warp 0: lane l owns bins 32l .. 32l+31; suffix-scan from the top
@@ -379,23 +370,13 @@ bootstrap_kernel(const JobState st, const float* __restrict__ scores_t, uint32_t
   const int cut = static_cast<int>(s_cut);
   const uint32_t list_id = first_spare_list + static_cast<uint32_t>(c) % (st.n_lists - first_spare_list);
   uint4* dst = st.list + static_cast<size_t>(list_id) * st.list_cap;
-  for (uint32_t i0 = tid; i0 < B; i0 += kBatch * kSelThreads) {
-    float v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const uint32_t i = i0 + static_cast<uint32_t>(u) * kSelThreads;
-      v[u] = i < B ? sc[i] + 0.0f : -INFINITY;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const uint32_t i = i0 + static_cast<uint32_t>(u) * kSelThreads;
-      const float s = v[u];
-      if (i < B && s >= st.thr && hist_bin(st, s) >= cut) {
-        const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
-        const uint64_t key = make_key(s, row_base + i);
-        if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
-        else atomicOr(st.flags, 2u);
-      }
+  for (uint32_t i = tid; i < B; i += kSelThreads) {
+    const float s = sc[i] + 0.0f;
+    if (s >= st.thr && hist_bin(st, s) >= cut) {
+      const uint32_t slot = s_base + atomicAdd(&s_fill, 1u);
+      const uint64_t key = make_key(s, row_base + i);
+      if (slot < st.list_cap) dst[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(c), 0u);
+      else atomicOr(st.flags, 2u);
     }
   }
   for (int b = cut + tid; b < kHistBins; b += kSelThreads)
