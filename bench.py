@@ -397,9 +397,11 @@ def run_ours(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = None
-    if world > 1:
+    all_cpus = os.sched_getaffinity(0)          # restored for the cpu_baseline leg, which uses every host core
+    if True:
         # pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated: the e2e leg streams
-        # 10 GB per rank out of host memory and should not cross the socket interconnect
+        # 10 GB per rank out of host memory and should not cross the socket interconnect (at N = 1 too: the same build
+        # measured 25-49 M rows/s end to end depending on where the scheduler had put the process)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -411,6 +413,7 @@ def run_ours(a, rank, world, local_rank):
                 numa = f"rank pinned to {len(cpus)} CPUs local to GPU {local_rank}"
         except Exception as e:          # affinity is an optimisation only
             numa = f"affinity not set: {type(e).__name__}"
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local_rank)
     if a.overfetch:
@@ -550,6 +553,11 @@ def run_ours(a, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
+        for tid in os.listdir("/proc/self/task"):          # every thread: OpenMP workers created while pinned keep their mask
+            try:
+                os.sched_setaffinity(int(tid), all_cpus)
+            except OSError:
+                pass
         cores = os.cpu_count()
         torch.set_num_threads(cores)
         vec, vec_sample = cpu_vectorised(a)
